@@ -1,0 +1,162 @@
+/* include/roms_b200.h -- C ABI of libroms_b200.so
+ *
+ * Drop-in boundary for the ROMS nonlinear main3d hot path.
+ * Each kernel entry point replaces the `CALL X_tile(...)` line inside the public
+ * wrapper `X(ng,tile)` of the reference; the Fortran side binds these symbols
+ * through ISO_C_BINDING (roms_b200/fortran/roms_b200_mod.F90).
+ *
+ * Model: the host (Fortran) owns the mod_ocean/mod_grid/mod_coupling/mod_mixing/
+ * mod_forces arrays; this library keeps a persistent DEVICE MIRROR of them with
+ * the identical layout (column-major, i fastest, explicit lower bounds
+ * (LBi:UBi,LBj:UBj[,k][,time][,tracer])).  `roms_b200_upload/download` move a
+ * field between `c_loc(array)` and its mirror; the kernel entry points operate
+ * on the mirror only and take the hidden module inputs of the reference
+ * `_tile` routines (time indices, iic, iif, ...) explicitly.
+ *
+ * All functions return 0 on success; non-zero maps to exit_flag=8 on the
+ * Fortran side (mod_scalars.F:548-561).  There is NO CPU fallback: if no CUDA
+ * device is usable, roms_b200_create fails.
+ */
+#ifndef ROMS_B200_H
+#define ROMS_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Application option sets (cpp headers ROMS/Include/upwelling.h, benchmark.h) */
+#define ROMS_B200_APP_UPWELLING 0
+#define ROMS_B200_APP_BENCHMARK 1
+
+/* Per-tile integers: BOUNDS(ng)%X(tile) from ROMS/Include/set_bounds.h:30-74,
+ * array bounds from ROMS/Include/tile.h / Utility/get_bounds.F:193-269, and the
+ * DOMAIN(ng)%*_Edge(tile) flags.  Passed verbatim; never re-derived on device. */
+typedef struct roms_b200_bounds {
+  int Lm, Mm, N, NT, NAT;
+  int LBi, UBi, LBj, UBj;
+  int Istr, Iend, Jstr, Jend;
+  int IstrR, IendR, JstrR, JendR;
+  int IstrU, JstrV;
+  int IstrP, IendP, JstrP, JendP;
+  int IstrT, IendT, JstrT, JendT;
+  int IstrB, IendB, JstrB, JendB;
+  int IstrM, JstrM;
+  int Istrm3, Istrm2, Istrm1, IstrUm2, IstrUm1, Iendp1, Iendp2, Iendp2i, Iendp3;
+  int Jstrm3, Jstrm2, Jstrm1, JstrVm2, JstrVm1, Jendp1, Jendp2, Jendp2i, Jendp3;
+  int Western_Edge, Eastern_Edge, Southern_Edge, Northern_Edge;
+  int EWperiodic, NSperiodic;
+  int NtileI, NtileJ, Itile, Jtile; /* Utility/get_bounds.F:1020-1039 */
+} roms_b200_bounds;
+
+/* Scalars the reference `_tile` routines read from mod_scalars / mod_param. */
+typedef struct roms_b200_params {
+  int app;               /* ROMS_B200_APP_*: selects the cpp option set */
+  double dt, dtfast;     /* dt(ng), dtfast(ng) */
+  int ndtfast, nfast;    /* set_weights.F */
+  double rho0, g;        /* mod_scalars.F:466 ; roms_*.in RHO0 */
+  double gamma2;         /* slipperiness, roms_*.in:466 */
+  double hc;             /* set_scoord.F:176-177 */
+  double R0, T0, S0, Tcoef, Scoef;   /* linear EOS */
+  double Akt_bak[2], Akv_bak;        /* ana_vmix.h */
+  double blk_ZQ, blk_ZT, blk_ZW;     /* bulk_flux.F heights */
+  double dstart;
+} roms_b200_params;
+
+/* Field identifiers of the device mirror.  X(name, kLB, nk, nl, nm):
+ * extents beyond (LBi:UBi,LBj:UBj) are (kLB:kLB+nk-1, 1:nl, 1:nm) with the
+ * symbolic sizes N (levels), Np1 (0:N), NT, NAT resolved at create time. */
+#define ROMS_B200_FIELDS(X) \
+  X(h,1,1,1,1) X(f,1,1,1,1) X(fomn,1,1,1,1) X(pm,1,1,1,1) X(pn,1,1,1,1) \
+  X(om_r,1,1,1,1) X(on_r,1,1,1,1) X(om_u,1,1,1,1) X(on_u,1,1,1,1) X(om_v,1,1,1,1) X(on_v,1,1,1,1) \
+  X(om_p,1,1,1,1) X(on_p,1,1,1,1) X(pmon_r,1,1,1,1) X(pnom_r,1,1,1,1) X(pmon_u,1,1,1,1) X(pnom_u,1,1,1,1) \
+  X(pmon_v,1,1,1,1) X(pnom_v,1,1,1,1) X(pmon_p,1,1,1,1) X(pnom_p,1,1,1,1) X(omn,1,1,1,1) \
+  X(dndx,1,1,1,1) X(dmde,1,1,1,1) X(lonr,1,1,1,1) X(latr,1,1,1,1) X(xr,1,1,1,1) X(yr,1,1,1,1) X(angler,1,1,1,1) \
+  X(rdrag,1,1,1,1) X(rdrag2,1,1,1,1) X(visc2_r,1,1,1,1) X(visc2_p,1,1,1,1) X(hsbl,1,1,1,1) X(Jwtype,1,1,1,1) \
+  X(Zt_avg1,1,1,1,1) X(DU_avg1,1,1,1,1) X(DU_avg2,1,1,1,1) X(DV_avg1,1,1,1,1) X(DV_avg2,1,1,1,1) \
+  X(rufrc,1,1,1,1) X(rvfrc,1,1,1,1) X(rhoA,1,1,1,1) X(rhoS,1,1,1,1) X(alpha,1,1,1,1) X(beta,1,1,1,1) \
+  X(sustr,1,1,1,1) X(svstr,1,1,1,1) X(bustr,1,1,1,1) X(bvstr,1,1,1,1) X(srflx,1,1,1,1) \
+  X(Uwind,1,1,1,1) X(Vwind,1,1,1,1) X(Tair,1,1,1,1) X(Pair,1,1,1,1) X(Hair,1,1,1,1) X(cloud,1,1,1,1) X(rain,1,1,1,1) \
+  X(lrflx,1,1,1,1) X(lhflx,1,1,1,1) X(shflx,1,1,1,1) \
+  X(Hz,1,N,1,1) X(z_r,1,N,1,1) X(z_w,0,Np1,1,1) X(Huon,1,N,1,1) X(Hvom,1,N,1,1) \
+  X(diff2,1,NT,1,1) X(Akv,0,Np1,1,1) X(bvf,0,Np1,1,1) X(Akt,0,Np1,NAT,1) X(ghats,0,Np1,NAT,1) \
+  X(zeta,1,3,1,1) X(ubar,1,3,1,1) X(vbar,1,3,1,1) X(rzeta,1,2,1,1) X(rubar,1,2,1,1) X(rvbar,1,2,1,1) \
+  X(rho,1,N,1,1) X(pden,1,N,1,1) X(W,0,Np1,1,1) \
+  X(u,1,N,2,1) X(v,1,N,2,1) X(ru,0,Np1,2,1) X(rv,0,Np1,2,1) X(t,1,N,3,NT) \
+  X(stflx,1,NT,1,1) X(btflx,1,NT,1,1) X(stflux,1,NT,1,1) X(btflux,1,NT,1,1)
+
+enum roms_b200_field {
+#define X(name, kLB, nk, nl, nm) ROMS_B200_F_##name,
+  ROMS_B200_FIELDS(X)
+#undef X
+  ROMS_B200_NFIELDS
+};
+
+typedef struct roms_b200_ctx roms_b200_ctx;
+
+/* Host helper: fill roms_b200_bounds exactly as Utility/get_bounds.F does for `tile` of an
+ * NtileI x NtileJ partition.  distributed!=0: MPI-style tile+halo array bounds (get_bounds.F:193-212),
+ * else whole-domain bounds of the serial build (:258-269).  A Fortran host passes BOUNDS(ng) instead. */
+int roms_b200_tile_bounds(int Lm, int Mm, int N, int NT, int NAT, int NtileI, int NtileJ, int tile,
+                          int EWperiodic, int NSperiodic, int distributed, roms_b200_bounds* out);
+
+/* ---- lifetime (replaces nothing in the reference; called from ROMS_initialize
+ *      after ROMS_allocate_arrays, Drivers/nl_roms.h:180, and from ROMS_finalize) */
+int roms_b200_create(const roms_b200_bounds* b, const roms_b200_params* p, int device, roms_b200_ctx** out);
+int roms_b200_destroy(roms_b200_ctx* ctx);
+/* S-coordinate vectors sc_r,Cs_r(1:N) and sc_w,Cs_w(0:N): SCALARS(ng)%... (Utility/set_scoord.F) */
+int roms_b200_set_scoord(roms_b200_ctx* ctx, const double* sc_r, const double* Cs_r, const double* sc_w, const double* Cs_w);
+/* weight(1,1:nfast+1,ng), weight(2,...) (Utility/set_weights.F); arrays are 1-based: w[0] unused, length >= nfast+2 */
+int roms_b200_set_weights(roms_b200_ctx* ctx, int nfast, const double* weight1, const double* weight2);
+
+/* ---- host <-> device mirror (c_loc of the module array) */
+int roms_b200_field_id(const char* name);
+long roms_b200_field_size(const roms_b200_ctx* ctx, int field);     /* doubles */
+int roms_b200_upload(roms_b200_ctx* ctx, int field, const double* host);
+int roms_b200_download(roms_b200_ctx* ctx, int field, double* host);
+void* roms_b200_device_ptr(roms_b200_ctx* ctx, int field);
+int roms_b200_sync(roms_b200_ctx* ctx);
+
+/* ---- per-tile kernels: each replaces `CALL X_tile(ng,tile,...)` in the wrapper `X(ng,tile)` */
+int roms_b200_set_massflux(roms_b200_ctx* ctx, int nrhs);                      /* set_massflux.F:73   */
+int roms_b200_rho_eos(roms_b200_ctx* ctx, int nrhs);                           /* rho_eos.F:111,576  */
+int roms_b200_omega(roms_b200_ctx* ctx);                                       /* omega.F:96          */
+int roms_b200_set_zeta(roms_b200_ctx* ctx);                                    /* set_zeta.F:59       */
+int roms_b200_set_depth(roms_b200_ctx* ctx);                                   /* set_depth.F:76      */
+int roms_b200_bulk_flux(roms_b200_ctx* ctx, int nrhs);                         /* bulk_flux.F:111     */
+int roms_b200_set_vbc(roms_b200_ctx* ctx, int nrhs);                           /* set_vbc.F           */
+int roms_b200_ana_vmix(roms_b200_ctx* ctx);                                    /* ana_vmix.h          */
+int roms_b200_lmd_vmix(roms_b200_ctx* ctx, int nstp);                          /* lmd_vmix.F:33       */
+int roms_b200_pre_step3d(roms_b200_ctx* ctx, int nrhs, int nstp, int nnew, int iic, int ntfirst);   /* pre_step3d.F:126 */
+int roms_b200_prsgrd(roms_b200_ctx* ctx, int nrhs);                            /* prsgrd32.h:109      */
+int roms_b200_t3dmix2(roms_b200_ctx* ctx, int nrhs, int nstp, int nnew);       /* t3dmix2_s.h / _geo.h */
+int roms_b200_rhs3d_tile(roms_b200_ctx* ctx, int nrhs);                        /* rhs3d.F:196         */
+int roms_b200_uv3dmix2(roms_b200_ctx* ctx, int nrhs, int nnew);                /* uv3dmix2_s.h        */
+/* rhs3d wrapper: pre_step3d -> prsgrd -> t3dmix2 -> rhs3d_tile -> uv3dmix2 (rhs3d.F:80-181) */
+int roms_b200_rhs3d(roms_b200_ctx* ctx, int nrhs, int nstp, int nnew, int iic, int ntfirst);
+int roms_b200_step2d(roms_b200_ctx* ctx, int krhs, int kstp, int knew, int nstp, int nnew,
+                     int iif, int predictor_2d_step, int iic, int ntfirst);    /* step2d_LF_AM3.h:163 */
+int roms_b200_step3d_uv(roms_b200_ctx* ctx, int nrhs, int nstp, int nnew, int iic, int ntfirst);   /* step3d_uv.F:134 */
+int roms_b200_step3d_t(roms_b200_ctx* ctx, int nrhs, int nstp, int nnew);      /* step3d_t.F:120      */
+/* diag_tile reductions: out[0]=avgke, out[1]=avgpe, out[2]=volume (diag.F:225-322) */
+int roms_b200_diag(roms_b200_ctx* ctx, int nstp, double* out3);
+
+/* ---- whole fast loop and whole baroclinic step on the device mirror.
+ * roms_b200_step2d_loop runs main3d.F:810-918 (2*nfast+1 step2d calls) and
+ * updates *indx1 as the reference does.  roms_b200_main3d runs nsteps of
+ * main3d.F:216-1148 with forcing taken from the mirror (upload it beforehand,
+ * or let analytic_forcing!=0 evaluate ana_* on the device each step). */
+int roms_b200_step2d_loop(roms_b200_ctx* ctx, int nstp, int nnew, int iic, int ntfirst, int* indx1);
+int roms_b200_main3d(roms_b200_ctx* ctx, int nsteps, int analytic_forcing, int with_diag);
+/* stepping state of the mirror-resident loop: iic, ntfirst, nstp, nnew, nrhs, indx1 ; time (s) */
+int roms_b200_get_stepping(const roms_b200_ctx* ctx, int* out6, double* time);
+int roms_b200_set_stepping(roms_b200_ctx* ctx, const int* in6, double time);
+/* analytic forcing on the device: set_data.F (ana_* branches) */
+int roms_b200_set_data(roms_b200_ctx* ctx, double tdays);
+/* number of kernel launches issued by this context so far */
+long roms_b200_launch_count(const roms_b200_ctx* ctx);
+/* average device time (ms) of the last `roms_b200_time_kernel` call */
+int roms_b200_time_step3d_t(roms_b200_ctx* ctx, int nrhs, int nstp, int nnew, int reps, float* ms_avg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROMS_B200_H */

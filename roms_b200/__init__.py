@@ -1,0 +1,8 @@
+"""roms_b200 -- B200-native (sm_100a) kernels for the ROMS nonlinear main3d hot path.
+
+The product is the C-ABI shared library ``libroms_b200.so`` (include/roms_b200.h);
+this package is the thin host-side binding used by tests, bench.py and the
+Python mirror of the ROMS_initialize / ROMS_run / ROMS_finalize driver surface.
+"""
+from .lib import (Lib, Bounds, Params, Context, FIELD_NAMES, APP_UPWELLING, APP_BENCHMARK,  # noqa: F401
+                  tile_bounds, library_path)

@@ -1,0 +1,349 @@
+// roms_b200/csrc/k_grid.cu -- depth / mass-flux / omega / EOS / vertical BC kernels.
+// One thread per water column (i fastest -> coalesced rows), marching k.
+// Reference routines (file:line) are cited at each kernel; arithmetic per point
+// follows the reference operation order so results are bit-identical to a
+// non-fast-math build (compiled with -fmad=false).
+#include "common.cuh"
+
+// ---- set_depth_tile, Nonlinear/set_depth.F:192-245 (Vtransform=2) -----------
+__global__ void set_depth_kernel(const Dev D, Box bx) {
+  IJ_FROM_BOX(bx);
+  const int N = D.b.N; const double hc = D.p.hc;
+  V2 h = v2(D, FID(h)), Zt = v2(D, FID(Zt_avg1));
+  V3 z_w = v3(D, FID(z_w)), z_r = v3(D, FID(z_r)), Hz = v3(D, FID(Hz));
+  const double hwater = h(i, j), zt = Zt(i, j);
+  const double hinv = 1.0 / (hc + hwater);
+  double zw_prev = -hwater;
+  st(D, z_w, i, j, 0, zw_prev);
+  for (int k = 1; k <= N; ++k) {
+    double cff_r = hc * D.sc_r[k], cff_w = hc * D.sc_w[k];
+    double cff2_r = (cff_r + D.Cs_r[k] * hwater) * hinv;
+    double cff2_w = (cff_w + D.Cs_w[k] * hwater) * hinv;
+    double zw = zt + (zt + hwater) * cff2_w;
+    double zr = zt + (zt + hwater) * cff2_r;
+    st(D, z_w, i, j, k, zw);
+    st(D, z_r, i, j, k, zr);
+    st(D, Hz, i, j, k, zw - zw_prev);
+    zw_prev = zw;
+  }
+}
+int k_set_depth(roms_b200_ctx* c) {
+  const roms_b200_bounds& b = c->D.b;
+  Box bx{b.IstrT, b.IendT, b.JstrT, b.JendT}; dim3 blk(64, 4);
+  set_depth_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx); c->launches++;
+  return 0;
+}
+
+// ---- set_massflux_tile, Nonlinear/set_massflux.F:140-163 -------------------
+__global__ void set_massflux_kernel(const Dev D, Box bx, int nrhs) {
+  IJ_FROM_BOX(bx);
+  const int k = 1 + blockIdx.z;
+  const roms_b200_bounds& b = D.b;
+  V3 Hz = v3(D, FID(Hz)), Huon = v3(D, FID(Huon)), Hvom = v3(D, FID(Hvom));
+  V3 u = v3l(D, FID(u), nrhs), v = v3l(D, FID(v), nrhs);
+  V2 on_u = v2(D, FID(on_u)), om_v = v2(D, FID(om_v));
+  if (i >= b.IstrP && i <= b.IendT && j >= b.JstrT && j <= b.JendT)
+    st(D, Huon, i, j, k, 0.5 * (Hz(i, j, k) + Hz(i - 1, j, k)) * u(i, j, k) * on_u(i, j));
+  if (i >= b.IstrT && i <= b.IendT && j >= b.JstrP && j <= b.JendT)
+    st(D, Hvom, i, j, k, 0.5 * (Hz(i, j, k) + Hz(i, j - 1, k)) * v(i, j, k) * om_v(i, j));
+}
+int k_set_massflux(roms_b200_ctx* c, int nrhs) {
+  const roms_b200_bounds& b = c->D.b;
+  Box bx{b.IstrT, b.IendT, b.JstrT, b.JendT}; dim3 blk(128, 2); dim3 g = grid2(bx, blk); g.z = b.N;
+  set_massflux_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs); c->launches++;
+  return 0;
+}
+
+// ---- omega_tile, Nonlinear/omega.F:215-355 + bc_w3d (bc_3d.F:588-723) --------
+__global__ void omega_kernel(const Dev D, Box bx) {
+  IJ_FROM_BOX(bx);
+  const int N = D.b.N; const roms_b200_bounds& b = D.b;
+  V3 W = v3(D, FID(W)), Huon = v3(D, FID(Huon)), Hvom = v3(D, FID(Hvom)), z_w = v3(D, FID(z_w));
+  const bool south = b.Southern_Edge && j == b.Jstr, north = b.Northern_Edge && j == b.Jend;
+  double w[RB_MAXN + 1];
+  w[0] = 0.0;
+  for (int k = 1; k <= N; ++k)
+    w[k] = w[k - 1] - (Huon(i + 1, j, k) - Huon(i, j, k) + Hvom(i, j + 1, k) - Hvom(i, j, k));
+  const double zw0 = z_w(i, j, 0);
+  const double wrk = w[N] / (z_w(i, j, N) - zw0);
+  for (int k = N - 1; k >= 1; --k) w[k] = w[k] - wrk * (z_w(i, j, k) - zw0);
+  w[N] = 0.0;
+  for (int k = 0; k <= N; ++k) {
+    st(D, W, i, j, k, w[k]);
+    if (south) st(D, W, i, j - 1, k, w[k]);
+    if (north) st(D, W, i, j + 1, k, w[k]);
+  }
+}
+int k_omega(roms_b200_ctx* c) {
+  const roms_b200_bounds& b = c->D.b;
+  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(64, 2);
+  omega_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx); c->launches++;
+  return 0;
+}
+
+// ---- set_zeta_tile, Nonlinear/set_zeta.F:101-118 -----------------------------
+__global__ void set_zeta_kernel(const Dev D, Box bx) {
+  IJ_FROM_BOX(bx);
+  V2 Zt = v2(D, FID(Zt_avg1)), z1 = v2l(D, FID(zeta), 1), z2 = v2l(D, FID(zeta), 2);
+  const double zt = Zt(i, j);
+  st(D, z1, i, j, zt); st(D, z2, i, j, zt);
+}
+int k_set_zeta(roms_b200_ctx* c) {
+  const roms_b200_bounds& b = c->D.b;
+  Box bx{b.IstrR, b.IendR, b.JstrR, b.JendR}; dim3 blk(128, 2);
+  set_zeta_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx); c->launches++;
+  return 0;
+}
+
+// ---- rho_eos_tile -----------------------------------------------------------
+// linear: Nonlinear/rho_eos.F:688-740 ; nonlinear (UNESCO / Jackett-McDougall):
+// rho_eos.F:293-440 with coefficients of Modules/mod_eoscoef.F:24-64.
+#define A00 (+1.909256e+04)
+#define A01 (+2.098925e+02)
+#define A02 (-3.041638e+00)
+#define A03 (-1.852732e-03)
+#define A04 (-1.361629e-05)
+#define B00 (+1.044077e+02)
+#define B01 (-6.500517e+00)
+#define B02 (+1.553190e-01)
+#define B03 (+2.326469e-04)
+#define D00 (-5.587545e+00)
+#define D01 (+7.390729e-01)
+#define D02 (-1.909078e-02)
+#define E00 (+4.721788e-01)
+#define E01 (+1.028859e-02)
+#define E02 (-2.512549e-04)
+#define E03 (-5.939910e-07)
+#define F00 (-1.571896e-02)
+#define F01 (-2.598241e-04)
+#define F02 (+7.267926e-06)
+#define G00 (+2.042967e-03)
+#define G01 (+1.045941e-05)
+#define G02 (-5.782165e-10)
+#define G03 (+1.296821e-07)
+#define H00 (-2.595994e-07)
+#define H01 (-1.248266e-09)
+#define H02 (-3.508914e-09)
+#define Q00 (+9.99842594e+02)
+#define Q01 (+6.793952e-02)
+#define Q02 (-9.095290e-03)
+#define Q03 (+1.001685e-04)
+#define Q04 (-1.120083e-06)
+#define Q05 (+6.536332e-09)
+#define U00 (+8.24493e-01)
+#define U01 (-4.08990e-03)
+#define U02 (+7.64380e-05)
+#define U03 (-8.24670e-07)
+#define U04 (+5.38750e-09)
+#define V00 (-5.72466e-03)
+#define V01 (+1.02270e-04)
+#define V02 (-1.65460e-06)
+#define W00 (+4.8314e-04)
+
+__global__ void rho_eos_kernel(const Dev D, Box bx, int nrhs) {
+  IJ_FROM_BOX(bx);
+  const int N = D.b.N; const double g = D.p.g, rho0 = D.p.rho0;
+  V3 Hz = v3(D, FID(Hz)), z_r = v3(D, FID(z_r)), z_w = v3(D, FID(z_w)), rho = v3(D, FID(rho)), pden = v3(D, FID(pden));
+  V3 T = v3l(D, FID(t), nrhs, 1), S = v3l(D, FID(t), nrhs, 2);
+  V2 rhoA = v2(D, FID(rhoA)), rhoS = v2(D, FID(rhoS));
+  double den[RB_MAXN + 1];
+  if (D.p.app == ROMS_B200_APP_UPWELLING) {
+    const double R0 = D.p.R0;
+    for (int k = 1; k <= N; ++k) {
+      double r = R0 - R0 * D.p.Tcoef * (T(i, j, k) - D.p.T0);
+      r = r + R0 * D.p.Scoef * (S(i, j, k) - D.p.S0);
+      r = r - 1000.0;
+      den[k] = r;
+      st(D, rho, i, j, k, r); st(D, pden, i, j, k, r);
+    }
+  } else {
+    V3 bvf = v3(D, FID(bvf)); V2 alpha = v2(D, FID(alpha)), beta = v2(D, FID(beta));
+    double p_den1 = 0, p_b0 = 0, p_b1 = 0, p_b2 = 0;   // level k-1
+    for (int k = 1; k <= N; ++k) {
+      const double Tt = fmax(-2.0, T(i, j, k)), Ts = fmax(0.0, S(i, j, k));
+      const double sqrtTs = sqrt(Ts), Tp = z_r(i, j, k), Tpr10 = 0.1 * Tp;
+      const double C0 = Q00 + Tt * (Q01 + Tt * (Q02 + Tt * (Q03 + Tt * (Q04 + Tt * Q05))));
+      const double C1 = U00 + Tt * (U01 + Tt * (U02 + Tt * (U03 + Tt * U04)));
+      const double C2 = V00 + Tt * (V01 + Tt * V02);
+      const double den1 = C0 + Ts * (C1 + sqrtTs * C2 + Ts * W00);
+      const double C3 = A00 + Tt * (A01 + Tt * (A02 + Tt * (A03 + Tt * A04)));
+      const double C4 = B00 + Tt * (B01 + Tt * (B02 + Tt * B03));
+      const double C5 = D00 + Tt * (D01 + Tt * D02);
+      const double C6 = E00 + Tt * (E01 + Tt * (E02 + Tt * E03));
+      const double C7 = F00 + Tt * (F01 + Tt * F02);
+      const double C8 = G01 + Tt * (G02 + Tt * G03);
+      const double C9 = H00 + Tt * (H01 + Tt * H02);
+      const double bulk0 = C3 + Ts * (C4 + sqrtTs * C5);
+      const double bulk1 = C6 + Ts * (C7 + sqrtTs * G00);
+      const double bulk2 = C8 + Ts * C9;
+      const double bulk = bulk0 - Tp * (bulk1 - Tp * bulk2);
+      const double cff = 1.0 / (bulk + Tpr10);
+      double dn = den1 * bulk * cff;
+      dn = dn - 1000.0;
+      den[k] = dn;
+      st(D, rho, i, j, k, dn); st(D, pden, i, j, k, (den1 - 1000.0));
+      if (k > 1) {                     // bvf at interface k-1 (rho_eos.F:402-424)
+        const double zw = z_w(i, j, k - 1);
+        const double bulk_up = bulk0 - zw * (bulk1 - bulk2 * zw);
+        const double bulk_dn = p_b0 - zw * (p_b1 - p_b2 * zw);
+        const double cff1 = 1.0 / (bulk_up + 0.1 * zw), cff2 = 1.0 / (bulk_dn + 0.1 * zw);
+        const double den_up = cff1 * (den1 * bulk_up), den_dn = cff2 * (p_den1 * bulk_dn);
+        st(D, bvf, i, j, k - 1, -g * (den_up - den_dn) / (0.5 * (den_up + den_dn) * (z_r(i, j, k) - z_r(i, j, k - 1))));
+      }
+      p_den1 = den1; p_b0 = bulk0; p_b1 = bulk1; p_b2 = bulk2;
+      if (k == N) {                    // thermal expansion / saline contraction at the surface (:426-470)
+        const double dC0 = Q01 + Tt * (2.0 * Q02 + Tt * (3.0 * Q03 + Tt * (4.0 * Q04 + Tt * 5.0 * Q05)));
+        const double dC1 = U01 + Tt * (2.0 * U02 + Tt * (3.0 * U03 + Tt * 4.0 * U04));
+        const double dC2 = V01 + Tt * 2.0 * V02;
+        const double Dden1DS = C1 + 1.5 * C2 * sqrtTs + 2.0 * W00 * Ts;
+        const double Dden1DT = dC0 + Ts * (dC1 + sqrtTs * dC2);
+        const double dC3 = A01 + Tt * (2.0 * A02 + Tt * (3.0 * A03 + Tt * 4.0 * A04));
+        const double dC4 = B01 + Tt * (2.0 * B02 + Tt * 3.0 * B03);
+        const double dC5 = D01 + Tt * 2.0 * D02;
+        const double dC6 = E01 + Tt * (2.0 * E02 + Tt * 3.0 * E03);
+        const double dC7 = F01 + Tt * 2.0 * F02;
+        const double dC8 = G02 + Tt * 2.0 * G03;
+        const double dC9 = H01 + Tt * 2.0 * H02;
+        const double DbulkDS = C4 + sqrtTs * 1.5 * C5 - Tp * (C7 + sqrtTs * 1.5 * G00 - Tp * C9);
+        const double DbulkDT = dC3 + Ts * (dC4 + sqrtTs * dC5) - Tp * (dC6 + Ts * dC7 - Tp * (dC8 + Ts * dC9));
+        const double c0 = bulk + Tpr10, c1 = Tpr10 * den1, c2 = bulk * c0;
+        const double wrk = (dn + 1000.0) * c0 * c0;
+        const double Tcof = -(DbulkDT * c1 + Dden1DT * c2);
+        const double Scof = (DbulkDS * c1 + Dden1DS * c2);
+        const double ci = 1.0 / wrk;
+        st(D, alpha, i, j, ci * Tcof); st(D, beta, i, j, ci * Scof);
+      }
+    }
+    st(D, bvf, i, j, 0, 0.0); st(D, bvf, i, j, N, 0.0);
+  }
+  // vertical averages for the barotropic pressure gradient (rho_eos.F:370-387 / :702-718)
+  double cff1 = den[N] * Hz(i, j, N);
+  double rS = 0.5 * cff1 * Hz(i, j, N), rA = cff1;
+  for (int k = N - 1; k >= 1; --k) {
+    const double hz = Hz(i, j, k);
+    cff1 = den[k] * hz;
+    rS = rS + hz * (rA + 0.5 * cff1);
+    rA = rA + cff1;
+  }
+  const double cff2 = 1.0 / rho0;
+  cff1 = 1.0 / (z_w(i, j, N) - z_w(i, j, 0));
+  st(D, rhoA, i, j, cff2 * cff1 * rA);
+  st(D, rhoS, i, j, 2.0 * cff1 * cff1 * cff2 * rS);
+}
+int k_rho_eos(roms_b200_ctx* c, int nrhs) {
+  const roms_b200_bounds& b = c->D.b;
+  Box bx{b.IstrT, b.IendT, b.JstrT, b.JendT}; dim3 blk(64, 2);
+  rho_eos_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx, nrhs); c->launches++;
+  return 0;
+}
+
+// ---- set_vbc_tile, Nonlinear/set_vbc.F:620-720 + bc_u2d/bc_v2d (bc_2d.F) ------
+__global__ void set_vbc_kernel(const Dev D, Box bx, int nrhs) {
+  IJ_FROM_BOX(bx);
+  const roms_b200_bounds& b = D.b; const int N = b.N;
+  V3 u = v3l(D, FID(u), nrhs), v = v3l(D, FID(v), nrhs), S = v3l(D, FID(t), nrhs, 2);
+  if (i >= b.IstrR && i <= b.IendR && j >= b.JstrR && j <= b.JendR) {
+    V2 st1 = v2l(D, FID(stflx), 1), bt1 = v2l(D, FID(btflx), 1), st2 = v2l(D, FID(stflx), 2), bt2 = v2l(D, FID(btflx), 2);
+    V2 sx1 = v2l(D, FID(stflux), 1), bx1 = v2l(D, FID(btflux), 1), sx2 = v2l(D, FID(stflux), 2);
+    st1(i, j) = sx1(i, j); bt1(i, j) = bx1(i, j);
+    const double EmP = sx2(i, j);
+    st2(i, j) = EmP * S(i, j, N);
+    bt2(i, j) = bt2(i, j) * S(i, j, 1);
+  }
+  V2 bustr = v2(D, FID(bustr)), bvstr = v2(D, FID(bvstr));
+  const bool quad = (D.p.app == ROMS_B200_APP_BENCHMARK);
+  if (i >= b.IstrU && i <= b.Iend && j >= b.Jstr && j <= b.Jend) {
+    double val;
+    if (quad) {
+      V2 rd = v2(D, FID(rdrag2));
+      const double cff1 = 0.25 * (v(i, j, 1) + v(i, j + 1, 1) + v(i - 1, j, 1) + v(i - 1, j + 1, 1));
+      const double cff2 = sqrt(u(i, j, 1) * u(i, j, 1) + cff1 * cff1);
+      val = 0.5 * (rd(i - 1, j) + rd(i, j)) * u(i, j, 1) * cff2;
+    } else {
+      V2 rd = v2(D, FID(rdrag));
+      val = 0.5 * (rd(i - 1, j) + rd(i, j)) * u(i, j, 1);
+    }
+    st(D, bustr, i, j, val);
+    if (b.Southern_Edge && j == b.Jstr) st(D, bustr, i, j - 1, D.p.gamma2 * val);
+    if (b.Northern_Edge && j == b.Jend) st(D, bustr, i, j + 1, D.p.gamma2 * val);
+  }
+  if (i >= b.Istr && i <= b.Iend && j >= b.JstrV && j <= b.Jend) {
+    double val;
+    if (quad) {
+      V2 rd = v2(D, FID(rdrag2));
+      const double cff1 = 0.25 * (u(i, j, 1) + u(i + 1, j, 1) + u(i, j - 1, 1) + u(i + 1, j - 1, 1));
+      const double cff2 = sqrt(cff1 * cff1 + v(i, j, 1) * v(i, j, 1));
+      val = 0.5 * (rd(i, j - 1) + rd(i, j)) * v(i, j, 1) * cff2;
+    } else {
+      V2 rd = v2(D, FID(rdrag));
+      val = 0.5 * (rd(i, j - 1) + rd(i, j)) * v(i, j, 1);
+    }
+    st(D, bvstr, i, j, val);
+  }
+  if (i >= b.Istr && i <= b.Iend) {                // bc_v2d: closed walls
+    if (b.Southern_Edge && j == b.Jstr) st(D, bvstr, i, b.Jstr, 0.0);
+    if (b.Northern_Edge && j == b.Jend) st(D, bvstr, i, b.Jend + 1, 0.0);
+  }
+}
+int k_set_vbc(roms_b200_ctx* c, int nrhs) {
+  const roms_b200_bounds& b = c->D.b;
+  Box bx{b.IstrR, b.IendR, b.JstrR, b.JendR}; dim3 blk(128, 2);
+  set_vbc_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx, nrhs); c->launches++;
+  return 0;
+}
+
+// ---- ana_vmix_tile, Functionals/ana_vmix.h:200-206,327-337 -------------------
+__global__ void ana_vmix_kernel(const Dev D, Box bx) {
+  IJ_FROM_BOX(bx);
+  const int N = D.b.N;
+  V3 Akv = v3(D, FID(Akv)), z_w = v3(D, FID(z_w)), Akt1 = v3l(D, FID(Akt), 1), Akt2 = v3l(D, FID(Akt), 2);
+  for (int k = 1; k <= N - 1; ++k) {
+    st(D, Akv, i, j, k, 2.0e-03 + 8.0e-03 * exp(z_w(i, j, k) / 150.0));
+    st(D, Akt1, i, j, k, D.p.Akt_bak[0]); st(D, Akt2, i, j, k, D.p.Akt_bak[1]);
+  }
+}
+int k_ana_vmix(roms_b200_ctx* c) {
+  const roms_b200_bounds& b = c->D.b;
+  Box bx{b.IstrT, b.IendT, b.JstrT, b.JendT}; dim3 blk(64, 4);
+  ana_vmix_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx); c->launches++;
+  return 0;
+}
+
+// ---- diag_tile reductions, Nonlinear/diag.F:225-322 --------------------------
+// One block per j-row strip; deterministic two-stage sum (block partials, then a
+// fixed-order host sum), so results are reproducible run to run.
+__global__ void diag_kernel(const Dev D, int nstp, double* __restrict__ partial) {
+  const roms_b200_bounds& b = D.b; const int N = b.N; const double g = D.p.g;
+  V3 Hz = v3(D, FID(Hz)), z_w = v3(D, FID(z_w)), z_r = v3(D, FID(z_r)), rho = v3(D, FID(rho));
+  V3 u = v3l(D, FID(u), nstp), v = v3l(D, FID(v), nstp); V2 omn = v2(D, FID(omn));
+  const int j = b.Jstr + blockIdx.x;
+  double ke = 0.0, pe = 0.0, vol = 0.0;
+  for (int i = b.Istr + threadIdx.x; i <= b.Iend; i += blockDim.x) {
+    double ke2 = 0.0, pe2 = 0.5 * g * z_w(i, j, N) * z_w(i, j, N);
+    const double cff = g / D.p.rho0;
+    for (int k = N; k >= 1; --k) {
+      ke2 = ke2 + Hz(i, j, k) * 0.25 * (u(i, j, k) * u(i, j, k) + u(i + 1, j, k) * u(i + 1, j, k) + v(i, j, k) * v(i, j, k) + v(i, j + 1, k) * v(i, j + 1, k));
+      pe2 = pe2 + cff * Hz(i, j, k) * (rho(i, j, k) + 1000.0) * (z_r(i, j, k) - z_w(i, j, 0));
+    }
+    vol += omn(i, j) * (z_w(i, j, N) - z_w(i, j, 0));
+    ke += omn(i, j) * ke2; pe += omn(i, j) * pe2;
+  }
+  __shared__ double s[3][256];
+  s[0][threadIdx.x] = ke; s[1][threadIdx.x] = pe; s[2][threadIdx.x] = vol;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) for (int q = 0; q < 3; ++q) s[q][threadIdx.x] += s[q][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) for (int q = 0; q < 3; ++q) partial[3 * blockIdx.x + q] = s[q][0];
+}
+int k_diag(roms_b200_ctx* c, int nstp, double* out3) {
+  const roms_b200_bounds& b = c->D.b; const int nb = b.Jend - b.Jstr + 1;
+  diag_kernel<<<nb, 256, 0, c->stream>>>(c->D, nstp, c->D.red); c->launches++;
+  CUDA_OK(cudaMemcpyAsync(c->h_red, c->D.red, sizeof(double) * 3 * nb, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  double ke = 0, pe = 0, vol = 0;
+  for (int q = 0; q < nb; ++q) { ke += c->h_red[3 * q]; pe += c->h_red[3 * q + 1]; vol += c->h_red[3 * q + 2]; }
+  out3[0] = ke / vol; out3[1] = pe / vol; out3[2] = vol;
+  return 0;
+}

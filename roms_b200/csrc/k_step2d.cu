@@ -1,0 +1,243 @@
+// roms_b200/csrc/k_step2d.cu -- one barotropic sub-step (LF predictor or AM3
+// corrector) of step2d_tile, Nonlinear/step2d_LF_AM3.h:606-3056, as ONE kernel.
+//
+// The reference stages ~20 tile-sized scratch planes (Drhs, DUon, DVom, zeta_new,
+// gzeta..., UFx, UFe, ...) between loop nests.  Here every thread owns one (i,j)
+// and re-evaluates the staggered transports / provisional free surface it needs
+// from the time levels it only READS (krhs,kstp), so the whole sub-step is a
+// single launch with no inter-block dependency: the 2*nfast+1 launches of a
+// baroclinic step are captured in a CUDA graph (roms_b200.cu).  All 2-D state of
+// a benchmark-size tile (~50 planes x 277 KB) stays resident in the 126 MB L2.
+#include "common.cuh"
+
+struct S2 {
+  V2 zk, zs, ub, vb;                      // zeta(:,:,krhs), zeta(:,:,kstp), ubar/vbar(:,:,krhs)
+  V2 h, pm, pn, on_u, om_v, rhoA, rhoS, rzs, rzp;   // rzeta(:,:,kstp), rzeta(:,:,ptsk)
+  double fac, dtfast; int mode;           // mode: 0 iif==1, 1 predictor, 2 corrector
+  int S, N, Jstr, Jend;
+};
+__device__ __forceinline__ double Drhs(const S2& s, int i, int j) { return s.zk(i, j) + s.h(i, j); }
+__device__ __forceinline__ double DUon(const S2& s, int i, int j) {
+  const double cff = 0.5 * s.on_u(i, j); const double cff1 = cff * (Drhs(s, i, j) + Drhs(s, i - 1, j));
+  return s.ub(i, j) * cff1;
+}
+__device__ __forceinline__ double DVom(const S2& s, int i, int j) {
+  const double cff = 0.5 * s.om_v(i, j); const double cff1 = cff * (Drhs(s, i, j) + Drhs(s, i, j - 1));
+  return s.vb(i, j) * cff1;
+}
+struct Zst { double rhs_zeta, zn, Dnew, zwrk, gzeta, gzeta2, gzetaSA; };
+// step2d_LF_AM3.h:899-980
+__device__ __forceinline__ Zst zstate(const S2& s, int i, int j) {
+  Zst z;
+  const double div = (DUon(s, i, j) - DUon(s, i + 1, j)) + (DVom(s, i, j) - DVom(s, i, j + 1));
+  const double pmn = s.pm(i, j) * s.pn(i, j);
+  z.rhs_zeta = div;
+  if (s.mode == 0) {
+    z.zn = s.zs(i, j) + pmn * s.dtfast * div;
+    z.zwrk = 0.5 * (s.zs(i, j) + z.zn);
+  } else if (s.mode == 1) {
+    const double cff1 = 2.0 * s.dtfast, cff4 = 4.0 / 25.0, cff5 = 1.0 - 2.0 * cff4;
+    z.zn = s.zs(i, j) + pmn * cff1 * div;
+    z.zwrk = cff5 * s.zk(i, j) + cff4 * (s.zs(i, j) + z.zn);
+  } else {
+    const double cff1 = s.dtfast * 5.0 / 12.0, cff2 = s.dtfast * 8.0 / 12.0, cff3 = s.dtfast * 1.0 / 12.0, cff4 = 2.0 / 5.0, cff5 = 1.0 - cff4;
+    const double cff = cff1 * div;
+    z.zn = s.zs(i, j) + pmn * (cff + cff2 * s.rzs(i, j) - cff3 * s.rzp(i, j));
+    z.zwrk = cff5 * z.zn + cff4 * s.zk(i, j);
+  }
+  z.Dnew = z.zn + s.h(i, j);
+  z.gzeta = (s.fac + s.rhoS(i, j)) * z.zwrk;
+  z.gzeta2 = z.gzeta * z.zwrk;
+  z.gzetaSA = z.zwrk * (s.rhoS(i, j) - s.rhoA(i, j));
+  return z;
+}
+// second differences with the closed-wall replacements (:1283-1296, 1361-1376)
+__device__ __forceinline__ double g_ux(const S2& s, int i, int j) { return s.ub(i - 1, j) - 2.0 * s.ub(i, j) + s.ub(i + 1, j); }
+__device__ __forceinline__ double g_Dux(const S2& s, int i, int j) { return DUon(s, i - 1, j) - 2.0 * DUon(s, i, j) + DUon(s, i + 1, j); }
+__device__ __forceinline__ double g_ue(const S2& s, int i, int j) {
+  int jj = j; if (s.S && j == s.Jstr - 1) jj = s.Jstr; if (s.N && j == s.Jend + 1) jj = s.Jend;
+  return s.ub(i, jj - 1) - 2.0 * s.ub(i, jj) + s.ub(i, jj + 1);
+}
+__device__ __forceinline__ double g_Dvx(const S2& s, int i, int j) { return DVom(s, i - 1, j) - 2.0 * DVom(s, i, j) + DVom(s, i + 1, j); }
+__device__ __forceinline__ double g_vx(const S2& s, int i, int j) { return s.vb(i - 1, j) - 2.0 * s.vb(i, j) + s.vb(i + 1, j); }
+__device__ __forceinline__ double g_Due(const S2& s, int i, int j) { return DUon(s, i, j - 1) - 2.0 * DUon(s, i, j) + DUon(s, i, j + 1); }
+__device__ __forceinline__ double g_ve(const S2& s, int i, int j) {
+  int jj = j; if (s.S && j == s.Jstr) jj = s.Jstr + 1; if (s.N && j == s.Jend + 1) jj = s.Jend;
+  return s.vb(i, jj - 1) - 2.0 * s.vb(i, jj) + s.vb(i, jj + 1);
+}
+__device__ __forceinline__ double g_Dve(const S2& s, int i, int j) {
+  int jj = j; if (s.S && j == s.Jstr) jj = s.Jstr + 1; if (s.N && j == s.Jend + 1) jj = s.Jend;
+  return DVom(s, i, jj - 1) - 2.0 * DVom(s, i, jj) + DVom(s, i, jj + 1);
+}
+#define C6 (1.0 / 6.0)
+// fourth-order centred advective fluxes (:1298-1393)
+__device__ __forceinline__ double a_UFx(const S2& s, int i, int j) {
+  return 0.25 * (s.ub(i, j) + s.ub(i + 1, j) - C6 * (g_ux(s, i, j) + g_ux(s, i + 1, j))) *
+         (DUon(s, i, j) + DUon(s, i + 1, j) - C6 * (g_Dux(s, i, j) + g_Dux(s, i + 1, j)));
+}
+__device__ __forceinline__ double a_UFe(const S2& s, int i, int j) {
+  return 0.25 * (s.ub(i, j) + s.ub(i, j - 1) - C6 * (g_ue(s, i, j) + g_ue(s, i, j - 1))) *
+         (DVom(s, i, j) + DVom(s, i - 1, j) - C6 * (g_Dvx(s, i, j) + g_Dvx(s, i - 1, j)));
+}
+__device__ __forceinline__ double a_VFx(const S2& s, int i, int j) {
+  return 0.25 * (s.vb(i, j) + s.vb(i - 1, j) - C6 * (g_vx(s, i, j) + g_vx(s, i - 1, j))) *
+         (DUon(s, i, j) + DUon(s, i, j - 1) - C6 * (g_Due(s, i, j) + g_Due(s, i, j - 1)));
+}
+__device__ __forceinline__ double a_VFe(const S2& s, int i, int j) {
+  return 0.25 * (s.vb(i, j) + s.vb(i, j + 1) - C6 * (g_ve(s, i, j) + g_ve(s, i, j + 1))) *
+         (DVom(s, i, j) + DVom(s, i, j + 1) - C6 * (g_Dve(s, i, j) + g_Dve(s, i, j + 1)));
+}
+struct V2D { V2 fomn, dndx, dmde, visc2_r, visc2_p, pmon_r, pnom_r, pmon_p, pnom_p, om_r, on_r, om_p, on_p; };
+// harmonic viscosity fluxes (:1591-1625): rho-point and psi-point strain terms
+__device__ __forceinline__ double v_r(const S2& s, const V2D& m, int i, int j) {
+  return m.visc2_r(i, j) * Drhs(s, i, j) * 0.5 *
+         (m.pmon_r(i, j) * ((s.pn(i, j) + s.pn(i + 1, j)) * s.ub(i + 1, j) - (s.pn(i - 1, j) + s.pn(i, j)) * s.ub(i, j)) -
+          m.pnom_r(i, j) * ((s.pm(i, j) + s.pm(i, j + 1)) * s.vb(i, j + 1) - (s.pm(i, j - 1) + s.pm(i, j)) * s.vb(i, j)));
+}
+__device__ __forceinline__ double v_p(const S2& s, const V2D& m, int i, int j) {
+  const double Dp = 0.25 * (Drhs(s, i, j) + Drhs(s, i - 1, j) + Drhs(s, i, j - 1) + Drhs(s, i - 1, j - 1));
+  return m.visc2_p(i, j) * Dp * 0.5 *
+         (m.pmon_p(i, j) * ((s.pn(i, j - 1) + s.pn(i, j)) * s.vb(i, j) - (s.pn(i - 1, j - 1) + s.pn(i - 1, j)) * s.vb(i - 1, j)) +
+          m.pnom_p(i, j) * ((s.pm(i - 1, j) + s.pm(i, j)) * s.ub(i, j) - (s.pm(i - 1, j - 1) + s.pm(i, j - 1)) * s.ub(i, j - 1)));
+}
+__device__ __forceinline__ void c_cor(const S2& s, const V2D& m, int i, int j, double& cu, double& cv) {
+  const double cff = 0.5 * Drhs(s, i, j) * m.fomn(i, j);
+  cu = cff * (s.vb(i, j) + s.vb(i, j + 1)); cv = cff * (s.ub(i, j) + s.ub(i + 1, j));
+}
+__device__ __forceinline__ void c_curv(const S2& s, const V2D& m, int i, int j, double& cu, double& cv) {
+  const double c1 = 0.5 * (s.vb(i, j) + s.vb(i, j + 1)), c2 = 0.5 * (s.ub(i, j) + s.ub(i + 1, j));
+  const double c3 = c1 * m.dndx(i, j), c4 = c2 * m.dmde(i, j);
+  const double cff = Drhs(s, i, j) * (c3 - c4);
+  cu = cff * c1; cv = cff * c2;
+}
+
+struct Step2dArgs { int krhs, kstp, knew, nstp, nnew, iif, pred, stepmode; };  // stepmode: 0 iic==ntfirst, 1 ntfirst+1, 2 later
+
+__global__ void __launch_bounds__(128) step2d_kernel(const Dev D, Box bx, Step2dArgs a) {
+  IJ_FROM_BOX(bx);
+  const roms_b200_bounds& b = D.b;
+  const int krhs = a.krhs, kstp = a.kstp, knew = a.knew, iif = a.iif, ptsk = 3 - kstp;
+  const bool PRED = a.pred != 0;
+  S2 s{v2l(D, FID(zeta), krhs), v2l(D, FID(zeta), kstp), v2l(D, FID(ubar), krhs), v2l(D, FID(vbar), krhs),
+       v2(D, FID(h)), v2(D, FID(pm)), v2(D, FID(pn)), v2(D, FID(on_u)), v2(D, FID(om_v)), v2(D, FID(rhoA)), v2(D, FID(rhoS)),
+       v2l(D, FID(rzeta), kstp > 2 ? 1 : kstp), v2l(D, FID(rzeta), ptsk < 1 ? 1 : ptsk),
+       1000.0 / D.p.rho0, D.p.dtfast, (iif == 1) ? 0 : (PRED ? 1 : 2),
+       b.Southern_Edge && !b.NSperiodic, b.Northern_Edge && !b.NSperiodic, b.Jstr, b.Jend};
+  // ---- fast-time averaging (:742-810)
+  {
+    V2 Zt = v2(D, FID(Zt_avg1)), DU1 = v2(D, FID(DU_avg1)), DU2 = v2(D, FID(DU_avg2)), DV1 = v2(D, FID(DV_avg1)), DV2 = v2(D, FID(DV_avg2));
+    const bool last = (iif == D.p.nfast + 1) && PRED;    // auxiliary pass: periodic images of the averages (:821-855)
+    const bool inR = (i >= b.IstrR && i <= b.IendR && j >= b.JstrR && j <= b.JendR);
+    const bool inU = (i >= b.Istr && i <= b.IendR && j >= b.JstrR && j <= b.JendR);
+    const bool inV = (i >= b.IstrR && i <= b.IendR && j >= b.Jstr && j <= b.JendR);
+    if (PRED) {
+      if (iif == 1) {
+        const double cff2 = (-1.0 / 12.0) * D.w2[iif + 1];
+        if (inR) Zt(i, j) = 0.0;
+        if (inU) { DU1(i, j) = 0.0; DU2(i, j) = cff2 * DUon(s, i, j); }
+        if (inV) { DV1(i, j) = 0.0; DV2(i, j) = cff2 * DVom(s, i, j); }
+      } else {
+        const double cff1 = D.w1[iif - 1];
+        const double cff2 = (8.0 / 12.0) * D.w2[iif] - (1.0 / 12.0) * D.w2[iif + 1];
+        if (inR) { const double val = Zt(i, j) + cff1 * s.zk(i, j); if (last) st(D, Zt, i, j, val); else Zt(i, j) = val; }
+        if (inU) { const double du = DUon(s, i, j); const double val = DU1(i, j) + cff1 * du; if (last) st(D, DU1, i, j, val); else DU1(i, j) = val; DU2(i, j) = DU2(i, j) + cff2 * du; }
+        if (inV) { const double dv = DVom(s, i, j); const double val = DV1(i, j) + cff1 * dv; if (last) st(D, DV1, i, j, val); else DV1(i, j) = val; DV2(i, j) = DV2(i, j) + cff2 * dv; }
+      }
+    } else {
+      const double cff2 = (iif == 1) ? D.w2[iif] : (5.0 / 12.0) * D.w2[iif];
+      if (inU) DU2(i, j) = DU2(i, j) + cff2 * DUon(s, i, j);
+      if (inV) DV2(i, j) = DV2(i, j) + cff2 * DVom(s, i, j);
+    }
+  }
+  if (iif > D.p.nfast) return;
+  if (!(i >= b.Istr && i <= b.Iend && j >= b.Jstr && j <= b.Jend)) return;
+  const bool doU = (i >= b.IstrU), doV = (j >= b.JstrV);
+  const bool south = s.S && j == b.Jstr, north = s.N && j == b.Jend;
+  // ---- free surface (:899-1072)
+  const Zst z0 = zstate(s, i, j);
+  {
+    V2 zn = v2l(D, FID(zeta), knew);
+    st(D, zn, i, j, z0.zn);
+    if (south) st(D, zn, i, j - 1, z0.zn);           // zetabc_tile closed: zero gradient (zetabc.F:353-358,437-442)
+    if (north) st(D, zn, i, j + 1, z0.zn);
+    if (PRED) st(D, v2l(D, FID(rzeta), krhs), i, j, z0.rhs_zeta);
+  }
+  V2D m{v2(D, FID(fomn)), v2(D, FID(dndx)), v2(D, FID(dmde)), v2(D, FID(visc2_r)), v2(D, FID(visc2_p)), v2(D, FID(pmon_r)), v2(D, FID(pnom_r)),
+        v2(D, FID(pmon_p)), v2(D, FID(pnom_p)), v2(D, FID(om_r)), v2(D, FID(on_r)), v2(D, FID(om_p)), v2(D, FID(on_p))};
+  const bool curv = (D.p.app == ROMS_B200_APP_BENCHMARK);
+  const double cg = 0.5 * D.p.g, c3 = 1.0 / 3.0;
+  for (int comp = 0; comp < 2; ++comp) {
+    if (comp == 0 && !doU) continue;
+    if (comp == 1 && !doV) continue;
+    const int di = comp == 0 ? 1 : 0, dj = 1 - di;
+    const Zst zm = zstate(s, i - di, j - dj);
+    const double hm = s.h(i - di, j - dj), h0 = s.h(i, j);
+    // pressure gradient with variable-density terms (:1088-1205)
+    double rhs = cg * (comp == 0 ? s.on_u(i, j) : s.om_v(i, j)) *
+                 ((hm + h0) * (zm.gzeta - z0.gzeta) +
+                  (hm - h0) * (zm.gzetaSA + z0.gzetaSA + c3 * (s.rhoA(i - di, j - dj) - s.rhoA(i, j)) * (zm.zwrk - z0.zwrk)) +
+                  (zm.gzeta2 - z0.gzeta2));
+    double cu0, cv0, cu1, cv1;
+    if (comp == 0) {
+      { const double c1 = a_UFx(s, i, j) - a_UFx(s, i - 1, j), c2 = a_UFe(s, i, j + 1) - a_UFe(s, i, j); rhs = rhs - (c1 + c2); }
+      c_cor(s, m, i, j, cu0, cv0); c_cor(s, m, i - 1, j, cu1, cv1); rhs = rhs + 0.5 * (cu0 + cu1);
+      if (curv) { c_curv(s, m, i, j, cu0, cv0); c_curv(s, m, i - 1, j, cu1, cv1); rhs = rhs + 0.5 * (cu0 + cu1); }
+      const double UFx0 = m.on_r(i, j) * m.on_r(i, j) * v_r(s, m, i, j), UFx1 = m.on_r(i - 1, j) * m.on_r(i - 1, j) * v_r(s, m, i - 1, j);
+      const double UFe1 = m.om_p(i, j + 1) * m.om_p(i, j + 1) * v_p(s, m, i, j + 1), UFe0 = m.om_p(i, j) * m.om_p(i, j) * v_p(s, m, i, j);
+      const double c1 = 0.5 * (s.pn(i - 1, j) + s.pn(i, j)) * (UFx0 - UFx1), c2 = 0.5 * (s.pm(i - 1, j) + s.pm(i, j)) * (UFe1 - UFe0);
+      rhs = rhs + (c1 + c2);
+    } else {
+      { const double c1 = a_VFx(s, i + 1, j) - a_VFx(s, i, j), c2 = a_VFe(s, i, j) - a_VFe(s, i, j - 1); rhs = rhs - (c1 + c2); }
+      c_cor(s, m, i, j, cu0, cv0); c_cor(s, m, i, j - 1, cu1, cv1); rhs = rhs - 0.5 * (cv0 + cv1);
+      if (curv) { c_curv(s, m, i, j, cu0, cv0); c_curv(s, m, i, j - 1, cu1, cv1); rhs = rhs - 0.5 * (cv0 + cv1); }
+      const double VFx1 = m.on_p(i + 1, j) * m.on_p(i + 1, j) * v_p(s, m, i + 1, j), VFx0 = m.on_p(i, j) * m.on_p(i, j) * v_p(s, m, i, j);
+      const double VFe0 = m.om_r(i, j) * m.om_r(i, j) * v_r(s, m, i, j), VFe1 = m.om_r(i, j - 1) * m.om_r(i, j - 1) * v_r(s, m, i, j - 1);
+      const double c1 = 0.5 * (s.pn(i, j - 1) + s.pn(i, j)) * (VFx1 - VFx0), c2 = 0.5 * (s.pm(i, j - 1) + s.pm(i, j)) * (VFe0 - VFe1);
+      rhs = rhs + (c1 - c2);
+    }
+    // coupling with the 3-D forcing (:2241-2459)
+    V2 frc = v2(D, comp == 0 ? FID(rufrc) : FID(rvfrc));
+    if (iif == 1 && PRED) {
+      V3 r0n = v3l(D, comp == 0 ? FID(ru) : FID(rv), a.nstp), r0w = v3l(D, comp == 0 ? FID(ru) : FID(rv), a.nnew);
+      const double fr = frc(i, j) - rhs;
+      frc(i, j) = fr;
+      if (a.stepmode == 0) rhs = rhs + fr;
+      else if (a.stepmode == 1) rhs = rhs + 1.5 * fr - 0.5 * r0w(i, j, 0);
+      else rhs = rhs + (23.0 / 12.0) * fr - (16.0 / 12.0) * r0w(i, j, 0) + (5.0 / 12.0) * r0n(i, j, 0);
+      r0n(i, j, 0) = fr;
+    } else rhs = rhs + frc(i, j);
+    // time stepping (:2493-2674)
+    const double Dstp = (s.zs(i, j) + h0) + (s.zs(i - di, j - dj) + hm);
+    const double cff = (s.pm(i, j) + s.pm(i - di, j - dj)) * (s.pn(i, j) + s.pn(i - di, j - dj));
+    const double fc = 1.0 / (z0.Dnew + zm.Dnew);
+    V2 qs = v2l(D, comp == 0 ? FID(ubar) : FID(vbar), kstp), qn = v2l(D, comp == 0 ? FID(ubar) : FID(vbar), knew);
+    double val;
+    if (iif == 1 || PRED) {
+      const double cff1 = (iif == 1) ? 0.5 * D.p.dtfast : D.p.dtfast;
+      val = (qs(i, j) * Dstp + cff * cff1 * rhs) * fc;
+    } else {
+      const double cff1 = 0.5 * D.p.dtfast * 5.0 / 12.0, cff2 = 0.5 * D.p.dtfast * 8.0 / 12.0, cff3 = 0.5 * D.p.dtfast * 1.0 / 12.0;
+      V2 rs = v2l(D, comp == 0 ? FID(rubar) : FID(rvbar), kstp), rp = v2l(D, comp == 0 ? FID(rubar) : FID(rvbar), ptsk);
+      val = (qs(i, j) * Dstp + cff * (cff1 * rhs + cff2 * rs(i, j) - cff3 * rp(i, j))) * fc;
+    }
+    if (PRED) v2l(D, comp == 0 ? FID(rubar) : FID(rvbar), krhs)(i, j) = rhs;
+    st(D, qn, i, j, val);
+    if (comp == 0) {                                  // u2dbc_im.F:483-496 (gamma2 slip on closed walls)
+      if (south) st(D, qn, i, j - 1, D.p.gamma2 * val);
+      if (north) st(D, qn, i, j + 1, D.p.gamma2 * val);
+    }
+  }
+  {                                                   // v2dbc_im.F:253-258,395-400 (no normal flow)
+    V2 vn = v2l(D, FID(vbar), knew);
+    if (south) st(D, vn, i, b.Jstr, 0.0);
+    if (north) st(D, vn, i, b.Jend + 1, 0.0);
+  }
+}
+
+int k_step2d(roms_b200_ctx* c, int krhs, int kstp, int knew, int nstp, int nnew, int iif, int pred, int iic, int ntfirst) {
+  const roms_b200_bounds& b = c->D.b;
+  Step2dArgs a{krhs, kstp, knew, nstp, nnew, iif, pred, (iic == ntfirst) ? 0 : (iic == ntfirst + 1 ? 1 : 2)};
+  Box bx{b.IstrR, b.IendR, b.JstrR, b.JendR}; dim3 blk(32, 4);
+  step2d_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx, a); c->launches++;
+  return 0;
+}

@@ -1,0 +1,299 @@
+// roms_b200/csrc/k_tracer.cu -- tracer predictor (pre_step3d), corrector (step3d_t)
+// and harmonic tracer mixing (t3dmix2).  Column-marching kernels: one thread per
+// water column, i fastest so every row access of a warp is one coalesced stripe;
+// the +-2 j-neighbour rows of the U3 stencil are re-read through L1/L2 by the
+// other warps of the (32 x 8) block.  Per-column tridiagonal work lives in
+// thread-private arrays.  Arithmetic order per point == reference (-fmad=false).
+#include "common.cuh"
+
+struct Edges { int S, N, Jstr, Jend; };
+__device__ __forceinline__ Edges edges(const Dev& D) { return Edges{D.b.Southern_Edge && !D.b.NSperiodic, D.b.Northern_Edge && !D.b.NSperiodic, D.b.Jstr, D.b.Jend}; }
+
+// first difference in eta with the closed-wall replacement FE(i,Jstr-1)=FE(i,Jstr),
+// FE(i,Jend+2)=FE(i,Jend+1)  (pre_step3d.F:480-493, step3d_t.F:705-723)
+__device__ __forceinline__ double dEta(const V3& q, int i, int j, int k, const Edges& e) {
+  int jj = j;
+  if (e.S && j == e.Jstr - 1) jj = e.Jstr;
+  if (e.N && j == e.Jend + 2) jj = e.Jend + 1;
+  return q(i, jj, k) - q(i, jj - 1, k);
+}
+// third-order upstream (U3) horizontal tracer fluxes, pre_step3d.F:406-533 == step3d_t.F:641-767
+__device__ __forceinline__ double fluxX_u3(const V3& q, const V3& Huon, int i, int j, int k) {
+  const double d0 = q(i - 1, j, k) - q(i - 2, j, k), d1 = q(i, j, k) - q(i - 1, j, k), d2 = q(i + 1, j, k) - q(i, j, k);
+  const double cm = d1 - d0, cp = d2 - d1, hu = Huon(i, j, k);
+  return hu * 0.5 * (q(i - 1, j, k) + q(i, j, k)) - (1.0 / 6.0) * (cm * fmax(hu, 0.0) + cp * fmin(hu, 0.0));
+}
+__device__ __forceinline__ double fluxE_u3(const V3& q, const V3& Hvom, int i, int j, int k, const Edges& e) {
+  const double d0 = dEta(q, i, j - 1, k, e), d1 = dEta(q, i, j, k, e), d2 = dEta(q, i, j + 1, k, e);
+  const double cm = d1 - d0, cp = d2 - d1, hv = Hvom(i, j, k);
+  return hv * 0.5 * (q(i, j - 1, k) + q(i, j, k)) - (1.0 / 6.0) * (cm * fmax(hv, 0.0) + cp * fmin(hv, 0.0));
+}
+// fourth-order centred vertical flux at w-level k (pre_step3d.F:773-808, step3d_t.F:1150-1185)
+__device__ __forceinline__ double fluxZ_c4(const V3& q, const V3& W, int i, int j, int k, int N) {
+  const double c1 = 0.5, c2 = 7.0 / 12.0, c3 = 1.0 / 12.0;
+  if (k == 0 || k == N) return 0.0;
+  if (k == 1) return W(i, j, 1) * (c1 * q(i, j, 1) + c2 * q(i, j, 2) - c3 * q(i, j, 3));
+  if (k == N - 1) return W(i, j, N - 1) * (c1 * q(i, j, N) + c2 * q(i, j, N - 1) - c3 * q(i, j, N - 2));
+  return W(i, j, k) * (c2 * (q(i, j, k) + q(i, j, k + 1)) - c3 * (q(i, j, k - 1) + q(i, j, k + 2)));
+}
+// store with the closed-wall gradient condition of t3dbc_im.F:334-341,415-422
+__device__ __forceinline__ void st_tbc(const Dev& D, const V3& A, int i, int j, int k, double val, const Edges& e) {
+  st(D, A, i, j, k, val);
+  if (e.S && j == e.Jstr) st(D, A, i, j - 1, k, val);
+  if (e.N && j == e.Jend) st(D, A, i, j + 1, k, val);
+}
+
+__constant__ double c_mu1[9] = {0.35, 0.6, 1.0, 1.5, 1.4, 0.42, 0.37, 0.33, 0.00468592};   // mod_scalars.F:1585
+__constant__ double c_mu2[9] = {23.0, 20.0, 17.0, 14.0, 7.9, 5.13, 3.54, 2.34, 1.51};      // mod_scalars.F:1589
+__constant__ double c_r1[9] = {0.58, 0.62, 0.67, 0.77, 0.78, 0.57, 0.57, 0.57, 0.55};      // mod_scalars.F:1593
+// lmd_swfrac_tile with Zscale=-1 (lmd_swfrac.F)
+__device__ __forceinline__ double swfrac(int Jindex, double Z) {
+  const double fac1 = -1.0 / c_mu1[Jindex - 1], fac2 = -1.0 / c_mu2[Jindex - 1], fac3 = c_r1[Jindex - 1];
+  return exp(Z * fac1) * fac3 + exp(Z * fac2) * (1.0 - fac3);
+}
+
+// ---- pre_step3d_tile, tracer part: pre_step3d.F:329-344,406-932,1152-1168 -----
+__global__ void __launch_bounds__(256) pre_step3d_t_kernel(const Dev D, Box bx, int nstp, int nnew, int first) {
+  IJ_FROM_BOX(bx);
+  const int itrc = 1 + blockIdx.z, N = D.b.N; const double dt = D.p.dt;
+  const Edges e = edges(D);
+  V3 Hz = v3(D, FID(Hz)), Huon = v3(D, FID(Huon)), Hvom = v3(D, FID(Hvom)), W = v3(D, FID(W)), z_r = v3(D, FID(z_r));
+  V3 tn = v3l(D, FID(t), nstp, itrc), tw = v3l(D, FID(t), nnew, itrc), t3 = v3l(D, FID(t), 3, itrc);
+  V3 Akt = v3l(D, FID(Akt), min(D.b.NAT, itrc));
+  const double pmn_pm = v2(D, FID(pm))(i, j), pmn_pn = v2(D, FID(pn))(i, j);
+  const double Gamma = 1.0 / 6.0;
+  double cff, cff1, cff2;
+  if (first) { cff = 0.5 * dt; cff1 = 1.0; cff2 = 0.0; } else { cff = (1.0 - Gamma) * dt; cff1 = 0.5 + Gamma; cff2 = 0.5 - Gamma; }
+  // horizontal predictor level by level, then the vertical part with artificial continuity
+  double FCm = 0.0;                      // FC(k-1)
+  const double cpm = cff * pmn_pm * pmn_pn;
+  for (int k = 1; k <= N; ++k) {
+    const double FXi = fluxX_u3(tn, Huon, i, j, k), FXp = fluxX_u3(tn, Huon, i + 1, j, k);
+    const double FEj = fluxE_u3(tn, Hvom, i, j, k, e), FEp = fluxE_u3(tn, Hvom, i, j + 1, k, e);
+    const double hz = Hz(i, j, k);
+    double t3h = hz * (cff1 * tn(i, j, k) + cff2 * tw(i, j, k)) - cpm * (FXp - FXi + FEp - FEj);
+    const double FCk = fluxZ_c4(tn, W, i, j, k, N);
+    const double DC = 1.0 / (hz - cpm * (Huon(i + 1, j, k) - Huon(i, j, k) + Hvom(i, j + 1, k) - Hvom(i, j, k) + (W(i, j, k) - W(i, j, k - 1))));
+    t3h = DC * (t3h - cpm * (FCk - FCm));
+    st_tbc(D, t3, i, j, k, t3h, e);
+    FCm = FCk;
+  }
+  // t(nnew) = Hz*t(nstp) + explicit vertical terms (pre_step3d.F:863-932)
+  const double cff3 = dt * (1.0 - 1.0 /*lambda*/);
+  const bool bench = (D.p.app == ROMS_B200_APP_BENCHMARK);
+  const double btf = v2l(D, FID(btflx), itrc)(i, j), stf = v2l(D, FID(stflx), itrc)(i, j);
+  double srf = 0.0, zwN = 0.0; int Jw = 1; V3 gh = v3l(D, FID(ghats), min(D.b.NAT, itrc)); V3 z_w = v3(D, FID(z_w));
+  if (bench) { srf = v2(D, FID(srflx))(i, j); zwN = z_w(i, j, N); Jw = (int)v2(D, FID(Jwtype))(i, j); }
+  double Fm = dt * btf;                  // FC(0)
+  for (int k = 1; k <= N; ++k) {
+    double Fk;
+    if (k < N) {
+      const double c = 1.0 / (z_r(i, j, k + 1) - z_r(i, j, k));
+      Fk = cff3 * c * Akt(i, j, k) * (tn(i, j, k + 1) - tn(i, j, k));
+      if (bench) {
+        if (itrc <= D.b.NAT) Fk = Fk - dt * Akt(i, j, k) * gh(i, j, k);
+        if (itrc == 1) Fk = Fk + dt * srf * swfrac(Jw, zwN - z_w(i, j, k));
+      }
+    } else Fk = dt * stf;
+    const double a = Hz(i, j, k) * tn(i, j, k), bdiff = Fk - Fm;
+    tw(i, j, k) = a + bdiff;
+    Fm = Fk;
+  }
+}
+
+// ---- pre_step3d_tile, momentum part: pre_step3d.F:943-1144 ------------------------
+__global__ void __launch_bounds__(256) pre_step3d_uv_kernel(const Dev D, Box bx, int nrhs, int nstp, int nnew, int mode) {
+  IJ_FROM_BOX(bx);
+  const roms_b200_bounds& b = D.b; const int N = b.N; const double dt = D.p.dt;
+  V3 Hz = v3(D, FID(Hz)), z_r = v3(D, FID(z_r)), Akv = v3(D, FID(Akv));
+  V2 pm = v2(D, FID(pm)), pn = v2(D, FID(pn));
+  const int indx = 3 - nrhs;
+  const double cff3 = dt * (1.0 - 1.0 /*lambda*/);
+  for (int comp = 0; comp < 2; ++comp) {
+    const int di = comp == 0 ? 1 : 0, dj = 1 - di;   // neighbour offset of the staggered point
+    if (comp == 0 && !(i >= b.IstrU && i <= b.Iend && j >= b.Jstr && j <= b.Jend)) continue;
+    if (comp == 1 && !(i >= b.Istr && i <= b.Iend && j >= b.JstrV && j <= b.Jend)) continue;
+    V3 q = v3l(D, comp == 0 ? FID(u) : FID(v), nstp), qn = v3l(D, comp == 0 ? FID(u) : FID(v), nnew);
+    V3 r1 = v3l(D, comp == 0 ? FID(ru) : FID(rv), nrhs), r2 = v3l(D, comp == 0 ? FID(ru) : FID(rv), indx);
+    const double bstr = v2(D, comp == 0 ? FID(bustr) : FID(bvstr))(i, j), sstr = v2(D, comp == 0 ? FID(sustr) : FID(svstr))(i, j);
+    const double DC0 = (dt * 0.25) * (pm(i, j) + pm(i - di, j - dj)) * (pn(i, j) + pn(i - di, j - dj));
+    double Fm = dt * bstr;
+    for (int k = 1; k <= N; ++k) {
+      double Fk;
+      if (k < N) {
+        const double c = 1.0 / (z_r(i, j, k + 1) + z_r(i - di, j - dj, k + 1) - z_r(i, j, k) - z_r(i - di, j - dj, k));
+        Fk = cff3 * c * (q(i, j, k + 1) - q(i, j, k)) * (Akv(i, j, k) + Akv(i - di, j - dj, k));
+      } else Fk = dt * sstr;
+      const double a = q(i, j, k) * 0.5 * (Hz(i, j, k) + Hz(i - di, j - dj, k));
+      const double d = Fk - Fm;
+      double val;
+      if (mode == 0) val = a + d;
+      else if (mode == 1) { const double c3 = 0.5 * DC0; val = a - c3 * r2(i, j, k) + d; }
+      else val = a + DC0 * ((5.0 / 12.0) * r1(i, j, k) - (16.0 / 12.0) * r2(i, j, k)) + d;
+      qn(i, j, k) = val;
+      Fm = Fk;
+    }
+  }
+}
+
+int k_pre_step3d(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntfirst) {
+  const roms_b200_bounds& b = c->D.b;
+  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT;
+  pre_step3d_t_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nstp, nnew, iic == ntfirst ? 1 : 0); c->launches++;
+  g.z = 1;
+  const int mode = (iic == ntfirst) ? 0 : (iic == ntfirst + 1 ? 1 : 2);
+  pre_step3d_uv_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs, nstp, nnew, mode); c->launches++;
+  return 0;
+}
+
+// ---- step3d_t_tile: step3d_t.F:393-399,641-916,1150-1365,1672-1721,1858-1924 ---
+// One pass: read t(3) (+halo through L1), Huon,Hvom,W,Hz,Akt once; read+write
+// t(nnew) once.  Algorithmic traffic 48 B per tracer-cell + 32 B per cell.
+__global__ void __launch_bounds__(256) step3d_t_kernel(const Dev D, Box bx, int nnew) {
+  IJ_FROM_BOX(bx);
+  const int itrc = 1 + blockIdx.z, N = D.b.N; const double dt = D.p.dt;
+  const Edges e = edges(D);
+  V3 Hz = v3(D, FID(Hz)), Huon = v3(D, FID(Huon)), Hvom = v3(D, FID(Hvom)), W = v3(D, FID(W));
+  V3 t3 = v3l(D, FID(t), 3, itrc), tw = v3l(D, FID(t), nnew, itrc), Akt = v3l(D, FID(Akt), min(D.b.NAT, itrc));
+  const double cff = dt * v2(D, FID(pm))(i, j) * v2(D, FID(pn))(i, j);
+  double q[RB_MAXN + 2], oHz[RB_MAXN + 2], CF[RB_MAXN + 1], DC[RB_MAXN + 1];
+  double FCm = 0.0;
+  for (int k = 1; k <= N; ++k) {
+    const double FXi = fluxX_u3(t3, Huon, i, j, k), FXp = fluxX_u3(t3, Huon, i + 1, j, k);
+    const double FEj = fluxE_u3(t3, Hvom, i, j, k, e), FEp = fluxE_u3(t3, Hvom, i, j + 1, k, e);
+    const double c1 = cff * (FXp - FXi), c2 = cff * (FEp - FEj), c3 = c1 + c2;
+    double tv = tw(i, j, k) - c3;
+    const double FCk = fluxZ_c4(t3, W, i, j, k, N);
+    const double cv = cff * (FCk - FCm);
+    oHz[k] = 1.0 / Hz(i, j, k);
+    tv = tv - cv;
+    q[k] = tv * oHz[k];
+    FCm = FCk;
+  }
+  // spline implicit vertical diffusion (step3d_t.F:1672-1721)
+  CF[0] = 0.0; DC[0] = 0.0;
+  {
+    double hz_k = Hz(i, j, 1), ak_km = Akt(i, j, 0), ak_k = Akt(i, j, 1);
+    for (int k = 1; k <= N - 1; ++k) {
+      const double hz_kp = Hz(i, j, k + 1), ak_kp = Akt(i, j, k + 1);
+      const double FC = (1.0 / 6.0) * hz_k - dt * ak_km * oHz[k];
+      const double CFk = (1.0 / 6.0) * hz_kp - dt * ak_kp * oHz[k + 1];
+      const double BC = (1.0 / 3.0) * (hz_k + hz_kp) + dt * ak_k * (oHz[k] + oHz[k + 1]);
+      const double cf = 1.0 / (BC - FC * CF[k - 1]);
+      CF[k] = cf * CFk;
+      DC[k] = cf * (q[k + 1] - q[k] - FC * DC[k - 1]);
+      hz_k = hz_kp; ak_km = ak_k; ak_k = ak_kp;
+    }
+  }
+  DC[N] = 0.0;
+  for (int k = N - 1; k >= 1; --k) DC[k] = DC[k] - CF[k] * DC[k + 1];
+  double dcm = DC[0];
+  for (int k = 1; k <= N; ++k) {
+    const double dck = DC[k] * Akt(i, j, k);
+    const double c1 = dt * oHz[k] * (dck - dcm);
+    st_tbc(D, tw, i, j, k, q[k] + c1, e);
+    dcm = dck;
+  }
+}
+int k_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew) {
+  (void)nrhs; (void)nstp;
+  const roms_b200_bounds& b = c->D.b;
+  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT;
+  step3d_t_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nnew); c->launches++;
+  return 0;
+}
+
+// ---- t3dmix2_s_tile, t3dmix2_s.h:198-301 (MIX_S_TS, UPWELLING) ---------------
+__global__ void t3dmix2_s_kernel(const Dev D, Box bx, int nrhs, int nnew) {
+  IJ_FROM_BOX(bx);
+  const int N = D.b.N, itrc = 1 + blockIdx.z; const double dt = D.p.dt;
+  V3 Hz = v3(D, FID(Hz)), tr = v3l(D, FID(t), nrhs, itrc), tw = v3l(D, FID(t), nnew, itrc);
+  V2 d2 = v2l(D, FID(diff2), itrc), pmon_u = v2(D, FID(pmon_u)), pnom_v = v2(D, FID(pnom_v));
+  const double cff = dt * v2(D, FID(pm))(i, j) * v2(D, FID(pn))(i, j);
+  const double cx0 = 0.25 * (d2(i, j) + d2(i - 1, j)) * pmon_u(i, j), cx1 = 0.25 * (d2(i + 1, j) + d2(i, j)) * pmon_u(i + 1, j);
+  const double ce0 = 0.25 * (d2(i, j) + d2(i, j - 1)) * pnom_v(i, j), ce1 = 0.25 * (d2(i, j + 1) + d2(i, j)) * pnom_v(i, j + 1);
+  for (int k = 1; k <= N; ++k) {
+    const double FX0 = cx0 * (Hz(i, j, k) + Hz(i - 1, j, k)) * (tr(i, j, k) - tr(i - 1, j, k));
+    const double FX1 = cx1 * (Hz(i + 1, j, k) + Hz(i, j, k)) * (tr(i + 1, j, k) - tr(i, j, k));
+    const double FE0 = ce0 * (Hz(i, j, k) + Hz(i, j - 1, k)) * (tr(i, j, k) - tr(i, j - 1, k));
+    const double FE1 = ce1 * (Hz(i, j + 1, k) + Hz(i, j, k)) * (tr(i, j + 1, k) - tr(i, j, k));
+    const double c1 = cff * (FX1 - FX0), c2 = cff * (FE1 - FE0), c3 = c1 + c2;
+    tw(i, j, k) = tw(i, j, k) + c3;
+  }
+}
+
+// ---- t3dmix2_geo_tile, t3dmix2_geo.h:219-419 (MIX_GEO_TS, BENCHMARK) ----------
+// Geopotential rotation of the mixing tensor.  The reference rolls two k-levels
+// (k1,k2) of dZdx,dTdx,dZde,dTde,dTdz,FS through scratch planes; here each thread
+// re-evaluates the slopes it needs for level pair (k,k+1) straight from z_r and t.
+struct GeoQ { V3 z_r, tr; V2 pm, pn; int N; };
+__device__ __forceinline__ double g_dTdz(const GeoQ& G, int i, int j, int kw) {   // at w-level kw (0 or N -> 0)
+  if (kw == 0 || kw == G.N) return 0.0;
+  const double c = 1.0 / (G.z_r(i, j, kw + 1) - G.z_r(i, j, kw));
+  return c * (G.tr(i, j, kw + 1) - G.tr(i, j, kw));
+}
+__device__ __forceinline__ void g_dx(const GeoQ& G, int i, int j, int k, double& dZ, double& dT) {   // at u-point, rho-level k
+  const double c = 0.5 * (G.pm(i, j) + G.pm(i - 1, j));
+  dZ = c * (G.z_r(i, j, k) - G.z_r(i - 1, j, k)); dT = c * (G.tr(i, j, k) - G.tr(i - 1, j, k));
+}
+__device__ __forceinline__ void g_de(const GeoQ& G, int i, int j, int k, double& dZ, double& dT) {   // at v-point
+  const double c = 0.5 * (G.pn(i, j) + G.pn(i, j - 1));
+  dZ = c * (G.z_r(i, j, k) - G.z_r(i, j - 1, k)); dT = c * (G.tr(i, j, k) - G.tr(i, j - 1, k));
+}
+// FX at u-point (i,j), level k: uses dTdz at w-levels k-1 (index k1 side) and k (k2 side)
+__device__ __forceinline__ double g_FX(const GeoQ& G, const V3& Hz, const V2& d2, const V2& on_u, int i, int j, int k) {
+  double dZ, dT; g_dx(G, i, j, k, dZ, dT);
+  const double c = 0.25 * (d2(i, j) + d2(i - 1, j)) * on_u(i, j);
+  return c * (Hz(i, j, k) + Hz(i - 1, j, k)) *
+         (dT - 0.5 * (fmin(dZ, 0.0) * (g_dTdz(G, i - 1, j, k - 1) + g_dTdz(G, i, j, k)) +
+                      fmax(dZ, 0.0) * (g_dTdz(G, i - 1, j, k) + g_dTdz(G, i, j, k - 1))));
+}
+__device__ __forceinline__ double g_FE(const GeoQ& G, const V3& Hz, const V2& d2, const V2& om_v, int i, int j, int k) {
+  double dZ, dT; g_de(G, i, j, k, dZ, dT);
+  const double c = 0.25 * (d2(i, j) + d2(i, j - 1)) * om_v(i, j);
+  return c * (Hz(i, j, k) + Hz(i, j - 1, k)) *
+         (dT - 0.5 * (fmin(dZ, 0.0) * (g_dTdz(G, i, j - 1, k - 1) + g_dTdz(G, i, j, k)) +
+                      fmax(dZ, 0.0) * (g_dTdz(G, i, j - 1, k) + g_dTdz(G, i, j, k - 1))));
+}
+// FS at w-level k (between rho-levels k and k+1); zero at k=0 and k=N
+__device__ __forceinline__ double g_FS(const GeoQ& G, const V2& d2, int i, int j, int k) {
+  if (k == 0 || k == G.N) return 0.0;
+  const double cff = 0.5 * d2(i, j), tz = g_dTdz(G, i, j, k);
+  double zx_a, tx_a, zx_b, tx_b, zx_c, tx_c, zx_d, tx_d;
+  g_dx(G, i, j, k, zx_a, tx_a);         // dZdx(i  ,j,k1)
+  g_dx(G, i + 1, j, k + 1, zx_b, tx_b); // dZdx(i+1,j,k2)
+  g_dx(G, i, j, k + 1, zx_c, tx_c);     // dZdx(i  ,j,k2)
+  g_dx(G, i + 1, j, k, zx_d, tx_d);     // dZdx(i+1,j,k1)
+  double c1 = fmin(zx_a, 0.0), c2 = fmin(zx_b, 0.0), c3 = fmax(zx_c, 0.0), c4 = fmax(zx_d, 0.0);
+  double FS = cff * (c1 * (c1 * tz - tx_a) + c2 * (c2 * tz - tx_b) + c3 * (c3 * tz - tx_c) + c4 * (c4 * tz - tx_d));
+  g_de(G, i, j, k, zx_a, tx_a); g_de(G, i, j + 1, k + 1, zx_b, tx_b); g_de(G, i, j, k + 1, zx_c, tx_c); g_de(G, i, j + 1, k, zx_d, tx_d);
+  c1 = fmin(zx_a, 0.0); c2 = fmin(zx_b, 0.0); c3 = fmax(zx_c, 0.0); c4 = fmax(zx_d, 0.0);
+  FS = FS + cff * (c1 * (c1 * tz - tx_a) + c2 * (c2 * tz - tx_b) + c3 * (c3 * tz - tx_c) + c4 * (c4 * tz - tx_d));
+  return FS;
+}
+__global__ void __launch_bounds__(256) t3dmix2_geo_kernel(const Dev D, Box bx, int nrhs, int nnew) {
+  IJ_FROM_BOX(bx);
+  const int N = D.b.N, itrc = 1 + blockIdx.z; const double dt = D.p.dt;
+  V3 Hz = v3(D, FID(Hz)), tw = v3l(D, FID(t), nnew, itrc);
+  GeoQ G{v3(D, FID(z_r)), v3l(D, FID(t), nrhs, itrc), v2(D, FID(pm)), v2(D, FID(pn)), N};
+  V2 d2 = v2l(D, FID(diff2), itrc), on_u = v2(D, FID(on_u)), om_v = v2(D, FID(om_v));
+  const double cff = dt * G.pm(i, j) * G.pn(i, j);
+  double FSm = 0.0;                      // FS at w-level k-1
+  for (int k = 1; k <= N; ++k) {
+    const double FX0 = g_FX(G, Hz, d2, on_u, i, j, k), FX1 = g_FX(G, Hz, d2, on_u, i + 1, j, k);
+    const double FE0 = g_FE(G, Hz, d2, om_v, i, j, k), FE1 = g_FE(G, Hz, d2, om_v, i, j + 1, k);
+    const double FSk = g_FS(G, d2, i, j, k);
+    const double c1 = cff * (FX1 - FX0), c2 = cff * (FE1 - FE0), c3 = dt * (FSk - FSm), c4 = c1 + c2 + c3;
+    tw(i, j, k) = tw(i, j, k) + c4;
+    FSm = FSk;
+  }
+}
+int k_t3dmix2(roms_b200_ctx* c, int nrhs, int nstp, int nnew) {
+  (void)nstp;
+  const roms_b200_bounds& b = c->D.b;
+  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT;
+  if (c->D.p.app == ROMS_B200_APP_UPWELLING) t3dmix2_s_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs, nnew);
+  else t3dmix2_geo_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs, nnew);
+  c->launches++;
+  return 0;
+}

@@ -1,0 +1,257 @@
+// roms_b200/csrc/roms_b200.cu -- C ABI of libroms_b200.so: device mirror,
+// kernel entry points, the barotropic fast loop (CUDA graph) and the main3d
+// sequencing.  See include/roms_b200.h for the contract.
+#include "common.cuh"
+#include <cstring>
+#include <cstdlib>
+#include <cmath>
+#include <string>
+#include <vector>
+
+namespace {
+struct FieldInfo { const char* name; int kLB; const char* nk; const char* nl; const char* nm; };
+#define X(name, kLB, nk, nl, nm) {#name, kLB, #nk, #nl, #nm},
+const FieldInfo kFields[ROMS_B200_NFIELDS] = {ROMS_B200_FIELDS(X)};
+#undef X
+int resolve(const char* s, const roms_b200_bounds& b) {
+  if (!strcmp(s, "N")) return b.N;
+  if (!strcmp(s, "Np1")) return b.N + 1;
+  if (!strcmp(s, "NT")) return b.NT;
+  if (!strcmp(s, "NAT")) return b.NAT;
+  return atoi(s);
+}
+template <typename T> int dev_alloc(T** p, size_t n) {
+  CUDA_OK(cudaMalloc((void**)p, n * sizeof(T)));
+  CUDA_OK(cudaMemset(*p, 0, n * sizeof(T)));
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int roms_b200_field_id(const char* name) {
+  for (int f = 0; f < ROMS_B200_NFIELDS; ++f) if (!strcmp(kFields[f].name, name)) return f;
+  return -1;
+}
+
+int roms_b200_create(const roms_b200_bounds* b, const roms_b200_params* p, int device, roms_b200_ctx** out) {
+  if (!b || !p || !out) return 1;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    fprintf(stderr, "roms_b200: no CUDA device available; this library has no CPU path\n");
+    return 2;
+  }
+  if (b->N > RB_MAXN) { fprintf(stderr, "roms_b200: N=%d exceeds RB_MAXN=%d\n", b->N, RB_MAXN); return 3; }
+  if (!b->EWperiodic || b->NSperiodic) { fprintf(stderr, "roms_b200: only E-W periodic / N-S closed channels are supported\n"); return 3; }
+  CUDA_OK(cudaSetDevice(device));
+  roms_b200_ctx* c = new roms_b200_ctx();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  Dev& D = c->D;
+  D.b = *b; D.p = *p;
+  D.ni = b->UBi - b->LBi + 1; D.nj = b->UBj - b->LBj + 1; D.nij = (size_t)D.ni * D.nj;
+  D.wrapEW = (b->EWperiodic && b->NtileI == 1) ? 1 : 0;
+  CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int f = 0; f < ROMS_B200_NFIELDS; ++f) {
+    const int nk = resolve(kFields[f].nk, *b), nl = resolve(kFields[f].nl, *b), nm = resolve(kFields[f].nm, *b);
+    D.kLB[f] = kFields[f].kLB; D.nk[f] = nk; D.nl[f] = nl;
+    c->fsize[f] = D.nij * nk * nl * nm;
+    if (dev_alloc(&D.f[f], c->fsize[f])) return 4;
+  }
+  double* v;
+  if (dev_alloc(&v, (size_t)(b->N + 1) * 4)) return 4;
+  D.sc_r = v; D.Cs_r = v + (b->N + 1); D.sc_w = v + 2 * (b->N + 1); D.Cs_w = v + 3 * (b->N + 1);
+  if (dev_alloc(&v, (size_t)2 * (2 * p->ndtfast + 4))) return 4;
+  D.w1 = v; D.w2 = v + (2 * p->ndtfast + 4);
+  if (dev_alloc(&D.P, D.nij * b->N)) return 4;
+  if (dev_alloc(&D.scratch2, D.nij * 8)) return 4;
+  c->nred_blocks = D.nj;
+  if (dev_alloc(&D.red, (size_t)3 * D.nj)) return 4;
+  if (dev_alloc(&D.ksbl, D.nij)) return 4;
+  CUDA_OK(cudaMallocHost((void**)&c->h_red, sizeof(double) * 3 * D.nj));
+  // initialise_mixing (mod_mixing.F:1430-1530) background values are the host's job (upload Akv,Akt,...)
+  c->iic = 0; c->ntfirst = 1; c->nstp = 1; c->nnew = 1; c->nrhs = 1; c->indx1 = 1; c->time = 0.0;
+  c->use_graph = (getenv("ROMS_B200_NO_GRAPH") == nullptr);
+  *out = c;
+  return 0;
+}
+
+int roms_b200_destroy(roms_b200_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (int a = 0; a < 12; ++a) if (c->graph2d[a]) cudaGraphExecDestroy(c->graph2d[a]);
+  for (int f = 0; f < ROMS_B200_NFIELDS; ++f) cudaFree(c->D.f[f]);
+  cudaFree((void*)c->D.sc_r); cudaFree((void*)c->D.w1); cudaFree(c->D.P); cudaFree(c->D.scratch2); cudaFree(c->D.red); cudaFree(c->D.ksbl);
+  cudaFreeHost(c->h_red);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int roms_b200_set_scoord(roms_b200_ctx* c, const double* sc_r, const double* Cs_r, const double* sc_w, const double* Cs_w) {
+  const int n = c->D.b.N + 1;   // host arrays are indexed k (sc_r[0], Cs_r[0] unused)
+  CUDA_OK(cudaMemcpy((void*)c->D.sc_r, sc_r, n * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy((void*)c->D.Cs_r, Cs_r, n * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy((void*)c->D.sc_w, sc_w, n * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy((void*)c->D.Cs_w, Cs_w, n * sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+int roms_b200_set_weights(roms_b200_ctx* c, int nfast, const double* w1, const double* w2) {
+  const int cap = 2 * c->D.p.ndtfast + 4;
+  if (nfast + 3 > cap) return 1;
+  std::vector<double> a(cap, 0.0), b(cap, 0.0);
+  for (int i = 0; i <= nfast + 2 && i < cap; ++i) { a[i] = w1[i]; b[i] = w2[i]; }
+  CUDA_OK(cudaMemcpy((void*)c->D.w1, a.data(), cap * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy((void*)c->D.w2, b.data(), cap * sizeof(double), cudaMemcpyHostToDevice));
+  c->D.p.nfast = nfast;
+  for (int x = 0; x < 12; ++x) if (c->graph2d[x]) { cudaGraphExecDestroy(c->graph2d[x]); c->graph2d[x] = nullptr; }
+  return 0;
+}
+
+long roms_b200_field_size(const roms_b200_ctx* c, int f) { return (f < 0 || f >= ROMS_B200_NFIELDS) ? -1 : (long)c->fsize[f]; }
+int roms_b200_upload(roms_b200_ctx* c, int f, const double* host) {
+  if (f < 0 || f >= ROMS_B200_NFIELDS) return 1;
+  CUDA_OK(cudaMemcpyAsync(c->D.f[f], host, c->fsize[f] * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int roms_b200_download(roms_b200_ctx* c, int f, double* host) {
+  if (f < 0 || f >= ROMS_B200_NFIELDS) return 1;
+  CUDA_OK(cudaMemcpyAsync(host, c->D.f[f], c->fsize[f] * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+void* roms_b200_device_ptr(roms_b200_ctx* c, int f) { return (f < 0 || f >= ROMS_B200_NFIELDS) ? nullptr : (void*)c->D.f[f]; }
+int roms_b200_sync(roms_b200_ctx* c) { CUDA_OK(cudaStreamSynchronize(c->stream)); CUDA_OK(cudaGetLastError()); return 0; }
+long roms_b200_launch_count(const roms_b200_ctx* c) { return c->launches; }
+
+#define ENTER(c) do { if (!(c)) return 1; CUDA_OK(cudaSetDevice((c)->device)); } while (0)
+#define LEAVE() do { CUDA_OK(cudaGetLastError()); return 0; } while (0)
+
+int roms_b200_set_massflux(roms_b200_ctx* c, int nrhs) { ENTER(c); k_set_massflux(c, nrhs); LEAVE(); }
+int roms_b200_rho_eos(roms_b200_ctx* c, int nrhs) { ENTER(c); k_rho_eos(c, nrhs); LEAVE(); }
+int roms_b200_omega(roms_b200_ctx* c) { ENTER(c); k_omega(c); LEAVE(); }
+int roms_b200_set_zeta(roms_b200_ctx* c) { ENTER(c); k_set_zeta(c); LEAVE(); }
+int roms_b200_set_depth(roms_b200_ctx* c) { ENTER(c); k_set_depth(c); LEAVE(); }
+int roms_b200_bulk_flux(roms_b200_ctx* c, int nrhs) { ENTER(c); k_bulk_flux(c, nrhs); LEAVE(); }
+int roms_b200_set_vbc(roms_b200_ctx* c, int nrhs) { ENTER(c); k_set_vbc(c, nrhs); LEAVE(); }
+int roms_b200_ana_vmix(roms_b200_ctx* c) { ENTER(c); k_ana_vmix(c); LEAVE(); }
+int roms_b200_lmd_vmix(roms_b200_ctx* c, int nstp) { ENTER(c); k_lmd_vmix(c, nstp); LEAVE(); }
+int roms_b200_pre_step3d(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntfirst) { ENTER(c); k_pre_step3d(c, nrhs, nstp, nnew, iic, ntfirst); LEAVE(); }
+int roms_b200_prsgrd(roms_b200_ctx* c, int nrhs) { ENTER(c); k_prsgrd(c, nrhs); LEAVE(); }
+int roms_b200_t3dmix2(roms_b200_ctx* c, int nrhs, int nstp, int nnew) { ENTER(c); k_t3dmix2(c, nrhs, nstp, nnew); LEAVE(); }
+int roms_b200_rhs3d_tile(roms_b200_ctx* c, int nrhs) { ENTER(c); k_rhs3d_tile(c, nrhs); LEAVE(); }
+int roms_b200_uv3dmix2(roms_b200_ctx* c, int nrhs, int nnew) { ENTER(c); k_uv3dmix2(c, nrhs, nnew); LEAVE(); }
+int roms_b200_rhs3d(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntfirst) {
+  ENTER(c);
+  k_pre_step3d(c, nrhs, nstp, nnew, iic, ntfirst); k_prsgrd(c, nrhs); k_t3dmix2(c, nrhs, nstp, nnew); k_rhs3d_tile(c, nrhs); k_uv3dmix2(c, nrhs, nnew);
+  LEAVE();
+}
+int roms_b200_step2d(roms_b200_ctx* c, int krhs, int kstp, int knew, int nstp, int nnew, int iif, int pred, int iic, int ntfirst) {
+  ENTER(c); k_step2d(c, krhs, kstp, knew, nstp, nnew, iif, pred, iic, ntfirst); LEAVE();
+}
+int roms_b200_step3d_uv(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntfirst) { ENTER(c); k_step3d_uv(c, nrhs, nstp, nnew, iic, ntfirst); LEAVE(); }
+int roms_b200_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew) { ENTER(c); k_step3d_t(c, nrhs, nstp, nnew); LEAVE(); }
+int roms_b200_diag(roms_b200_ctx* c, int nstp, double* out3) { ENTER(c); if (k_diag(c, nstp, out3)) return 1; LEAVE(); }
+int roms_b200_set_data(roms_b200_ctx* c, double tdays) { ENTER(c); k_set_data(c, tdays); LEAVE(); }
+
+// main3d.F:810-918: LF-AM3 fast loop.  The launch sequence depends only on
+// (indx1 at entry, which of the three AB start-up forms the first predictor
+// uses), so it is captured once per key and replayed as a CUDA graph.
+static int fast_loop_launch(roms_b200_ctx* c, int nstp, int nnew, int iic, int ntfirst, int* indx1_io) {
+  const int nfast = c->D.p.nfast;
+  int indx1 = *indx1_io, kstp = 1, knew = 1, krhs = 1, iif = 1; bool PRED = false;
+  for (int my_iif = 1; my_iif <= nfast + 1; ++my_iif) {
+    const int next_indx1 = 3 - indx1;
+    if (!PRED && my_iif <= nfast + 1) {
+      PRED = true; iif = my_iif;
+      kstp = (iif == 1) ? indx1 : 3 - indx1;
+      knew = 3; krhs = indx1;
+    }
+    if (my_iif <= nfast + 1) k_step2d(c, krhs, kstp, knew, nstp, nnew, iif, 1, iic, ntfirst);
+    if (PRED) {
+      PRED = false; knew = next_indx1; kstp = 3 - knew; krhs = 3;
+      if (iif < nfast + 1) indx1 = next_indx1;
+    }
+    if (iif < nfast + 1) k_step2d(c, krhs, kstp, knew, nstp, nnew, iif, 0, iic, ntfirst);
+  }
+  *indx1_io = indx1;
+  return 0;
+}
+int roms_b200_step2d_loop(roms_b200_ctx* c, int nstp, int nnew, int iic, int ntfirst, int* indx1) {
+  ENTER(c);
+  const int mode = (iic == ntfirst) ? 0 : (iic == ntfirst + 1 ? 1 : 2);
+  if (!c->use_graph) { if (fast_loop_launch(c, nstp, nnew, iic, ntfirst, indx1)) return 1; LEAVE(); }
+  // the launch sequence is a pure function of (indx1 at entry, nstp, AB start-up mode)
+  cudaGraphExec_t& ge = c->graph2d[((*indx1 - 1) & 1) * 6 + ((nstp - 1) & 1) * 3 + mode];
+  if (!ge) {
+    cudaGraph_t gph;
+    const long l0 = c->launches;
+    int tmp = *indx1;
+    CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    fast_loop_launch(c, nstp, nnew, iic, ntfirst, &tmp);
+    CUDA_OK(cudaStreamEndCapture(c->stream, &gph));
+    CUDA_OK(cudaGraphInstantiate(&ge, gph, 0));
+    CUDA_OK(cudaGraphDestroy(gph));
+    c->launches = l0;
+  }
+  CUDA_OK(cudaGraphLaunch(ge, c->stream));
+  c->launches += 2 * c->D.p.nfast + 1;
+  // advance indx1 exactly as the reference does: it flips once per completed sub-step pair
+  int x = *indx1;
+  for (int q = 0; q < c->D.p.nfast; ++q) x = 3 - x;
+  *indx1 = x;
+  LEAVE();
+}
+
+int roms_b200_get_stepping(const roms_b200_ctx* c, int* o, double* time) {
+  o[0] = c->iic; o[1] = c->ntfirst; o[2] = c->nstp; o[3] = c->nnew; o[4] = c->nrhs; o[5] = c->indx1; if (time) *time = c->time; return 0;
+}
+int roms_b200_set_stepping(roms_b200_ctx* c, const int* in, double time) {
+  c->iic = in[0]; c->ntfirst = in[1]; c->nstp = in[2]; c->nnew = in[3]; c->nrhs = in[4]; c->indx1 = in[5]; c->time = time; return 0;
+}
+
+// main3d.F:216-1148 on the device mirror (post_initial is the host's job: upload a state
+// that has been through ini_zeta/ini_fields, i.e. what the reference holds when the first
+// set_massflux is called).
+int roms_b200_main3d(roms_b200_ctx* c, int nsteps, int analytic_forcing, int with_diag) {
+  ENTER(c);
+  const bool bench = (c->D.p.app == ROMS_B200_APP_BENCHMARK);
+  for (int s = 0; s < nsteps; ++s) {
+    c->nstp = 1 + ((c->iic - c->ntfirst) % 2); c->nnew = 3 - c->nstp; c->nrhs = c->nstp;
+    const int nstp = c->nstp, nnew = c->nnew, nrhs = c->nrhs, iic = c->iic, ntf = c->ntfirst;
+    if (analytic_forcing) k_set_data(c, c->time / 86400.0);
+    k_set_massflux(c, nrhs); k_rho_eos(c, nrhs);
+    if (with_diag) { double d[3]; if (k_diag(c, nstp, d)) return 1; }
+    if (bench) k_bulk_flux(c, nrhs);
+    k_set_vbc(c, nrhs);
+    if (bench) k_lmd_vmix(c, nstp); else k_ana_vmix(c);
+    k_omega(c);
+    k_set_zeta(c);
+    k_pre_step3d(c, nrhs, nstp, nnew, iic, ntf); k_prsgrd(c, nrhs); k_t3dmix2(c, nrhs, nstp, nnew); k_rhs3d_tile(c, nrhs); k_uv3dmix2(c, nrhs, nnew);
+    if (roms_b200_step2d_loop(c, nstp, nnew, iic, ntf, &c->indx1)) return 1;
+    k_set_depth(c);
+    k_step3d_uv(c, nrhs, nstp, nnew, iic, ntf);
+    k_omega(c);
+    k_step3d_t(c, nrhs, nstp, nnew);
+    c->iic += 1; c->time += c->D.p.dt;
+  }
+  LEAVE();
+}
+
+int roms_b200_time_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int reps, float* ms_avg) {
+  ENTER(c);
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1));
+  CUDA_OK(cudaEventRecord(e0, c->stream));
+  for (int r = 0; r < reps; ++r) k_step3d_t(c, nrhs, nstp, nnew);
+  CUDA_OK(cudaEventRecord(e1, c->stream));
+  CUDA_OK(cudaEventSynchronize(e1));
+  float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_avg = ms / reps;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  LEAVE();
+}
+
+}  // extern "C"

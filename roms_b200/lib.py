@@ -1,0 +1,197 @@
+"""ctypes binding of libroms_b200.so (include/roms_b200.h).
+
+Fails loudly if the CUDA library is missing: there is no CPU fallback.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+APP_UPWELLING, APP_BENCHMARK = 0, 1
+
+
+def library_path():
+    return os.path.join(_HERE, "libroms_b200.so")
+
+
+def _field_names():
+    hdr = open(os.path.join(ROOT, "include", "roms_b200.h")).read()
+    block = hdr[hdr.index("#define ROMS_B200_FIELDS(X)"):hdr.index("enum roms_b200_field")]
+    return re.findall(r"X\((\w+),", block)
+
+
+FIELD_NAMES = _field_names()
+
+_BOUNDS_INTS = ("Lm Mm N NT NAT LBi UBi LBj UBj Istr Iend Jstr Jend IstrR IendR JstrR JendR IstrU JstrV "
+                "IstrP IendP JstrP JendP IstrT IendT JstrT JendT IstrB IendB JstrB JendB IstrM JstrM "
+                "Istrm3 Istrm2 Istrm1 IstrUm2 IstrUm1 Iendp1 Iendp2 Iendp2i Iendp3 "
+                "Jstrm3 Jstrm2 Jstrm1 JstrVm2 JstrVm1 Jendp1 Jendp2 Jendp2i Jendp3 "
+                "Western_Edge Eastern_Edge Southern_Edge Northern_Edge EWperiodic NSperiodic "
+                "NtileI NtileJ Itile Jtile").split()
+
+
+class Bounds(C.Structure):
+    _fields_ = [(n, C.c_int) for n in _BOUNDS_INTS]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n in _BOUNDS_INTS}
+
+
+class Params(C.Structure):
+    _fields_ = [("app", C.c_int), ("dt", C.c_double), ("dtfast", C.c_double), ("ndtfast", C.c_int), ("nfast", C.c_int),
+                ("rho0", C.c_double), ("g", C.c_double), ("gamma2", C.c_double), ("hc", C.c_double),
+                ("R0", C.c_double), ("T0", C.c_double), ("S0", C.c_double), ("Tcoef", C.c_double), ("Scoef", C.c_double),
+                ("Akt_bak", C.c_double * 2), ("Akv_bak", C.c_double),
+                ("blk_ZQ", C.c_double), ("blk_ZT", C.c_double), ("blk_ZW", C.c_double), ("dstart", C.c_double)]
+
+
+class Lib:
+    """Loaded libroms_b200.so with typed prototypes."""
+    _inst = None
+
+    def __init__(self):
+        path = library_path()
+        if not os.path.exists(path):
+            raise RuntimeError("roms_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)" % path)
+        L = self.L = C.CDLL(path)
+        vp, ci, cd = C.c_void_p, C.c_int, C.c_double
+        L.roms_b200_tile_bounds.argtypes = [ci] * 11 + [C.POINTER(Bounds)]
+        L.roms_b200_create.argtypes = [C.POINTER(Bounds), C.POINTER(Params), ci, C.POINTER(vp)]
+        L.roms_b200_destroy.argtypes = [vp]
+        L.roms_b200_set_scoord.argtypes = [vp] + [vp] * 4
+        L.roms_b200_set_weights.argtypes = [vp, ci, vp, vp]
+        L.roms_b200_field_id.argtypes = [C.c_char_p]
+        L.roms_b200_field_size.argtypes = [vp, ci]
+        L.roms_b200_field_size.restype = C.c_long
+        L.roms_b200_upload.argtypes = [vp, ci, vp]
+        L.roms_b200_download.argtypes = [vp, ci, vp]
+        L.roms_b200_device_ptr.argtypes = [vp, ci]
+        L.roms_b200_device_ptr.restype = vp
+        L.roms_b200_sync.argtypes = [vp]
+        L.roms_b200_launch_count.argtypes = [vp]
+        L.roms_b200_launch_count.restype = C.c_long
+        sig = {
+            "set_massflux": [ci], "rho_eos": [ci], "omega": [], "set_zeta": [], "set_depth": [], "bulk_flux": [ci],
+            "set_vbc": [ci], "ana_vmix": [], "lmd_vmix": [ci], "pre_step3d": [ci] * 5, "prsgrd": [ci], "t3dmix2": [ci] * 3,
+            "rhs3d_tile": [ci], "uv3dmix2": [ci] * 2, "rhs3d": [ci] * 5, "step2d": [ci] * 9, "step3d_uv": [ci] * 5,
+            "step3d_t": [ci] * 3, "set_data": [cd],
+        }
+        for name, args in sig.items():
+            getattr(L, "roms_b200_" + name).argtypes = [vp] + args
+        L.roms_b200_diag.argtypes = [vp, ci, vp]
+        L.roms_b200_step2d_loop.argtypes = [vp, ci, ci, ci, ci, C.POINTER(ci)]
+        L.roms_b200_main3d.argtypes = [vp, ci, ci, ci]
+        L.roms_b200_get_stepping.argtypes = [vp, vp, C.POINTER(cd)]
+        L.roms_b200_set_stepping.argtypes = [vp, vp, cd]
+        L.roms_b200_time_step3d_t.argtypes = [vp, ci, ci, ci, ci, C.POINTER(C.c_float)]
+
+    @classmethod
+    def get(cls):
+        if cls._inst is None:
+            cls._inst = Lib()
+        return cls._inst
+
+
+def tile_bounds(Lm, Mm, N, NT=2, NAT=2, NtileI=1, NtileJ=1, tile=0, EWperiodic=1, NSperiodic=0, distributed=0):
+    b = Bounds()
+    rc = Lib.get().L.roms_b200_tile_bounds(Lm, Mm, N, NT, NAT, NtileI, NtileJ, tile, EWperiodic, NSperiodic, distributed,
+                                           C.byref(b))
+    if rc:
+        raise ValueError("roms_b200_tile_bounds failed")
+    return b
+
+
+class Context:
+    """Device mirror + kernel entry points for one tile on one GPU."""
+
+    def __init__(self, bounds, params, device=0):
+        self.lib = Lib.get()
+        self.L = self.lib.L
+        self.bounds, self.params = bounds, params
+        h = C.c_void_p()
+        rc = self.L.roms_b200_create(C.byref(bounds), C.byref(params), device, C.byref(h))
+        if rc:
+            raise RuntimeError("roms_b200_create failed (rc=%d): a CUDA device is required" % rc)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.roms_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _chk(self, rc, what):
+        if rc:
+            raise RuntimeError("roms_b200_%s failed rc=%d" % (what, rc))
+
+    def fid(self, name):
+        f = self.L.roms_b200_field_id(name.encode())
+        if f < 0:
+            raise KeyError(name)
+        return f
+
+    def size(self, name):
+        return self.L.roms_b200_field_size(self.h, self.fid(name))
+
+    def upload(self, name, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64).ravel()
+        assert a.size == self.size(name), (name, a.size, self.size(name))
+        self._chk(self.L.roms_b200_upload(self.h, self.fid(name), a.ctypes.data), "upload")
+
+    def download(self, name, out=None):
+        if out is None:
+            out = np.empty(self.size(name))
+        self._chk(self.L.roms_b200_download(self.h, self.fid(name), out.ctypes.data), "download")
+        return out
+
+    def set_scoord(self, sc_r, Cs_r, sc_w, Cs_w):
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (sc_r, Cs_r, sc_w, Cs_w)]
+        self._chk(self.L.roms_b200_set_scoord(self.h, *[a.ctypes.data for a in arrs]), "set_scoord")
+
+    def set_weights(self, nfast, w1, w2):
+        w1 = np.ascontiguousarray(w1, dtype=np.float64)
+        w2 = np.ascontiguousarray(w2, dtype=np.float64)
+        self._chk(self.L.roms_b200_set_weights(self.h, nfast, w1.ctypes.data, w2.ctypes.data), "set_weights")
+
+    def call(self, name, *args):
+        self._chk(getattr(self.L, "roms_b200_" + name)(self.h, *args), name)
+
+    def sync(self):
+        self._chk(self.L.roms_b200_sync(self.h), "sync")
+
+    def diag(self, nstp):
+        out = np.zeros(3)
+        self._chk(self.L.roms_b200_diag(self.h, nstp, out.ctypes.data), "diag")
+        return out
+
+    def step2d_loop(self, nstp, nnew, iic, ntfirst, indx1):
+        x = C.c_int(indx1)
+        self._chk(self.L.roms_b200_step2d_loop(self.h, nstp, nnew, iic, ntfirst, C.byref(x)), "step2d_loop")
+        return x.value
+
+    def main3d(self, nsteps, analytic_forcing=1, with_diag=0):
+        self._chk(self.L.roms_b200_main3d(self.h, nsteps, analytic_forcing, with_diag), "main3d")
+
+    def get_stepping(self):
+        a = (C.c_int * 6)()
+        t = C.c_double()
+        self.L.roms_b200_get_stepping(self.h, a, C.byref(t))
+        return dict(zip(["iic", "ntfirst", "nstp", "nnew", "nrhs", "indx1"], list(a))), t.value
+
+    def set_stepping(self, iic, ntfirst, nstp, nnew, nrhs, indx1, time):
+        a = (C.c_int * 6)(iic, ntfirst, nstp, nnew, nrhs, indx1)
+        self.L.roms_b200_set_stepping(self.h, a, time)
+
+    def launches(self):
+        return self.L.roms_b200_launch_count(self.h)
+
+    def time_step3d_t(self, nrhs, nstp, nnew, reps):
+        ms = C.c_float()
+        self._chk(self.L.roms_b200_time_step3d_t(self.h, nrhs, nstp, nnew, reps, C.byref(ms)), "time_step3d_t")
+        return ms.value

@@ -1,0 +1,94 @@
+"""Shared plumbing of the parity tests: build an oracle Model and a roms_b200
+Context with identical configuration, move state between them, compare fields."""
+import ctypes as C
+
+import numpy as np
+
+import oracle_lib as ol
+import roms_b200 as rb
+
+# oracle phase -> (C-ABI entry point, argument builder from the oracle's stepping dict)
+GPU_PHASE = {
+    "set_massflux": ("set_massflux", lambda s: (s["nrhs"],)),
+    "rho_eos": ("rho_eos", lambda s: (s["nrhs"],)),
+    "bulk_flux": ("bulk_flux", lambda s: (s["nrhs"],)),
+    "set_vbc": ("set_vbc", lambda s: (s["nrhs"],)),
+    "omega": ("omega", lambda s: ()),
+    "set_zeta": ("set_zeta", lambda s: ()),
+    "pre_step3d": ("pre_step3d", lambda s: (s["nrhs"], s["nstp"], s["nnew"], s["iic"], s["ntfirst"])),
+    "prsgrd": ("prsgrd", lambda s: (s["nrhs"],)),
+    "t3dmix2": ("t3dmix2", lambda s: (s["nrhs"], s["nstp"], s["nnew"])),
+    "rhs3d_tile": ("rhs3d_tile", lambda s: (s["nrhs"],)),
+    "uv3dmix2": ("uv3dmix2", lambda s: (s["nrhs"], s["nnew"])),
+    "set_depth": ("set_depth", lambda s: ()),
+    "step3d_uv": ("step3d_uv", lambda s: (s["nrhs"], s["nstp"], s["nnew"], s["iic"], s["ntfirst"])),
+    "omega2": ("omega", lambda s: ()),
+    "step3d_t": ("step3d_t", lambda s: (s["nrhs"], s["nstp"], s["nnew"])),
+}
+# kernels that call exp/log/pow: device libm vs glibc differ by a few ulp
+TRANSCENDENTAL = {"vmix", "bulk_flux"}
+FORCING_FIELDS = ["srflx", "sustr", "svstr", "stflux", "btflux", "cloud", "Tair", "Hair", "Pair", "rain", "Uwind", "Vwind"]
+PROGNOSTIC = ["zeta", "ubar", "vbar", "u", "v", "t"]
+
+
+def make_params(o):
+    d, sc, c = o.dims(), o.scalars(), None
+    p = rb.Params()
+    p.app = o.app
+    p.dt, p.dtfast, p.ndtfast, p.nfast = sc["dt"], sc["dtfast"], d["ndtfast"], d["nfast"]
+    p.rho0, p.g, p.gamma2, p.hc = 1025.0, 9.81, 1.0, sc["hc"]
+    if o.app == ol.UPWELLING:
+        p.R0, p.T0, p.S0, p.Tcoef, p.Scoef = 1027.0, 14.0, 35.0, 1.7e-4, 0.0
+        p.Akt_bak[0] = p.Akt_bak[1] = 1.0e-6
+        p.Akv_bak = 1.0e-5
+    else:
+        p.R0, p.T0, p.S0, p.Tcoef, p.Scoef = 1027.0, 10.0, 35.0, 1.7e-4, 7.6e-4
+        p.Akt_bak[0] = p.Akt_bak[1] = 1.0e-5
+        p.Akv_bak = 1.0e-4
+    p.blk_ZQ = p.blk_ZT = p.blk_ZW = 10.0
+    p.dstart = 0.0
+    return p
+
+
+def make_pair(app, Lm=0, Mm=0, N=0, device=0, dt=None, ndtfast=None):
+    """Oracle (1x1 tiling) + GPU context for the same configuration; oracle initialised."""
+    o = ol.Oracle(app, Lm, Mm, N, dt=dt, ndtfast=ndtfast)
+    o.initial()
+    d = o.dims()
+    b = rb.tile_bounds(d["Lm"], d["Mm"], d["N"], d["NT"], d["NAT"])
+    assert (b.LBi, b.UBi, b.LBj, b.UBj) == (d["LBi"], d["UBi"], d["LBj"], d["UBj"])
+    ctx = rb.Context(b, make_params(o), device)
+    ctx.set_scoord(o.vec("sc_r"), o.vec("Cs_r"), o.vec("sc_w"), o.vec("Cs_w"))
+    ctx.set_weights(d["nfast"], o.vec("weight1"), o.vec("weight2"))
+    return o, ctx
+
+
+def push(o, ctx, names=None):
+    for n in (names or rb.FIELD_NAMES):
+        ctx.upload(n, o.get(n))
+
+
+def diff_fields(o, ctx, names=None):
+    """max |gpu-oracle| and the scale max|oracle| per field."""
+    out = {}
+    for n in (names or rb.FIELD_NAMES):
+        a, g = o.get(n), ctx.download(n)
+        out[n] = (float(np.max(np.abs(a - g))) if a.size else 0.0, float(np.max(np.abs(a))) if a.size else 0.0,
+                  bool(np.array_equal(a, g)))
+    return out
+
+
+def run_phase_gpu(o, ctx, ph):
+    s = o.stepping()
+    if ph == "vmix":
+        if o.app == ol.BENCHMARK:
+            ctx.call("lmd_vmix", s["nstp"])
+        else:
+            ctx.call("ana_vmix")
+    elif ph == "step2d_loop":
+        return ctx.step2d_loop(s["nstp"], s["nnew"], s["iic"], s["ntfirst"], s["indx1"])
+    else:
+        name, argf = GPU_PHASE[ph]
+        ctx.call(name, *argf(s))
+    ctx.sync()
+    return None

@@ -1,0 +1,127 @@
+"""GPU parity tests: every kernel of the main3d path, called through the C ABI of
+libroms_b200.so, against the CPU restatement (oracle/) on identical inputs.
+
+Bar: bit-exact (np.array_equal over the WHOLE array including halos) for the
+kernels without transcendental functions; 1e-12 relative (scaled by the field's
+max-abs) for KPP / bulk fluxes / analytical mixing, which call exp/log/pow whose
+device and glibc implementations differ by a few ulp.  Whole-loop: prognostic
+fields within 1e-10 relative after 100 baroclinic steps (BASELINE.json target).
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import roms_b200 as rb
+from parity_common import (GPU_PHASE, TRANSCENDENTAL, PROGNOSTIC, FORCING_FIELDS, make_pair, push, diff_fields,
+                           run_phase_gpu)
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("upwelling", ol.UPWELLING, 0, 0, 0), ("benchmark_small", ol.BENCHMARK, 96, 40, 30)]
+
+
+def _check_phase(o, ctx, ph, bitwise):
+    bad = []
+    for n, (dmax, scale, eq) in diff_fields(o, ctx).items():
+        if bitwise:
+            if not eq:
+                bad.append((n, dmax, scale))
+        elif dmax > 1e-12 * max(scale, 1e-300):
+            bad.append((n, dmax, scale))
+    assert not bad, "phase %s: fields differ from the oracle: %s" % (ph, bad)
+
+
+@pytest.mark.parametrize("name,app,Lm,Mm,N", CASES)
+def test_every_kernel_matches_oracle(name, app, Lm, Mm, N):
+    """Stop the oracle between every two tile loops of main3d for the first 4 steps
+    (covers the three AB start-up forms), push its state, run ONE kernel, compare all fields."""
+    o, ctx = make_pair(app, Lm, Mm, N)
+    for step in range(4):
+        for ph in ol.PHASES:
+            gpu = ph in GPU_PHASE or ph in ("vmix", "step2d_loop")
+            if ph == "bulk_flux" and app != ol.BENCHMARK:
+                gpu = False
+            if gpu:
+                push(o, ctx)
+                indx1 = run_phase_gpu(o, ctx, ph)
+            o.phase(ph)
+            if gpu:
+                bitwise = ph not in TRANSCENDENTAL and not (ph == "pre_step3d" and app == ol.BENCHMARK)
+                _check_phase(o, ctx, ph, bitwise)
+                if ph == "step2d_loop":
+                    assert indx1 == o.stepping()["indx1"]
+    ctx.close()
+
+
+@pytest.mark.parametrize("name,app,Lm,Mm,N,nsteps", [("upwelling", ol.UPWELLING, 0, 0, 0, 100),
+                                                    ("benchmark_small", ol.BENCHMARK, 96, 40, 30, 100)])
+def test_100_steps_prognostic_fields(name, app, Lm, Mm, N, nsteps):
+    """Device-resident main3d loop (forcing evaluated on the device) vs the oracle after 100 steps:
+    zeta,u,v,T,S within 1e-10 relative (max-norm scaled by the field's range)."""
+    o, ctx = make_pair(app, Lm, Mm, N)
+    o.phase("begin")
+    push(o, ctx)
+    s = o.stepping()
+    ctx.set_stepping(s["iic"], s["ntfirst"], s["nstp"], s["nnew"], s["nrhs"], s["indx1"], o.scalars()["time"])
+    for ph in ol.PHASES[1:]:
+        o.phase(ph)
+    ctx.main3d(1, analytic_forcing=0)
+    o.step(nsteps - 1)
+    ctx.main3d(nsteps - 1, analytic_forcing=1)
+    ctx.sync()
+    st, tm = ctx.get_stepping()
+    assert st["iic"] == o.stepping()["iic"] and st["indx1"] == o.stepping()["indx1"]
+    bad = []
+    for n in PROGNOSTIC:
+        a, g = o.get(n), ctx.download(n)
+        rng = float(a.max() - a.min())
+        rel = float(np.max(np.abs(a - g))) / max(rng, 1e-300)
+        if not rel <= 1e-10:
+            bad.append((n, rel))
+    assert not bad, bad
+    ctx.close()
+
+
+def test_bitwise_loop_with_host_forcing():
+    """UPWELLING has no transcendental kernel on the device when forcing comes from the host:
+    20 full steps must then be BIT-IDENTICAL to the oracle (ana_vmix's exp is time-independent
+    only through z_w, so Akv is pushed from the oracle each step)."""
+    o, ctx = make_pair(ol.UPWELLING)
+    o.phase("begin")
+    push(o, ctx)
+    s = o.stepping()
+    ctx.set_stepping(s["iic"], s["ntfirst"], s["nstp"], s["nnew"], s["nrhs"], s["indx1"], o.scalars()["time"])
+    for step in range(20):
+        if step > 0:
+            o.phase("begin")
+            push(o, ctx, FORCING_FIELDS)
+        s = o.stepping()
+        # GPU: same sequence as roms_b200_main3d, with Akv taken from the oracle after its vmix phase
+        ctx.call("set_massflux", s["nrhs"]); ctx.call("rho_eos", s["nrhs"]); ctx.call("set_vbc", s["nrhs"])
+        for ph in ol.PHASES[1:7]:
+            o.phase(ph)
+        push(o, ctx, ["Akv", "Akt"])
+        ctx.call("omega"); ctx.call("set_zeta")
+        ctx.call("rhs3d", s["nrhs"], s["nstp"], s["nnew"], s["iic"], s["ntfirst"])
+        indx1 = ctx.step2d_loop(s["nstp"], s["nnew"], s["iic"], s["ntfirst"], s["indx1"])
+        ctx.call("set_depth"); ctx.call("step3d_uv", s["nrhs"], s["nstp"], s["nnew"], s["iic"], s["ntfirst"])
+        ctx.call("omega"); ctx.call("step3d_t", s["nrhs"], s["nstp"], s["nnew"])
+        ctx.sync()
+        for ph in ol.PHASES[7:]:
+            o.phase(ph)
+        assert indx1 == o.stepping()["indx1"]
+    bad = [n for n, (d, sc, eq) in diff_fields(o, ctx, PROGNOSTIC + ["Huon", "Hvom", "W", "ru", "rv", "Zt_avg1"]).items() if not eq]
+    assert not bad, bad
+    ctx.close()
+
+
+def test_diag_reductions():
+    o, ctx = make_pair(ol.BENCHMARK, 96, 40, 30)
+    o.step(3)
+    o.phase("begin"); o.phase("set_massflux"); o.phase("rho_eos")
+    push(o, ctx)
+    o.phase("diag")
+    d = ctx.diag(o.stepping()["nstp"])
+    sc = o.scalars()
+    np.testing.assert_allclose(d, [sc["avgke"], sc["avgpe"], sc["volume"]], rtol=1e-12)
+    ctx.close()
