@@ -1,0 +1,196 @@
+#!/usr/bin/env python
+"""bench.py -- baroclinic-step throughput of the roms_b200 main3d path.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...          # the reference's own CPU algorithm (oracle port)
+
+Metric (BASELINE.json): 3-D cell-updates/s of the baroclinic step = Lm*Mm*N*K / time(K steps of main3d),
+workload BENCHMARK1 (512x64x30, full main3d loop: EOS, KPP, bulk fluxes, 59 barotropic sub-steps, ...).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "3D cell-updates/sec (baroclinic step)"
+UNIT = "cell-updates/s"
+WORKLOADS = {"BENCHMARK1": (512, 64, 30), "BENCHMARK2": (1024, 128, 30), "BENCHMARK3": (2048, 256, 30)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.p, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(workload, nsteps, warm=1):
+    """The oracle (CPU restatement of the reference algorithm, kind="port") on this box's host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    Lm, Mm, N = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    nti, ntj = 1, 1
+    while nti * ntj < cores:            # tiles = host threads, like the reference's NtileI*NtileJ = cores
+        if nti <= ntj * 4:
+            nti *= 2
+        else:
+            ntj *= 2
+    o = ol.Oracle(ol.BENCHMARK, Lm, Mm, N, NtileI=nti, NtileJ=ntj)
+    o.set_threads(cores)
+    o.initial()
+    o.step(warm)
+    t0 = time.perf_counter()
+    o.step(nsteps)
+    dt = time.perf_counter() - t0
+    return {"value": Lm * Mm * N * nsteps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d baroclinic steps of %s (%dx%dx%d), %dx%d tiles on %d threads, %.2f s" % (nsteps, workload, Lm, Mm, N, nti, ntj, cores, dt)}, dt / nsteps
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cb, sps = cpu_baseline(args.workload, args.steps, max(1, min(args.warmup, 2)))
+    Lm, Mm, N = WORKLOADS[args.workload]
+    line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (analytical BENCHMARK grid/initial state/forcing)", "impl": "reference",
+            "config": {"workload": "%s %dx%dx%d full main3d loop" % (args.workload, Lm, Mm, N)},
+            "cpu_baseline": cb, "gpu_launches": 0,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def roofline_step3d_t(rb, peak, peak_kind):
+    """step3d_t on a grid whose working set is >> L2 (126 MB): 96 B algorithmic per cell per call (NT=2)."""
+    Lm, Mm, N = 1024, 512, 50
+    cfg = rb.default_config(rb.APP_BENCHMARK, Lm, Mm, N)
+    cfg.dt, cfg.ndtfast = 20.0, 20          # smaller DT for the finer synthetic grid (arithmetic unchanged)
+    d = rb.Driver(cfg)
+    d.run(3)                                # non-degenerate state (upwind branches active)
+    st, _ = d.ctx.get_stepping()
+    d.ctx.time_step3d_t(st["nrhs"], st["nstp"], st["nnew"], 3)
+    ms = d.ctx.time_step3d_t(st["nrhs"], st["nstp"], st["nnew"], 20)
+    cells = Lm * Mm * N
+    achieved = 96.0 * cells / (ms * 1e-3) / 1e9
+    d.finalize()
+    return {"bound": "hbm", "kernel": "step3d_t_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_kind": peak_kind, "traffic": None, "grid": "%dx%dx%d (t working set %.1f GB >> L2)" % (Lm, Mm, N, 6 * cells * 8 / 1e9),
+            "ms_per_launch": ms, "cell_updates_per_s": cells / (ms * 1e-3), "algorithmic_bytes_per_cell": 96}
+
+
+def run_ours(args, rank, world):
+    import roms_b200 as rb
+    if world > 1:
+        raise SystemExit("multi-GPU bench path not implemented in this revision")
+    Lm, Mm, N = WORKLOADS[args.workload]
+    cfg = rb.default_config(rb.APP_BENCHMARK, Lm, Mm, N)
+    d = rb.Driver(cfg, device=0)
+    cells = Lm * Mm * N
+    # ---- device-resident throughput (inputs already in HBM, forcing evaluated on the device)
+    d.run(max(args.warmup, 3))
+    l0 = d.ctx.launches()
+    clk = ClockSampler(0)
+    clk.start()
+    d.ctx.sync()
+    d.timer_start()
+    d.run(args.steps)
+    ms = d.timer_stop()
+    clocks = clk.stop()
+    launches = d.ctx.launches() - l0
+    value = cells * args.steps / (ms * 1e-3)
+    # ---- end to end through the driver surface with HOST buffers: per step the host evaluates
+    # set_data (ana_srflux), uploads it (H2D), runs main3d, and reads the diag scalars back (D2H)
+    d.run(2, host_forcing=True)
+    d.ctx.sync()
+    t0 = time.perf_counter()
+    diag = d.run(args.steps, host_forcing=True)
+    d.ctx.sync()
+    e2e_s = time.perf_counter() - t0
+    ni, nj = cfg.Lm + 6 + (0 if cfg.Lm % 2 else 0), cfg.Mm + 3
+    b = rb.tile_bounds(Lm, Mm, N)
+    ni, nj = b.UBi - b.LBi + 1, b.UBj - b.LBj + 1
+    e2e = {"value": cells * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ni * nj * 8, "d2h_bytes_per_step": 3 * nj * 8,
+           "ms_per_step": 1e3 * e2e_s / args.steps, "last_diag": {"avgke": diag[0], "avgpe": diag[1], "volume": diag[2]}}
+    d.finalize()
+    peak, peak_kind = measured_peak()
+    roof = roofline_step3d_t(rb, peak, peak_kind) if not args.no_roofline else None
+    cb = None
+    if not args.no_cpu:
+        cb, _ = cpu_baseline(args.workload, args.cpu_steps)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (analytical BENCHMARK grid/initial state/forcing, random-free)",
+            "config": {"workload": "%s %dx%dx%d full main3d loop (rho_eos, bulk_flux, KPP, %d step2d sub-steps, rhs3d, step3d_uv, step3d_t)"
+                       % (args.workload, Lm, Mm, N, 2 * d.nfast + 1), "tiles": "1x1", "l2": "state 0.3 GB per step > 126 MB L2, no explicit flush",
+                       "fmad": "false (parity build)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="BENCHMARK1", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

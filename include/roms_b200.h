@@ -156,6 +156,39 @@ long roms_b200_launch_count(const roms_b200_ctx* ctx);
 /* average device time (ms) of the last `roms_b200_time_kernel` call */
 int roms_b200_time_step3d_t(roms_b200_ctx* ctx, int nrhs, int nstp, int nnew, int reps, float* ms_avg);
 
+/* CUDA-event stopwatch on the context's launch stream, and an L2 flush (writes `mbytes` MiB) */
+int roms_b200_timer_start(roms_b200_ctx* ctx);
+int roms_b200_timer_stop(roms_b200_ctx* ctx, float* ms);
+int roms_b200_flush_l2(roms_b200_ctx* ctx, int mbytes);
+
+/* ---- start-up helpers on the device mirror */
+int roms_b200_fill(roms_b200_ctx* ctx, int field, double value);       /* mod_*.F initialisation values */
+int roms_b200_ana_initial(roms_b200_ctx* ctx);                         /* Functionals/ana_initial.h */
+int roms_b200_ini_fields(roms_b200_ctx* ctx, int nstp, int kstp);      /* Nonlinear/ini_fields.F (ini_zeta + ini_fields) */
+
+/* ---- driver surface of Master/roms_kernel.F -> Drivers/nl_roms.h for the analytical applications
+ * (host side written in C++ because no Fortran compiler exists in the build image; a Fortran ROMS
+ * keeps its own ROMS_initialize/run/finalize and only binds the kernel entry points above). */
+typedef struct roms_b200_config {       /* roms_*.in values (Utility/read_phypar.F keywords) */
+  int app, Lm, Mm, N, NT, NAT, NtileI, NtileJ;
+  double dt; int ndtfast;
+  double theta_s, theta_b, Tcline;
+  double rho0, g, gamma2, rdrg, rdrg2;
+  double Akt_bak[2], Akv_bak, tnu2[2], visc2;
+  double R0, T0, S0, Tcoef, Scoef;
+  double blk_ZQ, blk_ZT, blk_ZW; int lmd_Jwt;
+} roms_b200_config;
+typedef struct roms_b200_driver roms_b200_driver;
+void roms_b200_default_config(int app, int Lm, int Mm, int N, roms_b200_config* cfg);   /* roms_upwelling.in / roms_benchmark1.in */
+void roms_b200_host_scoord(int N, double theta_s, double theta_b, double* sc_r, double* Cs_r, double* sc_w, double* Cs_w); /* set_scoord.F */
+int roms_b200_host_weights(int ndtfast, double* weight1, double* weight2);              /* set_weights.F; returns nfast */
+int roms_b200_ROMS_initialize(const roms_b200_config* cfg, int tile, int distributed, int device, roms_b200_driver** out); /* nl_roms.h:61 */
+int roms_b200_ROMS_run(roms_b200_driver* drv, int nsteps, int host_forcing, double* diag3);                                 /* nl_roms.h:247 */
+int roms_b200_ROMS_finalize(roms_b200_driver* drv);                                                                         /* nl_roms.h:320 */
+roms_b200_ctx* roms_b200_driver_ctx(roms_b200_driver* drv);
+void roms_b200_driver_bounds(roms_b200_driver* drv, roms_b200_bounds* b);
+int roms_b200_driver_nfast(roms_b200_driver* drv);
+
 #ifdef __cplusplus
 }
 #endif

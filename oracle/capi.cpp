@@ -16,6 +16,7 @@ void* orc_create(int app, int Lm, int Mm, int N, int NtileI, int NtileJ) {
 }
 void orc_destroy(void* h) { delete (Model*)h; }
 void orc_set_dt(void* h, double dt, int ndtfast) { Model* M = (Model*)h; M->c.dt = dt; M->c.ndtfast = ndtfast; }
+void orc_set_threads(void* h, int n) { ((Model*)h)->nthreads = n; }
 void orc_initial(void* h) { initial(*(Model*)h); }
 void orc_step(void* h, int n) { for (int i = 0; i < n; ++i) main3d_step(*(Model*)h); }
 int orc_phase(void* h, const char* ph) { try { main3d_phase(*(Model*)h, ph); } catch (...) { return 1; } return 0; }

@@ -3,6 +3,7 @@
 #include "oracle.h"
 #include <algorithm>
 #include <stdexcept>
+#include <thread>
 
 namespace orc {
 
@@ -372,8 +373,18 @@ void initial(Model& M) {
 // One baroclinic step, Nonlinear/main3d.F:216-1148, as named phases so that a
 // test can stop between any two reference tile loops.
 void main3d_phase(Model& M, const std::string& ph) {
-  auto fwd = [&](auto fn) { for (size_t t = 0; t < M.tiles.size(); ++t) fn(M.tiles[t]); };
-  auto rev = [&](auto fn) { for (size_t t = M.tiles.size(); t-- > 0;) fn(M.tiles[t]); };
+  // Tile loops.  With nthreads>1 the tiles of one loop run concurrently and the
+  // loop end is the barrier -- the reference's shared-memory (OpenMP) mode,
+  // Drivers/nl_roms.h:304-310 + main3d.F `!$OMP BARRIER` between tile loops.
+  auto par = [&](auto fn) {
+    const int nt = std::min<int>(M.nthreads, (int)M.tiles.size());
+    std::vector<std::thread> th;
+    for (int w = 0; w < nt; ++w)
+      th.emplace_back([&, w]() { for (size_t t = w; t < M.tiles.size(); t += nt) fn(M.tiles[t]); });
+    for (auto& x : th) x.join();
+  };
+  auto fwd = [&](auto fn) { if (M.nthreads > 1) { par(fn); return; } for (size_t t = 0; t < M.tiles.size(); ++t) fn(M.tiles[t]); };
+  auto rev = [&](auto fn) { if (M.nthreads > 1) { par(fn); return; } for (size_t t = M.tiles.size(); t-- > 0;) fn(M.tiles[t]); };
   if (ph == "begin") {
     M.nstp = 1 + ((M.iic - M.ntstart) % 2); M.nnew = 3 - M.nstp; M.nrhs = M.nstp;   // main3d.F:222-224
     M.tdays = M.time / 86400.0;

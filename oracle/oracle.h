@@ -139,6 +139,7 @@ struct Model {
   double time = 0.0, tdays = 0.0;
   // diagnostics (Nonlinear/diag.F)
   double avgke = 0, avgpe = 0, volume = 0;
+  int nthreads = 1;   // >1: tiles of one tile loop run concurrently (reference's OpenMP mode)
 
   // grid (mod_grid)
   F2 h, f, fomn, pm, pn, om_r, on_r, om_u, on_u, om_v, on_v, om_p, on_p;

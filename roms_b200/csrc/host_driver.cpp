@@ -1,0 +1,329 @@
+// roms_b200/csrc/host_driver.cpp -- host side above the C ABI.
+//
+// The reference host is Fortran (Master/roms_kernel.F -> Drivers/nl_roms.h:
+// ROMS_initialize / ROMS_run / ROMS_finalize); no Fortran compiler exists in
+// this image, so the same driver surface is written here in C++ for the two
+// analytical applications (UPWELLING, BENCHMARK).  It does what the Fortran
+// host does around the kernels and nothing on the hot path itself:
+//   ROMS_initialize : inp_par values, set_scoord, set_weights, ana_grid, metrics,
+//                     ini_hmixcoef (2-D, on the host) -> upload; then the 3-D
+//                     start-up sequence of Nonlinear/initial.F on the device.
+//   ROMS_run        : main3d loop; per step the host evaluates set_data's ana_*
+//                     forcing (2-D) into pinned memory, uploads it, launches the
+//                     step and reads back the diag scalars (NINFO=1).
+//   ROMS_finalize   : release.
+// Compiled by g++ (needs __float128 for set_weights' real(r16) sums).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include "../../include/roms_b200.h"
+
+namespace {
+const double pi = 3.14159265358979323846, deg2rad = pi / 180.0, Eradius = 6371315.0, Cp = 3985.0, Csolar = 1353.0;
+
+struct H2 {   // host 2-D field with Fortran bounds
+  std::vector<double> d; int LBi, ni, LBj, nj;
+  void init(const roms_b200_bounds& b) { LBi = b.LBi; ni = b.UBi - b.LBi + 1; LBj = b.LBj; nj = b.UBj - b.LBj + 1; d.assign((size_t)ni * nj, 0.0); }
+  double& operator()(int i, int j) { return d[(i - LBi) + (size_t)ni * (j - LBj)]; }
+};
+}  // namespace
+
+struct roms_b200_driver {
+  roms_b200_config cfg;
+  roms_b200_bounds b;
+  roms_b200_params p;
+  roms_b200_ctx* ctx;
+  H2 lonr, latr, srflx, sustr, svstr;
+  std::vector<double> sc_r, Cs_r, sc_w, Cs_w, w1, w2;
+  int nfast;
+  double last_diag[3];
+};
+
+extern "C" {
+
+void roms_b200_default_config(int app, int Lm, int Mm, int N, roms_b200_config* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->app = app; c->NtileI = 1; c->NtileJ = 1; c->NT = 2; c->NAT = 2;
+  c->rho0 = 1025.0; c->g = 9.81; c->gamma2 = 1.0; c->rdrg = 3.0e-4; c->rdrg2 = 3.0e-3; c->R0 = 1027.0; c->S0 = 35.0; c->Tcoef = 1.7e-4;
+  c->blk_ZQ = c->blk_ZT = c->blk_ZW = 10.0; c->lmd_Jwt = 1;
+  if (app == ROMS_B200_APP_UPWELLING) {      // roms_upwelling.in
+    c->Lm = Lm > 0 ? Lm : 41; c->Mm = Mm > 0 ? Mm : 80; c->N = N > 0 ? N : 16;
+    c->dt = 300.0; c->ndtfast = 30; c->theta_s = 3.0; c->theta_b = 0.0; c->Tcline = 25.0;
+    c->Akt_bak[0] = c->Akt_bak[1] = 1.0e-6; c->Akv_bak = 1.0e-5; c->tnu2[0] = c->tnu2[1] = 0.0; c->visc2 = 5.0;
+    c->T0 = 14.0; c->Scoef = 0.0;
+  } else {                                   // roms_benchmark1.in
+    c->Lm = Lm; c->Mm = Mm; c->N = N;
+    c->dt = 150.0; c->ndtfast = 20; c->theta_s = 0.0; c->theta_b = 0.0; c->Tcline = 400.0;
+    c->Akt_bak[0] = c->Akt_bak[1] = 1.0e-5; c->Akv_bak = 1.0e-4; c->tnu2[0] = c->tnu2[1] = 500.0; c->visc2 = 5000.0;
+    c->T0 = 10.0; c->Scoef = 7.6e-4;
+  }
+}
+
+// Utility/set_scoord.F:165-178,393-433 (Vtransform=2, Vstretching=4); arrays indexed k = 0..N
+void roms_b200_host_scoord(int N, double theta_s, double theta_b, double* sc_r, double* Cs_r, double* sc_w, double* Cs_w) {
+  const double ds = 1.0 / (double)N;
+  auto stretch = [&](double s) {
+    double Csur = (theta_s > 0.0) ? (1.0 - std::cosh(theta_s * s)) / (std::cosh(theta_s) - 1.0) : -(s * s);
+    return (theta_b > 0.0) ? (std::exp(theta_b * Csur) - 1.0) / (1.0 - std::exp(-theta_b)) : Csur;
+  };
+  sc_w[N] = 0.0; Cs_w[N] = 0.0; sc_w[0] = -1.0; Cs_w[0] = -1.0; sc_r[0] = 0.0; Cs_r[0] = 0.0;
+  for (int k = N - 1; k >= 1; --k) { sc_w[k] = ds * (double)(k - N); Cs_w[k] = stretch(sc_w[k]); }
+  for (int k = 1; k <= N; ++k) { sc_r[k] = ds * ((double)(k - N) - 0.5); Cs_r[k] = stretch(sc_r[k]); }
+}
+
+// Utility/set_weights.F:47-195 (POWER_LAW); w1,w2 sized >= 2*ndtfast+2, 1-based
+int roms_b200_host_weights(int ndtfast, double* w1, double* w2) {
+  typedef __float128 q;
+  const double Falpha = 2.0, Fbeta = 4.0, Fgamma = 0.284;
+  const int n2 = 2 * ndtfast;
+  for (int i = 0; i <= n2 + 1; ++i) { w1[i] = 0.0; w2[i] = 0.0; }
+  int nfast = 0;
+  double scale = (Falpha + 1.0) * (Falpha + Fbeta + 1.0) / ((Falpha + 2.0) * (Falpha + Fbeta + 2.0) * (double)ndtfast);
+  const double gamma = Fgamma * std::max(0.0, 1.0 - 10.0 / (double)ndtfast);
+  for (int iter = 1; iter <= 16; ++iter) {
+    nfast = 0;
+    for (int i = 1; i <= n2; ++i) {
+      const q x = (q)scale * (q)(double)i, x2 = x * x;
+      w1[i] = (double)(x2 - x2 * x2 * x2 - (q)gamma * x);
+      if (w1[i] > 0.0) nfast = i;
+      if (nfast > 0 && w1[i] < 0.0) w1[i] = 0.0;
+    }
+    q wsum = 0, shift = 0;
+    for (int i = 1; i <= nfast; ++i) { wsum = wsum + (q)w1[i]; shift = shift + (q)w1[i] * (q)(double)i; }
+    scale = (double)((q)scale * shift / (wsum * (q)(double)ndtfast));
+  }
+  for (int iter = 1; iter <= ndtfast; ++iter) {
+    q wsum = 0, shift = 0;
+    for (int i = 1; i <= nfast; ++i) { wsum = wsum + (q)w1[i]; shift = shift + (q)(double)i * (q)w1[i]; }
+    shift = shift / wsum;
+    const q cff = (q)(double)ndtfast - shift;
+    if (cff > (q)1.0) { nfast += 1; for (int i = nfast; i >= 2; --i) w1[i] = w1[i - 1]; w1[1] = 0.0; }
+    else if (cff > (q)0.0) { const q ws = (q)1.0 - cff; for (int i = nfast; i >= 2; --i) w1[i] = (double)(ws * (q)w1[i] + cff * (q)w1[i - 1]); w1[1] = (double)(ws * (q)w1[1]); }
+    else if (cff < (q)(-1.0)) { nfast -= 1; for (int i = 1; i <= nfast; ++i) w1[i] = w1[i + 1]; w1[nfast + 1] = 0.0; }
+    else if (cff < (q)0.0) { const q ws = (q)1.0 + cff; for (int i = 1; i <= nfast - 1; ++i) w1[i] = (double)(ws * (q)w1[i] - cff * (q)w1[i + 1]); w1[nfast] = (double)(ws * (q)w1[nfast]); }
+  }
+  for (int j = 1; j <= nfast; ++j) { const q c = (q)w1[j]; for (int i = 1; i <= j; ++i) w2[i] = (double)((q)w2[i] + c); }
+  q wsum = 0, cs = 0;
+  for (int i = 1; i <= nfast; ++i) { wsum = wsum + (q)w1[i]; cs = cs + (q)w2[i]; }
+  wsum = (q)1.0 / wsum; cs = (q)1.0 / cs;
+  for (int i = 1; i <= nfast; ++i) { w1[i] = (double)(wsum * (q)w1[i]); w2[i] = (double)(cs * (q)w2[i]); }
+  return nfast;
+}
+
+}  // extern "C"
+
+namespace {
+// caldate for time_ref=0 (Utility/dateclock.F): day-of-year and hour for ana_srflux
+double ufloor_(double X) { return X - std::fmod(X, 1.0) - std::fmod(2.0 + std::copysign(1.0, X), 3.0); }
+double tfloor_(double X, double CT) {
+  double Q = 1.0; if (X < 0.0) Q = 1.0 - CT;
+  const double RMAX = Q / (2.0 - CT), EPS5 = CT / Q;
+  const double Y = ufloor_(X + std::max(CT, std::min(RMAX, EPS5 * std::fabs(1.0 + ufloor_(X)))));
+  return (X <= 0.0 || (Y - X) < RMAX) ? Y : Y - 1.0;
+}
+
+// value of a field that the reference computes on IstrT..IendT and then wraps periodically:
+// evaluate the analytical formula at the periodic image of the global index.
+inline int wrap_i(int i, int Lm) { return i < 1 ? i + Lm : (i > Lm ? i - Lm : i); }
+
+int up(roms_b200_driver* d, const char* name, H2& a) { return roms_b200_upload(d->ctx, roms_b200_field_id(name), a.d.data()); }
+
+// ana_grid (Functionals/ana_grid.h) + metrics (Utility/metrics.F) + ini_hmixcoef, all 2-D, on the host
+int host_grid(roms_b200_driver* d) {
+  const roms_b200_bounds& b = d->b; const roms_b200_config& c = d->cfg;
+  const int Lm = b.Lm, Mm = b.Mm;
+  H2 pm, pn, f, h, dndx, dmde, angler, xr, yr, q;
+  for (H2* a : {&pm, &pn, &f, &h, &dndx, &dmde, &angler, &xr, &yr, &q, &d->lonr, &d->latr, &d->srflx, &d->sustr, &d->svstr}) a->init(b);
+  // rows/columns of this tile's arrays that hold physical or periodic-image points
+  const int j0 = std::max(b.LBj, 0), j1 = std::min(b.UBj, Mm + 1);
+  const int i0 = std::max(b.LBi, -2), i1 = std::min(b.UBi, Lm + 2);
+  if (c.app == ROMS_B200_APP_BENCHMARK) {
+    const double Xsize = 360.0, Esize = 20.0, dx = Xsize / (double)Lm, dy = Esize / (double)Mm;
+    const double val1 = (double)Lm / (2.0 * pi * Eradius), val2 = (double)Mm * 360.0 / (2.0 * pi * Eradius * Esize);
+    const double v1 = 2.0 * (2.0 * pi * 366.25 / 365.25) / 86400.0;
+    for (int j = j0; j <= j1; ++j) {
+      const double lat = -70.0 + dy * ((double)j - 0.5);
+      const double cff = 1.0 / std::cos(lat * deg2rad);
+      for (int i = i0; i <= i1; ++i) {
+        if (i >= 0 && i <= Lm + 1) { d->lonr(i, j) = dx * ((double)i - 0.5); d->latr(i, j) = lat; }   // no exchange in the reference
+        pm(i, j) = val1 * cff; pn(i, j) = val2; angler(i, j) = 0.0;
+        f(i, j) = v1 * std::sin(lat * deg2rad);
+        h(i, j) = 500.0 + 1750.0 * (1.0 + std::tanh((68.0 + lat) / dy));
+      }
+    }
+    // dndx,dmde on interior rows only (ana_grid.h:677-691), then periodic images
+    for (int j = std::max(j0, 1); j <= std::min(j1, Mm); ++j) {
+      const double wm = val1 * (1.0 / std::cos((-70.0 + dy * ((double)(j - 1) - 0.5)) * deg2rad));
+      const double wp = val1 * (1.0 / std::cos((-70.0 + dy * ((double)(j + 1) - 0.5)) * deg2rad));
+      for (int i = i0; i <= i1; ++i) { dndx(i, j) = 0.5 * ((1.0 / val2) - (1.0 / val2)); dmde(i, j) = 0.5 * ((1.0 / wp) - (1.0 / wm)); }
+    }
+  } else {
+    const double Xsize = 1000.0 * (double)Lm, Esize = 1000.0 * (double)Mm, depth = 150.0, f0 = -8.26e-05;
+    const double dx = Xsize / (double)Lm, dy = Esize / (double)Mm;
+    for (int j = j0; j <= j1; ++j) {
+      const double vj = (j <= Mm / 2) ? (double)j : (double)(Mm + 1 - j);
+      const double hh = std::min(depth, 84.5 + 66.526 * std::tanh((vj - 10.0) / 7.0));
+      for (int i = i0; i <= i1; ++i) {
+        if (i >= 0 && i <= Lm + 1) { xr(i, j) = dx * ((double)(i - 1) + 0.5); yr(i, j) = dy * ((double)(j - 1) + 0.5); }
+        pm(i, j) = 1.0 / dx; pn(i, j) = 1.0 / dy; angler(i, j) = 0.0; f(i, j) = f0; h(i, j) = hh;
+      }
+    }
+  }
+  int rc = 0;
+  rc |= up(d, "pm", pm); rc |= up(d, "pn", pn); rc |= up(d, "f", f); rc |= up(d, "h", h); rc |= up(d, "dndx", dndx); rc |= up(d, "dmde", dmde);
+  rc |= up(d, "angler", angler); rc |= up(d, "lonr", d->lonr); rc |= up(d, "latr", d->latr); rc |= up(d, "xr", xr); rc |= up(d, "yr", yr);
+  // metrics.F: every derived array is a point function of pm,pn(,f) at the point and its i-1/j-1 neighbours
+  auto ok = [&](int i, int j) { return i >= i0 && i <= i1 && j >= j0 && j <= j1; };
+  auto fill = [&](const char* name, int di, int dj, auto fn) {
+    q.d.assign(q.d.size(), 0.0);
+    for (int j = j0 + dj; j <= j1; ++j) for (int i = i0 + di; i <= i1; ++i) if (ok(i - di, j - dj)) q(i, j) = fn(i, j);
+    // the padding column Lm+3 (even Lm) is never set by the reference
+    rc |= up(d, name, q);
+  };
+  fill("om_r", 0, 0, [&](int i, int j) { return 1.0 / pm(i, j); });
+  fill("on_r", 0, 0, [&](int i, int j) { return 1.0 / pn(i, j); });
+  fill("omn", 0, 0, [&](int i, int j) { return 1.0 / (pm(i, j) * pn(i, j)); });
+  fill("fomn", 0, 0, [&](int i, int j) { return f(i, j) * (1.0 / (pm(i, j) * pn(i, j))); });
+  fill("pnom_r", 0, 0, [&](int i, int j) { return pn(i, j) / pm(i, j); });
+  fill("pmon_r", 0, 0, [&](int i, int j) { return pm(i, j) / pn(i, j); });
+  fill("pmon_u", 1, 0, [&](int i, int j) { return (pm(i - 1, j) + pm(i, j)) / (pn(i - 1, j) + pn(i, j)); });
+  fill("pnom_u", 1, 0, [&](int i, int j) { return (pn(i - 1, j) + pn(i, j)) / (pm(i - 1, j) + pm(i, j)); });
+  fill("om_u", 1, 0, [&](int i, int j) { return 2.0 / (pm(i - 1, j) + pm(i, j)); });
+  fill("on_u", 1, 0, [&](int i, int j) { return 2.0 / (pn(i - 1, j) + pn(i, j)); });
+  fill("pmon_v", 0, 1, [&](int i, int j) { return (pm(i, j - 1) + pm(i, j)) / (pn(i, j - 1) + pn(i, j)); });
+  fill("pnom_v", 0, 1, [&](int i, int j) { return (pn(i, j - 1) + pn(i, j)) / (pm(i, j - 1) + pm(i, j)); });
+  fill("om_v", 0, 1, [&](int i, int j) { return 2.0 / (pm(i, j - 1) + pm(i, j)); });
+  fill("on_v", 0, 1, [&](int i, int j) { return 2.0 / (pn(i, j - 1) + pn(i, j)); });
+  fill("pnom_p", 1, 1, [&](int i, int j) { return (pn(i - 1, j - 1) + pn(i - 1, j) + pn(i, j - 1) + pn(i, j)) / (pm(i - 1, j - 1) + pm(i - 1, j) + pm(i, j - 1) + pm(i, j)); });
+  fill("pmon_p", 1, 1, [&](int i, int j) { return (pm(i - 1, j - 1) + pm(i - 1, j) + pm(i, j - 1) + pm(i, j)) / (pn(i - 1, j - 1) + pn(i - 1, j) + pn(i, j - 1) + pn(i, j)); });
+  fill("om_p", 1, 1, [&](int i, int j) { return 4.0 / (pm(i - 1, j - 1) + pm(i - 1, j) + pm(i, j - 1) + pm(i, j)); });
+  fill("on_p", 1, 1, [&](int i, int j) { return 4.0 / (pn(i - 1, j - 1) + pn(i - 1, j) + pn(i, j - 1) + pn(i, j)); });
+  // ini_hmixcoef.F, mod_grid.F:1382-1384, mod_mixing.F:1527
+  const int fid_d2 = roms_b200_field_id("diff2");
+  std::vector<double> d2(q.d.size() * 2);
+  for (size_t n = 0; n < q.d.size(); ++n) { d2[n] = c.tnu2[0]; d2[q.d.size() + n] = c.tnu2[1]; }
+  rc |= roms_b200_upload(d->ctx, fid_d2, d2.data());
+  rc |= roms_b200_fill(d->ctx, roms_b200_field_id("visc2_r"), c.visc2); rc |= roms_b200_fill(d->ctx, roms_b200_field_id("visc2_p"), c.visc2);
+  rc |= roms_b200_fill(d->ctx, roms_b200_field_id("rdrag"), c.rdrg); rc |= roms_b200_fill(d->ctx, roms_b200_field_id("rdrag2"), c.rdrg2);
+  rc |= roms_b200_fill(d->ctx, roms_b200_field_id("Jwtype"), (double)c.lmd_Jwt);
+  rc |= roms_b200_fill(d->ctx, roms_b200_field_id("Akv"), c.Akv_bak);
+  {
+    const long n = roms_b200_field_size(d->ctx, roms_b200_field_id("Akt"));
+    std::vector<double> a((size_t)n);
+    for (long x = 0; x < n; ++x) a[x] = (x < n / 2) ? c.Akt_bak[0] : c.Akt_bak[1];
+    rc |= roms_b200_upload(d->ctx, roms_b200_field_id("Akt"), a.data());
+  }
+  return rc;
+}
+
+// set_data.F analytical branches that change in time, evaluated on the host (2-D) exactly as the
+// Fortran host does, then uploaded: ana_srflux (BENCHMARK), ana_smflux (UPWELLING).
+int host_set_data(roms_b200_driver* d, double tdays) {
+  const roms_b200_bounds& b = d->b; const roms_b200_config& c = d->cfg;
+  const int j0 = std::max(b.LBj, 0), j1 = std::min(b.UBj, b.Mm + 1), i0 = std::max(b.LBi, -2), i1 = std::min(b.UBi, b.Lm + 2);
+  if (c.app == ROMS_B200_APP_BENCHMARK) {
+    const double DateNumber = 367.0 + tdays, DayFraction = std::fabs(DateNumber - std::trunc(DateNumber));
+    const double seconds = tfloor_(DayFraction * 86400.0 + 0.5, 3.0 * 2.220446049250313e-16);
+    const double hour = seconds / 3600.0, yday = (double)(1 + (int)std::floor(tdays)) + DayFraction;
+    double Dangle = 23.44 * std::cos((172.0 - yday) * 2.0 * pi / 365.2425);
+    Dangle = Dangle * deg2rad;
+    const double Hangle = (12.0 - hour) * pi / 12.0, Rsolar = Csolar / (c.rho0 * Cp);
+    const double Tair = 4.0, Hair = 0.8, cloud = 0.6;
+    for (int j = j0; j <= j1; ++j) for (int i = i0; i <= i1; ++i) {
+      const int iw = wrap_i(i, b.Lm);                 // periodic image of the interior value
+      const double LatRad = d->latr(std::min(std::max(iw, 0), b.Lm + 1), j) * deg2rad, lon = (360.0 / (double)b.Lm) * ((double)iw - 0.5);
+      const double cff1 = std::sin(LatRad) * std::sin(Dangle), cff2 = std::cos(LatRad) * std::cos(Dangle);
+      double sr = 0.0;
+      const double zenith = cff1 + cff2 * std::cos(Hangle - lon * deg2rad);
+      if (zenith > 0.0) {
+        const double cff = (0.7859 + 0.03477 * Tair) / (1.0 + 0.00412 * Tair);
+        const double vap_p = std::pow(10.0, cff) * Hair;
+        sr = Rsolar * zenith * zenith * (1.0 - 0.6 * (cloud * cloud * cloud)) / ((zenith + 2.7) * vap_p * 1.0e-3 + 1.085 * zenith + 0.1);
+      }
+      d->srflx(i, j) = (1.0 - 0.06) * sr;
+    }
+    return up(d, "srflx", d->srflx);
+  }
+  double windamp;
+  if ((tdays - 0.0) <= 2.0) windamp = -0.1 * std::sin(pi * (tdays - 0.0) / 4.0) / c.rho0; else windamp = -0.1 / c.rho0;
+  for (int j = j0; j <= j1; ++j) for (int i = i0; i <= i1; ++i) { d->sustr(i, j) = windamp; d->svstr(i, j) = 0.0; }
+  return up(d, "sustr", d->sustr) | up(d, "svstr", d->svstr);
+}
+}  // namespace
+
+extern "C" {
+
+// Drivers/nl_roms.h:61-245 (ROMS_initialize) for the analytical applications
+int roms_b200_ROMS_initialize(const roms_b200_config* cfg, int tile, int distributed, int device, roms_b200_driver** out) {
+  roms_b200_driver* d = new roms_b200_driver();
+  d->cfg = *cfg;
+  if (roms_b200_tile_bounds(cfg->Lm, cfg->Mm, cfg->N, cfg->NT, cfg->NAT, cfg->NtileI, cfg->NtileJ, tile, 1, 0, distributed, &d->b)) return 1;
+  const int N = cfg->N;
+  d->sc_r.resize(N + 1); d->Cs_r.resize(N + 1); d->sc_w.resize(N + 1); d->Cs_w.resize(N + 1);
+  roms_b200_host_scoord(N, cfg->theta_s, cfg->theta_b, d->sc_r.data(), d->Cs_r.data(), d->sc_w.data(), d->Cs_w.data());
+  d->w1.assign(2 * cfg->ndtfast + 4, 0.0); d->w2.assign(2 * cfg->ndtfast + 4, 0.0);
+  d->nfast = roms_b200_host_weights(cfg->ndtfast, d->w1.data(), d->w2.data());
+  roms_b200_params& p = d->p; std::memset(&p, 0, sizeof(p));
+  p.app = cfg->app; p.dt = cfg->dt; p.ndtfast = cfg->ndtfast; p.dtfast = cfg->dt / (double)cfg->ndtfast; p.nfast = d->nfast;
+  p.rho0 = cfg->rho0; p.g = cfg->g; p.gamma2 = cfg->gamma2; p.hc = cfg->Tcline;
+  p.R0 = cfg->R0; p.T0 = cfg->T0; p.S0 = cfg->S0; p.Tcoef = cfg->Tcoef; p.Scoef = cfg->Scoef;
+  p.Akt_bak[0] = cfg->Akt_bak[0]; p.Akt_bak[1] = cfg->Akt_bak[1]; p.Akv_bak = cfg->Akv_bak;
+  p.blk_ZQ = cfg->blk_ZQ; p.blk_ZT = cfg->blk_ZT; p.blk_ZW = cfg->blk_ZW; p.dstart = 0.0;
+  if (roms_b200_create(&d->b, &p, device, &d->ctx)) { delete d; return 2; }
+  int rc = roms_b200_set_scoord(d->ctx, d->sc_r.data(), d->Cs_r.data(), d->sc_w.data(), d->Cs_w.data());
+  rc |= roms_b200_set_weights(d->ctx, d->nfast, d->w1.data(), d->w2.data());
+  rc |= host_grid(d);
+  // Nonlinear/initial.F:277-577: set_depth -> ana_initial -> set_depth -> set_massflux -> omega, rho_eos
+  rc |= roms_b200_set_depth(d->ctx);
+  rc |= roms_b200_ana_initial(d->ctx);
+  rc |= roms_b200_set_depth(d->ctx);
+  rc |= roms_b200_set_massflux(d->ctx, 1);
+  rc |= roms_b200_omega(d->ctx);
+  rc |= roms_b200_rho_eos(d->ctx, 1);
+  // time-independent forcing of set_data (evaluated once) and the first-step post_initial
+  rc |= roms_b200_set_data(d->ctx, 0.0);
+  rc |= roms_b200_ini_fields(d->ctx, 1, 1);
+  rc |= roms_b200_set_depth(d->ctx);
+  const int st[6] = {1, 1, 1, 2, 1, 1};    // iic=ntstart=1, ntfirst=1, nstp=1, nnew=2, nrhs=1, indx1=1
+  rc |= roms_b200_set_stepping(d->ctx, st, 0.0);
+  rc |= roms_b200_sync(d->ctx);
+  if (rc) { roms_b200_destroy(d->ctx); delete d; return 3; }
+  *out = d;
+  return 0;
+}
+
+// Drivers/nl_roms.h:247-318 (ROMS_run): nsteps of main3d.
+// host_forcing!=0: per step, set_data on the host + H2D of the forcing + D2H of the diag scalars
+// (the reference's NINFO=1 behaviour); host_forcing==0: everything stays on the device.
+int roms_b200_ROMS_run(roms_b200_driver* d, int nsteps, int host_forcing, double* diag3) {
+  int rc = 0;
+  if (!host_forcing) rc = roms_b200_main3d(d->ctx, nsteps, 1, 0);
+  else {
+    for (int s = 0; s < nsteps && !rc; ++s) {
+      int st[6]; double time;
+      roms_b200_get_stepping(d->ctx, st, &time);
+      rc |= host_set_data(d, time / 86400.0);
+      rc |= roms_b200_main3d(d->ctx, 1, 0, 0);
+      roms_b200_get_stepping(d->ctx, st, &time);
+      rc |= roms_b200_diag(d->ctx, st[3] /* the level just completed is nnew of that step */, d->last_diag);
+    }
+    if (diag3) std::memcpy(diag3, d->last_diag, sizeof(d->last_diag));
+  }
+  return rc;
+}
+
+roms_b200_ctx* roms_b200_driver_ctx(roms_b200_driver* d) { return d->ctx; }
+void roms_b200_driver_bounds(roms_b200_driver* d, roms_b200_bounds* b) { *b = d->b; }
+int roms_b200_driver_nfast(roms_b200_driver* d) { return d->nfast; }
+
+// Drivers/nl_roms.h:320-430 (ROMS_finalize)
+int roms_b200_ROMS_finalize(roms_b200_driver* d) {
+  if (!d) return 0;
+  roms_b200_destroy(d->ctx);
+  delete d;
+  return 0;
+}
+
+}  // extern "C"

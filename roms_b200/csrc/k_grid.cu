@@ -347,3 +347,78 @@ int k_diag(roms_b200_ctx* c, int nstp, double* out3) {
   out3[0] = ke / vol; out3[1] = pe / vol; out3[2] = vol;
   return 0;
 }
+
+// ---- ana_initial (Functionals/ana_initial.h: BENCHMARK :545-558, UPWELLING :828-848) -------
+// Analytical initial conditions evaluated on the device from the device z_r:
+// fluid at rest, zeta=0, T(z), S.  Writes time level 1 (Nonlinear/initial.F:358).
+__global__ void ana_initial_kernel(const Dev D, Box bx) {
+  IJ_FROM_BOX(bx);
+  const roms_b200_bounds& b = D.b; const int N = b.N;
+  V3 z_r = v3(D, FID(z_r)), T = v3l(D, FID(t), 1, 1), S = v3l(D, FID(t), 1, 2);
+  // u, v, ubar, vbar, zeta start from the zero-initialised mirror (fluid at rest)
+  const double val1 = (44.69 / 39.382) * (44.69 / 39.382);
+  const double val2 = val1 * (D.p.rho0 * 800.0 / D.p.g) * (5.0e-05 / ((42.689 / 44.69) * (42.689 / 44.69)));
+  for (int k = 1; k <= N; ++k) {
+    const double z = z_r(i, j, k);
+    if (D.p.app == ROMS_B200_APP_BENCHMARK) { st(D, T, i, j, k, val2 * exp(z / 800.0) * (0.6 - 0.4 * tanh(z / 800.0))); st(D, S, i, j, k, 35.0); }
+    else { st(D, T, i, j, k, D.p.T0 + 8.0 * exp(z / 50.0)); st(D, S, i, j, k, D.p.S0); }
+  }
+}
+// ---- post_initial: ini_zeta_tile + ini_fields_tile (Nonlinear/ini_fields.F) -----------------
+// lateral BCs + periodic images on time level (nstp,kstp), Zt_avg1=zeta(kstp), ubar/vbar = vertical mean of u,v.
+__global__ void ini_fields_kernel(const Dev D, Box bx, int nstp, int kstp) {
+  IJ_FROM_BOX(bx);
+  const roms_b200_bounds& b = D.b; const int N = b.N;
+  const bool S = b.Southern_Edge && !b.NSperiodic, Nn = b.Northern_Edge && !b.NSperiodic;
+  const bool south = S && j == b.Jstr, north = Nn && j == b.Jend;
+  V3 Hz = v3(D, FID(Hz)), u = v3l(D, FID(u), nstp), v = v3l(D, FID(v), nstp);
+  V2 zeta = v2l(D, FID(zeta), kstp), Zt = v2(D, FID(Zt_avg1)), ubar = v2l(D, FID(ubar), kstp), vbar = v2l(D, FID(vbar), kstp);
+  {
+    const double z = zeta(i, j);
+    st(D, zeta, i, j, z); st(D, Zt, i, j, z);
+    if (south) { st(D, zeta, i, j - 1, z); st(D, Zt, i, j - 1, z); }
+    if (north) { st(D, zeta, i, j + 1, z); st(D, Zt, i, j + 1, z); }
+  }
+  for (int itrc = 1; itrc <= b.NT; ++itrc) {
+    V3 T = v3l(D, FID(t), nstp, itrc);
+    for (int k = 1; k <= N; ++k) {
+      const double val = T(i, j, k);
+      st(D, T, i, j, k, val);
+      if (south) st(D, T, i, j - 1, k, val);
+      if (north) st(D, T, i, j + 1, k, val);
+    }
+  }
+  double DC0 = 0.0, CF0 = 0.0;
+  for (int k = 1; k <= N; ++k) {
+    const double uu = u(i, j, k), dc = 0.5 * (Hz(i, j, k) + Hz(i - 1, j, k));
+    DC0 = DC0 + dc; CF0 = CF0 + dc * uu;
+    st(D, u, i, j, k, uu);
+    if (south) st(D, u, i, j - 1, k, D.p.gamma2 * uu);
+    if (north) st(D, u, i, j + 1, k, D.p.gamma2 * uu);
+  }
+  { const double c1 = 1.0 / DC0; const double ub = CF0 * c1; st(D, ubar, i, j, ub);
+    if (south) st(D, ubar, i, j - 1, D.p.gamma2 * ub); if (north) st(D, ubar, i, j + 1, D.p.gamma2 * ub); }
+  if (j >= b.JstrM) {
+    DC0 = 0.0; CF0 = 0.0;
+    for (int k = 1; k <= N; ++k) {
+      const double vv = v(i, j, k), dc = 0.5 * (Hz(i, j, k) + Hz(i, j - 1, k));
+      DC0 = DC0 + dc; CF0 = CF0 + dc * vv;
+      st(D, v, i, j, k, vv);
+    }
+    const double c1 = 1.0 / DC0; st(D, vbar, i, j, CF0 * c1);
+  }
+  if (south) { for (int k = 1; k <= N; ++k) st(D, v, i, b.Jstr, k, 0.0); st(D, vbar, i, b.Jstr, 0.0); }
+  if (north) { for (int k = 1; k <= N; ++k) st(D, v, i, b.Jend + 1, k, 0.0); st(D, vbar, i, b.Jend + 1, 0.0); }
+}
+int k_ana_initial(roms_b200_ctx* c) {
+  const roms_b200_bounds& b = c->D.b;
+  Box bx{b.IstrT, b.IendT, b.JstrT, b.JendT}; dim3 blk(64, 4);
+  ana_initial_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx); c->launches++;
+  return 0;
+}
+int k_ini_fields(roms_b200_ctx* c, int nstp, int kstp) {
+  const roms_b200_bounds& b = c->D.b;
+  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(64, 4);
+  ini_fields_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx, nstp, kstp); c->launches++;
+  return 0;
+}

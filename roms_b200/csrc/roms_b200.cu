@@ -155,6 +155,15 @@ int roms_b200_step3d_uv(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic,
 int roms_b200_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew) { ENTER(c); k_step3d_t(c, nrhs, nstp, nnew); LEAVE(); }
 int roms_b200_diag(roms_b200_ctx* c, int nstp, double* out3) { ENTER(c); if (k_diag(c, nstp, out3)) return 1; LEAVE(); }
 int roms_b200_set_data(roms_b200_ctx* c, double tdays) { ENTER(c); k_set_data(c, tdays); LEAVE(); }
+int roms_b200_ana_initial(roms_b200_ctx* c) { ENTER(c); k_ana_initial(c); LEAVE(); }
+int roms_b200_ini_fields(roms_b200_ctx* c, int nstp, int kstp) { ENTER(c); k_ini_fields(c, nstp, kstp); LEAVE(); }
+int roms_b200_fill(roms_b200_ctx* c, int f, double value) {
+  ENTER(c);
+  if (f < 0 || f >= ROMS_B200_NFIELDS) return 1;
+  std::vector<double> h(c->fsize[f], value);
+  CUDA_OK(cudaMemcpy(c->D.f[f], h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+  LEAVE();
+}
 
 // main3d.F:810-918: LF-AM3 fast loop.  The launch sequence depends only on
 // (indx1 at entry, which of the three AB start-up forms the first predictor
@@ -240,6 +249,31 @@ int roms_b200_main3d(roms_b200_ctx* c, int nsteps, int analytic_forcing, int wit
   LEAVE();
 }
 
+// CUDA-event stopwatch on the context's launch stream (cudaEvent sees only that stream)
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+int roms_b200_timer_start(roms_b200_ctx* c) {
+  ENTER(c);
+  if (!g_ev0) { CUDA_OK(cudaEventCreate(&g_ev0)); CUDA_OK(cudaEventCreate(&g_ev1)); }
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  CUDA_OK(cudaEventRecord(g_ev0, c->stream));
+  LEAVE();
+}
+int roms_b200_timer_stop(roms_b200_ctx* c, float* ms) {
+  ENTER(c);
+  CUDA_OK(cudaEventRecord(g_ev1, c->stream));
+  CUDA_OK(cudaEventSynchronize(g_ev1));
+  CUDA_OK(cudaEventElapsedTime(ms, g_ev0, g_ev1));
+  LEAVE();
+}
+// write `mbytes` MiB of scratch so that the next kernel starts with a cold L2
+int roms_b200_flush_l2(roms_b200_ctx* c, int mbytes) {
+  ENTER(c);
+  static void* buf = nullptr; static size_t cap = 0;
+  const size_t n = (size_t)mbytes << 20;
+  if (cap < n) { if (buf) cudaFree(buf); CUDA_OK(cudaMalloc(&buf, n)); cap = n; }
+  CUDA_OK(cudaMemsetAsync(buf, 1, n, c->stream));
+  LEAVE();
+}
 int roms_b200_time_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int reps, float* ms_avg) {
   ENTER(c);
   cudaEvent_t e0, e1;

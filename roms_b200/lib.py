@@ -195,3 +195,78 @@ class Context:
         ms = C.c_float()
         self._chk(self.L.roms_b200_time_step3d_t(self.h, nrhs, nstp, nnew, reps, C.byref(ms)), "time_step3d_t")
         return ms.value
+
+
+class Config(C.Structure):
+    _fields_ = [("app", C.c_int), ("Lm", C.c_int), ("Mm", C.c_int), ("N", C.c_int), ("NT", C.c_int), ("NAT", C.c_int),
+                ("NtileI", C.c_int), ("NtileJ", C.c_int), ("dt", C.c_double), ("ndtfast", C.c_int),
+                ("theta_s", C.c_double), ("theta_b", C.c_double), ("Tcline", C.c_double),
+                ("rho0", C.c_double), ("g", C.c_double), ("gamma2", C.c_double), ("rdrg", C.c_double), ("rdrg2", C.c_double),
+                ("Akt_bak", C.c_double * 2), ("Akv_bak", C.c_double), ("tnu2", C.c_double * 2), ("visc2", C.c_double),
+                ("R0", C.c_double), ("T0", C.c_double), ("S0", C.c_double), ("Tcoef", C.c_double), ("Scoef", C.c_double),
+                ("blk_ZQ", C.c_double), ("blk_ZT", C.c_double), ("blk_ZW", C.c_double), ("lmd_Jwt", C.c_int)]
+
+
+def default_config(app, Lm=0, Mm=0, N=0):
+    L = Lib.get().L
+    L.roms_b200_default_config.argtypes = [C.c_int] * 4 + [C.POINTER(Config)]
+    L.roms_b200_default_config.restype = None
+    c = Config()
+    L.roms_b200_default_config(app, Lm, Mm, N, C.byref(c))
+    return c
+
+
+class Driver:
+    """Mirror of the reference driver surface (Drivers/nl_roms.h): ROMS_initialize / ROMS_run / ROMS_finalize."""
+
+    def __init__(self, cfg, tile=0, distributed=0, device=0):
+        self.L = L = Lib.get().L
+        L.roms_b200_ROMS_initialize.argtypes = [C.POINTER(Config), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.roms_b200_ROMS_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.roms_b200_ROMS_finalize.argtypes = [C.c_void_p]
+        L.roms_b200_driver_ctx.argtypes = [C.c_void_p]
+        L.roms_b200_driver_ctx.restype = C.c_void_p
+        L.roms_b200_driver_nfast.argtypes = [C.c_void_p]
+        L.roms_b200_timer_start.argtypes = [C.c_void_p]
+        L.roms_b200_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.roms_b200_flush_l2.argtypes = [C.c_void_p, C.c_int]
+        self.cfg = cfg
+        d = C.c_void_p()
+        rc = L.roms_b200_ROMS_initialize(C.byref(cfg), tile, distributed, device, C.byref(d))
+        if rc:
+            raise RuntimeError("ROMS_initialize failed rc=%d (a CUDA device is required; no CPU fallback)" % rc)
+        self.d = d
+        # borrow the context for field access without owning it
+        self.ctx = Context.__new__(Context)
+        self.ctx.lib = Lib.get()
+        self.ctx.L = L
+        self.ctx.h = C.c_void_p(L.roms_b200_driver_ctx(d))
+        self.ctx.close = lambda: None
+        self.nfast = L.roms_b200_driver_nfast(d)
+
+    def run(self, nsteps, host_forcing=False):
+        diag = np.zeros(3)
+        rc = self.L.roms_b200_ROMS_run(self.d, nsteps, 1 if host_forcing else 0, diag.ctypes.data)
+        if rc:
+            raise RuntimeError("ROMS_run failed rc=%d" % rc)
+        return diag
+
+    def timer_start(self):
+        self.L.roms_b200_timer_start(self.ctx.h)
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self.L.roms_b200_timer_stop(self.ctx.h, C.byref(ms))
+        return ms.value
+
+    def flush_l2(self, mbytes=256):
+        self.L.roms_b200_flush_l2(self.ctx.h, mbytes)
+
+    def finalize(self):
+        if getattr(self, "d", None):
+            self.ctx.h = None
+            self.L.roms_b200_ROMS_finalize(self.d)
+            self.d = None
+
+    def __del__(self):
+        self.finalize()

@@ -30,6 +30,7 @@ def lib():
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_set_dt.argtypes = [C.c_void_p, C.c_double, C.c_int]
         L.orc_initial.argtypes = [C.c_void_p]
+        L.orc_set_threads.argtypes = [C.c_void_p, C.c_int]
         L.orc_step.argtypes = [C.c_void_p, C.c_int]
         L.orc_phase.argtypes = [C.c_void_p, C.c_char_p]
         L.orc_field_size.restype = C.c_long
@@ -69,6 +70,9 @@ class Oracle:
         if getattr(self, "h", None):
             self.L.orc_destroy(self.h)
             self.h = None
+
+    def set_threads(self, n):
+        self.L.orc_set_threads(self.h, n)
 
     def initial(self):
         self.L.orc_initial(self.h)
