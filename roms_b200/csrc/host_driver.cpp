@@ -174,14 +174,30 @@ int host_grid(roms_b200_driver* d) {
   int rc = 0;
   rc |= up(d, "pm", pm); rc |= up(d, "pn", pn); rc |= up(d, "f", f); rc |= up(d, "h", h); rc |= up(d, "dndx", dndx); rc |= up(d, "dmde", dmde);
   rc |= up(d, "angler", angler); rc |= up(d, "lonr", d->lonr); rc |= up(d, "latr", d->latr); rc |= up(d, "xr", xr); rc |= up(d, "yr", yr);
-  // metrics.F: every derived array is a point function of pm,pn(,f) at the point and its i-1/j-1 neighbours
-  auto ok = [&](int i, int j) { return i >= i0 && i <= i1 && j >= j0 && j <= j1; };
+  // metrics.F: every derived array is a point function of pm,pn(,f) at the point and its i-1/j-1
+  // neighbours.  pm,pn are analytical, so neighbours outside this tile's arrays (i0-1 under the
+  // periodic wrap or a tile halo) are re-evaluated instead of exchanged: same expression, same bits.
+  const double bx_dx = 360.0 / (double)Lm, bx_dy = 20.0 / (double)Mm;
+  (void)bx_dx;
+  const double b_val1 = (double)Lm / (2.0 * pi * Eradius), b_val2 = (double)Mm * 360.0 / (2.0 * pi * Eradius * 20.0);
+  const double u_pm = 1.0 / ((1000.0 * (double)Lm) / (double)Lm), u_pn = 1.0 / ((1000.0 * (double)Mm) / (double)Mm);
+  const bool bench = (c.app == ROMS_B200_APP_BENCHMARK);
+  struct Metric {
+    bool bench; double b_val1, b_val2, dy, u_pm, u_pn;
+    double pm(int, int j) const { return bench ? b_val1 * (1.0 / std::cos((-70.0 + dy * ((double)j - 0.5)) * deg2rad)) : u_pm; }
+    double pn(int, int) const { return bench ? b_val2 : u_pn; }
+  } MT{bench, b_val1, b_val2, bx_dy, u_pm, u_pn};
+  struct PMV { const Metric& m; double operator()(int i, int j) const { return m.pm(i, j); } } pmv{MT};
+  struct PNV { const Metric& m; double operator()(int i, int j) const { return m.pn(i, j); } } pnv{MT};
+  auto& pm_ = pmv; auto& pn_ = pnv;
   auto fill = [&](const char* name, int di, int dj, auto fn) {
     q.d.assign(q.d.size(), 0.0);
-    for (int j = j0 + dj; j <= j1; ++j) for (int i = i0 + di; i <= i1; ++i) if (ok(i - di, j - dj)) q(i, j) = fn(i, j);
-    // the padding column Lm+3 (even Lm) is never set by the reference
+    for (int j = j0 + dj; j <= j1; ++j) for (int i = i0; i <= i1; ++i) q(i, j) = fn(i, j);
+    (void)di;
     rc |= up(d, name, q);
   };
+#define pm pm_
+#define pn pn_
   fill("om_r", 0, 0, [&](int i, int j) { return 1.0 / pm(i, j); });
   fill("on_r", 0, 0, [&](int i, int j) { return 1.0 / pn(i, j); });
   fill("omn", 0, 0, [&](int i, int j) { return 1.0 / (pm(i, j) * pn(i, j)); });
@@ -200,6 +216,8 @@ int host_grid(roms_b200_driver* d) {
   fill("pmon_p", 1, 1, [&](int i, int j) { return (pm(i - 1, j - 1) + pm(i - 1, j) + pm(i, j - 1) + pm(i, j)) / (pn(i - 1, j - 1) + pn(i - 1, j) + pn(i, j - 1) + pn(i, j)); });
   fill("om_p", 1, 1, [&](int i, int j) { return 4.0 / (pm(i - 1, j - 1) + pm(i - 1, j) + pm(i, j - 1) + pm(i, j)); });
   fill("on_p", 1, 1, [&](int i, int j) { return 4.0 / (pn(i - 1, j - 1) + pn(i - 1, j) + pn(i, j - 1) + pn(i, j)); });
+#undef pm
+#undef pn
   // ini_hmixcoef.F, mod_grid.F:1382-1384, mod_mixing.F:1527
   const int fid_d2 = roms_b200_field_id("diff2");
   std::vector<double> d2(q.d.size() * 2);
