@@ -5,6 +5,7 @@
 // other warps of the (32 x 8) block.  Per-column tridiagonal work lives in
 // thread-private arrays.  Arithmetic order per point == reference (-fmad=false).
 #include "common.cuh"
+#include <cstdlib>
 
 struct Edges { int S, N, Jstr, Jend; };
 __device__ __forceinline__ Edges edges(const Dev& D) { return Edges{D.b.Southern_Edge && !D.b.NSperiodic, D.b.Northern_Edge && !D.b.NSperiodic, D.b.Jstr, D.b.Jend}; }
@@ -197,6 +198,8 @@ __global__ void __launch_bounds__(256) step3d_t_kernel(const Dev D, Box bx, int 
 }
 int k_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew) {
   (void)nrhs; (void)nstp;
+  static const bool use_v1 = (getenv("ROMS_B200_STEP3D_T_V1") != nullptr);   // first (local-memory) version, kept for A/B timing
+  if (!use_v1) return k_step3d_t_v2(c, nnew);
   const roms_b200_bounds& b = c->D.b;
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT;
   step3d_t_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nnew); c->launches++;
