@@ -199,7 +199,10 @@ __global__ void __launch_bounds__(256) step3d_t_kernel(const Dev D, Box bx, int 
 int k_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew) {
   (void)nrhs; (void)nstp;
   static const bool use_v1 = (getenv("ROMS_B200_STEP3D_T_V1") != nullptr);   // first (local-memory) version, kept for A/B timing
-  if (!use_v1) return k_step3d_t_v2(c, nnew);
+  static const bool use_v2 = (getenv("ROMS_B200_STEP3D_T_V2") != nullptr);   // fused-sweep shared-memory version
+  int k_step3d_t_v3(roms_b200_ctx* c, int nnew);
+  if (use_v2) return k_step3d_t_v2(c, nnew);
+  if (!use_v1) return k_step3d_t_v3(c, nnew);
   const roms_b200_bounds& b = c->D.b;
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT;
   step3d_t_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nnew); c->launches++;
