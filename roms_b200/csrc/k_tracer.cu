@@ -202,7 +202,10 @@ int k_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew) {
   static const bool use_v2 = (getenv("ROMS_B200_STEP3D_T_V2") != nullptr);   // fused-sweep shared-memory version
   int k_step3d_t_v3(roms_b200_ctx* c, int nnew);
   if (use_v2) return k_step3d_t_v2(c, nnew);
-  if (!use_v1) return k_step3d_t_v3(c, nnew);
+  static const bool use_v3 = (getenv("ROMS_B200_STEP3D_T_V3") != nullptr);   // phase-separated shared-memory version
+  int k_step3d_t_v4(roms_b200_ctx* c, int nnew);
+  if (use_v3) return k_step3d_t_v3(c, nnew);
+  if (!use_v1) return k_step3d_t_v4(c, nnew);
   const roms_b200_bounds& b = c->D.b;
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT;
   step3d_t_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nnew); c->launches++;
