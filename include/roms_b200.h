@@ -156,6 +156,16 @@ long roms_b200_launch_count(const roms_b200_ctx* ctx);
 /* average device time (ms) of the last `roms_b200_time_kernel` call */
 int roms_b200_time_step3d_t(roms_b200_ctx* ctx, int nrhs, int nstp, int nnew, int reps, float* ms_avg);
 
+/* ---- multi-GPU: one rank = one tile = one GPU (Drivers/nl_roms.h:145-157).  The halo swaps of
+ * Utility/mp_exchange.F (mp_exchange2d/3d/4d) become NCCL send/recv inside roms_b200_main3d /
+ * roms_b200_step2d_loop.  Rank 0 creates the id, the host broadcasts it (MPI_Bcast / torch.distributed),
+ * every rank calls comm_init with rank == Jtile*NtileI+Itile of its bounds. */
+int roms_b200_comm_unique_id(char* id128);
+int roms_b200_comm_init(roms_b200_ctx* ctx, int rank, int nranks, const char* id128);
+int roms_b200_comm_destroy(roms_b200_ctx* ctx);
+/* copy the interior (Istr:Iend,Jstr:Jend[,k]) of one (l,m) volume of a field into a dense host buffer */
+int roms_b200_download_interior(roms_b200_ctx* ctx, int field, int l, int m, double* host);
+
 /* CUDA-event stopwatch on the context's launch stream, and an L2 flush (writes `mbytes` MiB) */
 int roms_b200_timer_start(roms_b200_ctx* ctx);
 int roms_b200_timer_stop(roms_b200_ctx* ctx, float* ms);

@@ -6,4 +6,4 @@ Python mirror of the ROMS_initialize / ROMS_run / ROMS_finalize driver surface.
 """
 from .lib import (Lib, Bounds, Params, Context, Config, Driver, default_config, FIELD_NAMES, APP_UPWELLING,  # noqa: F401
                   APP_BENCHMARK,
-                  tile_bounds, library_path)
+                  tile_bounds, library_path, comm_unique_id)

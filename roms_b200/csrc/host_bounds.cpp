@@ -24,11 +24,11 @@ extern "C" int roms_b200_tile_bounds(int Lm, int Mm, int N, int NT, int NAT, int
   o->Western_Edge = W; o->Eastern_Edge = E; o->Southern_Edge = S; o->Northern_Edge = Nn;
   // array bounds: mod_param.F:1633-1636 padding, get_bounds.F:193-212 (distributed) / :258-269 (serial)
   const int Im = Lm + ((Lm + 2) / 2 - (Lm + 1) / 2), Jm = Mm + ((Mm + 2) / 2 - (Mm + 1) / 2);
-  const int Ng = 2;
+  const int Ng = (distributed > 2) ? distributed : 2;     // NghostPoints (Utility/inp_par.F:211-226); >2 for a wider device mirror
   const int Imin = EWperiodic ? -Ng : 0, Imax = EWperiodic ? Im + Ng : Im + 1;
   const int Jmin = NSperiodic ? -Ng : 0, Jmax = NSperiodic ? Jm + Ng : Jm + 1;
   if (distributed) {
-    o->LBi = W ? Imin : Is - Ng; o->UBi = E ? Imax : Ie + Ng;
+    o->LBi = (W && !EWperiodic) ? Imin : Is - Ng; o->UBi = (E && !EWperiodic) ? Imax : Ie + Ng;
     o->LBj = S ? Jmin : Js - Ng; o->UBj = Nn ? Jmax : Je + Ng;
   } else { o->LBi = Imin; o->UBi = Imax; o->LBj = Jmin; o->UBj = Jmax; }
   // var_bounds, get_bounds.F:1044-1884

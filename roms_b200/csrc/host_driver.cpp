@@ -137,8 +137,11 @@ int host_grid(roms_b200_driver* d) {
   H2 pm, pn, f, h, dndx, dmde, angler, xr, yr, q;
   for (H2* a : {&pm, &pn, &f, &h, &dndx, &dmde, &angler, &xr, &yr, &q, &d->lonr, &d->latr, &d->srflx, &d->sustr, &d->svstr}) a->init(b);
   // rows/columns of this tile's arrays that hold physical or periodic-image points
+  const bool dist = (b.NtileI * b.NtileJ > 1);
   const int j0 = std::max(b.LBj, 0), j1 = std::min(b.UBj, Mm + 1);
-  const int i0 = std::max(b.LBi, -2), i1 = std::min(b.UBi, Lm + 2);
+  // serial arrays: the reference leaves the padding column Lm+3 untouched; distributed mirrors hold
+  // periodic images over their whole i-range
+  const int i0 = dist ? b.LBi : std::max(b.LBi, -2), i1 = dist ? b.UBi : std::min(b.UBi, Lm + 2);
   if (c.app == ROMS_B200_APP_BENCHMARK) {
     const double Xsize = 360.0, Esize = 20.0, dx = Xsize / (double)Lm, dy = Esize / (double)Mm;
     const double val1 = (double)Lm / (2.0 * pi * Eradius), val2 = (double)Mm * 360.0 / (2.0 * pi * Eradius * Esize);
@@ -147,7 +150,8 @@ int host_grid(roms_b200_driver* d) {
       const double lat = -70.0 + dy * ((double)j - 0.5);
       const double cff = 1.0 / std::cos(lat * deg2rad);
       for (int i = i0; i <= i1; ++i) {
-        if (i >= 0 && i <= Lm + 1) { d->lonr(i, j) = dx * ((double)i - 0.5); d->latr(i, j) = lat; }   // no exchange in the reference
+        if (dist) { d->lonr(i, j) = dx * ((double)wrap_i(i, Lm) - 0.5); d->latr(i, j) = lat; }
+        else if (i >= 0 && i <= Lm + 1) { d->lonr(i, j) = dx * ((double)i - 0.5); d->latr(i, j) = lat; }   // no exchange in the reference
         pm(i, j) = val1 * cff; pn(i, j) = val2; angler(i, j) = 0.0;
         f(i, j) = v1 * std::sin(lat * deg2rad);
         h(i, j) = 500.0 + 1750.0 * (1.0 + std::tanh((68.0 + lat) / dy));
@@ -240,7 +244,9 @@ int host_grid(roms_b200_driver* d) {
 // Fortran host does, then uploaded: ana_srflux (BENCHMARK), ana_smflux (UPWELLING).
 int host_set_data(roms_b200_driver* d, double tdays) {
   const roms_b200_bounds& b = d->b; const roms_b200_config& c = d->cfg;
-  const int j0 = std::max(b.LBj, 0), j1 = std::min(b.UBj, b.Mm + 1), i0 = std::max(b.LBi, -2), i1 = std::min(b.UBi, b.Lm + 2);
+  const bool dist = (b.NtileI * b.NtileJ > 1);
+  const int j0 = std::max(b.LBj, 0), j1 = std::min(b.UBj, b.Mm + 1);
+  const int i0 = dist ? b.LBi : std::max(b.LBi, -2), i1 = dist ? b.UBi : std::min(b.UBi, b.Lm + 2);
   if (c.app == ROMS_B200_APP_BENCHMARK) {
     const double DateNumber = 367.0 + tdays, DayFraction = std::fabs(DateNumber - std::trunc(DateNumber));
     const double seconds = tfloor_(DayFraction * 86400.0 + 0.5, 3.0 * 2.220446049250313e-16);
@@ -277,6 +283,8 @@ extern "C" {
 int roms_b200_ROMS_initialize(const roms_b200_config* cfg, int tile, int distributed, int device, roms_b200_driver** out) {
   roms_b200_driver* d = new roms_b200_driver();
   d->cfg = *cfg;
+  // distributed mirrors carry a halo of 3 (the fused step2d kernel reaches zeta(i-3); NghostPoints=3 in ROMS terms)
+  if (cfg->NtileI * cfg->NtileJ > 1) distributed = 3;
   if (roms_b200_tile_bounds(cfg->Lm, cfg->Mm, cfg->N, cfg->NT, cfg->NAT, cfg->NtileI, cfg->NtileJ, tile, 1, 0, distributed, &d->b)) return 1;
   const int N = cfg->N;
   d->sc_r.resize(N + 1); d->Cs_r.resize(N + 1); d->sc_w.resize(N + 1); d->Cs_w.resize(N + 1);

@@ -29,7 +29,7 @@ __global__ void set_depth_kernel(const Dev D, Box bx) {
 }
 int k_set_depth(roms_b200_ctx* c) {
   const roms_b200_bounds& b = c->D.b;
-  Box bx{b.IstrT, b.IendT, b.JstrT, b.JendT}; dim3 blk(64, 4);
+  Box bx{c->D.rI0, c->D.rI1, c->D.rJ0, c->D.rJ1}; dim3 blk(64, 4);
   set_depth_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx); c->launches++;
   return 0;
 }
@@ -42,14 +42,14 @@ __global__ void set_massflux_kernel(const Dev D, Box bx, int nrhs) {
   V3 Hz = v3(D, FID(Hz)), Huon = v3(D, FID(Huon)), Hvom = v3(D, FID(Hvom));
   V3 u = v3l(D, FID(u), nrhs), v = v3l(D, FID(v), nrhs);
   V2 on_u = v2(D, FID(on_u)), om_v = v2(D, FID(om_v));
-  if (i >= b.IstrP && i <= b.IendT && j >= b.JstrT && j <= b.JendT)
+  if (i >= D.uI0)
     st(D, Huon, i, j, k, 0.5 * (Hz(i, j, k) + Hz(i - 1, j, k)) * u(i, j, k) * on_u(i, j));
-  if (i >= b.IstrT && i <= b.IendT && j >= b.JstrP && j <= b.JendT)
+  if (j >= D.vJ0)
     st(D, Hvom, i, j, k, 0.5 * (Hz(i, j, k) + Hz(i, j - 1, k)) * v(i, j, k) * om_v(i, j));
 }
 int k_set_massflux(roms_b200_ctx* c, int nrhs) {
   const roms_b200_bounds& b = c->D.b;
-  Box bx{b.IstrT, b.IendT, b.JstrT, b.JendT}; dim3 blk(128, 2); dim3 g = grid2(bx, blk); g.z = b.N;
+  Box bx{c->D.rI0, c->D.rI1, c->D.rJ0, c->D.rJ1}; dim3 blk(128, 2); dim3 g = grid2(bx, blk); g.z = b.N;
   set_massflux_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs); c->launches++;
   return 0;
 }
@@ -76,7 +76,7 @@ __global__ void omega_kernel(const Dev D, Box bx) {
 }
 int k_omega(roms_b200_ctx* c) {
   const roms_b200_bounds& b = c->D.b;
-  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(64, 2);
+  Box bx{c->D.oI0, c->D.oI1, c->D.oJ0, c->D.oJ1}; dim3 blk(64, 2);
   omega_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx); c->launches++;
   return 0;
 }
@@ -90,7 +90,7 @@ __global__ void set_zeta_kernel(const Dev D, Box bx) {
 }
 int k_set_zeta(roms_b200_ctx* c) {
   const roms_b200_bounds& b = c->D.b;
-  Box bx{b.IstrR, b.IendR, b.JstrR, b.JendR}; dim3 blk(128, 2);
+  Box bx{c->D.rI0, c->D.rI1, c->D.rJ0, c->D.rJ1}; dim3 blk(128, 2);   // == IstrR..IendR x JstrR..JendR on a single tile
   set_zeta_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx); c->launches++;
   return 0;
 }
@@ -232,7 +232,7 @@ __global__ void rho_eos_kernel(const Dev D, Box bx, int nrhs) {
 }
 int k_rho_eos(roms_b200_ctx* c, int nrhs) {
   const roms_b200_bounds& b = c->D.b;
-  Box bx{b.IstrT, b.IendT, b.JstrT, b.JendT}; dim3 blk(64, 2);
+  Box bx{c->D.rI0, c->D.rI1, c->D.rJ0, c->D.rJ1}; dim3 blk(64, 2);
   rho_eos_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx, nrhs); c->launches++;
   return 0;
 }
@@ -304,7 +304,7 @@ __global__ void ana_vmix_kernel(const Dev D, Box bx) {
 }
 int k_ana_vmix(roms_b200_ctx* c) {
   const roms_b200_bounds& b = c->D.b;
-  Box bx{b.IstrT, b.IendT, b.JstrT, b.JendT}; dim3 blk(64, 4);
+  Box bx{c->D.rI0, c->D.rI1, c->D.rJ0, c->D.rJ1}; dim3 blk(64, 4);
   ana_vmix_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx); c->launches++;
   return 0;
 }
@@ -344,6 +344,14 @@ int k_diag(roms_b200_ctx* c, int nstp, double* out3) {
   CUDA_OK(cudaStreamSynchronize(c->stream));
   double ke = 0, pe = 0, vol = 0;
   for (int q = 0; q < nb; ++q) { ke += c->h_red[3 * q]; pe += c->h_red[3 * q + 1]; vol += c->h_red[3 * q + 2]; }
+  if (c->comm) {                       // mp_reduce of diag.F:405 across tiles
+    c->h_red[0] = ke; c->h_red[1] = pe; c->h_red[2] = vol;
+    CUDA_OK(cudaMemcpyAsync(c->D.red, c->h_red, 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (halo_allreduce_sum(c, c->D.red)) return 1;
+    CUDA_OK(cudaMemcpyAsync(c->h_red, c->D.red, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    ke = c->h_red[0]; pe = c->h_red[1]; vol = c->h_red[2];
+  }
   out3[0] = ke / vol; out3[1] = pe / vol; out3[2] = vol;
   return 0;
 }
@@ -412,7 +420,7 @@ __global__ void ini_fields_kernel(const Dev D, Box bx, int nstp, int kstp) {
 }
 int k_ana_initial(roms_b200_ctx* c) {
   const roms_b200_bounds& b = c->D.b;
-  Box bx{b.IstrT, b.IendT, b.JstrT, b.JendT}; dim3 blk(64, 4);
+  Box bx{c->D.rI0, c->D.rI1, c->D.rJ0, c->D.rJ1}; dim3 blk(64, 4);
   ana_initial_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx); c->launches++;
   return 0;
 }

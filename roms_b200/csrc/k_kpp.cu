@@ -357,7 +357,6 @@ __global__ void set_data_kernel(const Dev D, Box bx, ForcingArgs fa) {
   IJ_FROM_BOX(bx);
   const roms_b200_bounds& b = D.b;
   if (D.p.app == ROMS_B200_APP_BENCHMARK) {
-    if (!(i >= b.IstrT && i <= b.IendT && j >= b.JstrT && j <= b.JendT)) return;
     const double deg2rad = PI_D / 180.0;
     st(D, v2(D, FID(cloud)), i, j, 0.6); st(D, v2(D, FID(Tair)), i, j, 4.0); st(D, v2(D, FID(Hair)), i, j, 0.8);
     const double latr = v2(D, FID(latr))(i, j), lonr = v2(D, FID(lonr))(i, j);
@@ -379,12 +378,12 @@ __global__ void set_data_kernel(const Dev D, Box bx, ForcingArgs fa) {
     v2l(D, FID(btflux), 1)(i, j) = 0.0; v2l(D, FID(btflux), 2)(i, j) = 0.0;
     st(D, v2l(D, FID(stflux), 2), i, j, 0.0);
   } else {
-    if (i >= b.IstrT && i <= b.IendT && j >= b.JstrT && j <= b.JendT) {
+    {
       st(D, v2l(D, FID(stflux), 1), i, j, 0.0); st(D, v2l(D, FID(stflux), 2), i, j, 0.0);
       v2l(D, FID(btflux), 1)(i, j) = 0.0; v2l(D, FID(btflux), 2)(i, j) = 0.0;
     }
-    if (i >= b.IstrP && i <= b.IendT && j >= b.JstrT && j <= b.JendT) st(D, v2(D, FID(sustr)), i, j, fa.windamp);
-    if (i >= b.IstrT && i <= b.IendT && j >= b.JstrP && j <= b.JendT) st(D, v2(D, FID(svstr)), i, j, 0.0);
+    if (i >= D.uI0) st(D, v2(D, FID(sustr)), i, j, fa.windamp);
+    if (j >= D.vJ0) st(D, v2(D, FID(svstr)), i, j, 0.0);
   }
 }
 // host part of caldate/datevec (Utility/dateclock.F) for time_ref=0
@@ -411,7 +410,7 @@ int k_set_data(roms_b200_ctx* c, double tdays) {
     if ((tdays - p.dstart) <= 2.0) fa.windamp = -0.1 * sin(PI_D * (tdays - p.dstart) / 4.0) / p.rho0;
     else fa.windamp = -0.1 / p.rho0;
   }
-  Box bx{b.IstrT, b.IendT, b.JstrT, b.JendT}; dim3 blk(128, 2);
+  Box bx{c->D.rI0, c->D.rI1, c->D.rJ0, c->D.rJ1}; dim3 blk(128, 2);
   set_data_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx, fa); c->launches++;
   return 0;
 }

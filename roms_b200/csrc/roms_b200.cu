@@ -51,6 +51,23 @@ int roms_b200_create(const roms_b200_bounds* b, const roms_b200_params* p, int d
   D.b = *b; D.p = *p;
   D.ni = b->UBi - b->LBi + 1; D.nj = b->UBj - b->LBj + 1; D.nij = (size_t)D.ni * D.nj;
   D.wrapEW = (b->EWperiodic && b->NtileI == 1) ? 1 : 0;
+  D.dist = (b->NtileI * b->NtileJ > 1) ? 1 : 0;
+  D.halo = D.dist ? (b->Istr - b->LBi) : 2;
+  if (D.dist && (D.halo < 3 || b->UBi - b->Iend < 3)) { fprintf(stderr, "roms_b200: distributed tiles need a mirror halo >= 3 (tile_bounds distributed=3)\n"); return 3; }
+  {
+    const int j0 = b->LBj > 0 ? b->LBj : 0, j1 = b->UBj < b->Mm + 1 ? b->UBj : b->Mm + 1;   // physical rows held by this tile
+    if (D.dist) {
+      const int i0 = D.wrapEW ? b->IstrT : b->LBi, i1 = D.wrapEW ? b->IendT : b->UBi;       // one tile in i: periodic images via st()
+      D.rI0 = i0; D.rI1 = i1; D.rJ0 = j0; D.rJ1 = j1;
+      D.uI0 = D.wrapEW ? b->IstrP : b->LBi + 1; D.vJ0 = (b->LBj + 1 > 1) ? b->LBj + 1 : 1;
+      D.oI0 = D.wrapEW ? b->Istr : b->LBi + 1; D.oI1 = D.wrapEW ? b->Iend : b->UBi - 1;
+      D.oJ0 = (b->LBj + 1 > 1) ? b->LBj + 1 : 1; D.oJ1 = (b->UBj - 1 < b->Mm) ? b->UBj - 1 : b->Mm;
+    } else {
+      D.rI0 = b->IstrT; D.rI1 = b->IendT; D.rJ0 = b->JstrT; D.rJ1 = b->JendT;
+      D.uI0 = b->IstrP; D.vJ0 = b->JstrP;
+      D.oI0 = b->Istr; D.oI1 = b->Iend; D.oJ0 = b->Jstr; D.oJ1 = b->Jend;
+    }
+  }
   CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (int f = 0; f < ROMS_B200_NFIELDS; ++f) {
     const int nk = resolve(kFields[f].nk, *b), nl = resolve(kFields[f].nl, *b), nm = resolve(kFields[f].nm, *b);
@@ -84,6 +101,7 @@ int roms_b200_destroy(roms_b200_ctx* c) {
   for (int f = 0; f < ROMS_B200_NFIELDS; ++f) cudaFree(c->D.f[f]);
   cudaFree((void*)c->D.sc_r); cudaFree((void*)c->D.w1); cudaFree(c->D.P); cudaFree(c->D.scratch2); cudaFree(c->D.red); cudaFree(c->D.ksbl);
   cudaFreeHost(c->h_red);
+  roms_b200_comm_destroy(c);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -119,6 +137,19 @@ int roms_b200_upload(roms_b200_ctx* c, int f, const double* host) {
 int roms_b200_download(roms_b200_ctx* c, int f, double* host) {
   if (f < 0 || f >= ROMS_B200_NFIELDS) return 1;
   CUDA_OK(cudaMemcpyAsync(host, c->D.f[f], c->fsize[f] * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int roms_b200_download_interior(roms_b200_ctx* c, int f, int l, int m, double* host) {
+  if (f < 0 || f >= ROMS_B200_NFIELDS) return 1;
+  const Dev& D = c->D; const roms_b200_bounds& b = D.b;
+  const int nk = D.nk[f], wi = b.Iend - b.Istr + 1, wj = b.Jend - b.Jstr + 1;
+  const double* base = D.f[f] + D.nij * nk * ((size_t)(l - 1) + (size_t)D.nl[f] * (m - 1));
+  for (int k = 0; k < nk; ++k) {
+    const double* src = base + D.nij * k + (b.Istr - b.LBi) + (size_t)D.ni * (b.Jstr - b.LBj);
+    CUDA_OK(cudaMemcpy2DAsync(host + (size_t)k * wi * wj, wi * sizeof(double), src, D.ni * sizeof(double), wi * sizeof(double), wj,
+                              cudaMemcpyDeviceToHost, c->stream));
+  }
   CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
@@ -165,6 +196,20 @@ int roms_b200_fill(roms_b200_ctx* c, int f, double value) {
   LEAVE();
 }
 
+// halo exchange of named fields / planes (no-op on a single tile)
+struct XF { int fid; int plane0; int nplanes; };      // plane0: first (i,j) plane of the field's storage
+static int xchg(roms_b200_ctx* c, const XF* x, int n) {
+  if (!c->comm) return 0;
+  double* bases[HALO_MAXF]; int np[HALO_MAXF];
+  for (int q = 0; q < n; ++q) { bases[q] = c->D.f[x[q].fid] + (size_t)x[q].plane0 * c->D.nij; np[q] = x[q].nplanes; }
+  return halo_exchange(c, bases, np, n);
+}
+static inline XF xf3(const roms_b200_ctx* c, int fid, int l = 1, int m = 1) {      // volume (l,m) of a 3-D field
+  const int nk = c->D.nk[fid];
+  return XF{fid, nk * ((l - 1) + c->D.nl[fid] * (m - 1)), nk};
+}
+static inline XF xf2(int fid, int l = 1) { return XF{fid, l - 1, 1}; }
+
 // main3d.F:810-918: LF-AM3 fast loop.  The launch sequence depends only on
 // (indx1 at entry, which of the three AB start-up forms the first predictor
 // uses), so it is captured once per key and replayed as a CUDA graph.
@@ -178,12 +223,21 @@ static int fast_loop_launch(roms_b200_ctx* c, int nstp, int nnew, int iic, int n
       kstp = (iif == 1) ? indx1 : 3 - indx1;
       knew = 3; krhs = indx1;
     }
-    if (my_iif <= nfast + 1) k_step2d(c, krhs, kstp, knew, nstp, nnew, iif, 1, iic, ntfirst);
+    if (my_iif <= nfast + 1) {
+      k_step2d(c, krhs, kstp, knew, nstp, nnew, iif, 1, iic, ntfirst);
+      if (c->comm) {      // mp_exchange2d calls of step2d_LF_AM3.h:842,1013,1068,3043 aggregated into one message
+        if (iif == nfast + 1) { const XF x[3] = {xf2(FID(Zt_avg1)), xf2(FID(DU_avg1)), xf2(FID(DV_avg1))}; if (xchg(c, x, 3)) return 1; }
+        else { const XF x[4] = {xf2(FID(zeta), knew), xf2(FID(ubar), knew), xf2(FID(vbar), knew), xf2(FID(rzeta), krhs)}; if (xchg(c, x, 4)) return 1; }
+      }
+    }
     if (PRED) {
       PRED = false; knew = next_indx1; kstp = 3 - knew; krhs = 3;
       if (iif < nfast + 1) indx1 = next_indx1;
     }
-    if (iif < nfast + 1) k_step2d(c, krhs, kstp, knew, nstp, nnew, iif, 0, iic, ntfirst);
+    if (iif < nfast + 1) {
+      k_step2d(c, krhs, kstp, knew, nstp, nnew, iif, 0, iic, ntfirst);
+      if (c->comm) { const XF x[3] = {xf2(FID(zeta), knew), xf2(FID(ubar), knew), xf2(FID(vbar), knew)}; if (xchg(c, x, 3)) return 1; }
+    }
   }
   *indx1_io = indx1;
   return 0;
@@ -235,15 +289,21 @@ int roms_b200_main3d(roms_b200_ctx* c, int nsteps, int analytic_forcing, int wit
     if (with_diag) { double d[3]; if (k_diag(c, nstp, d)) return 1; }
     if (bench) k_bulk_flux(c, nrhs);
     k_set_vbc(c, nrhs);
-    if (bench) k_lmd_vmix(c, nstp); else k_ana_vmix(c);
+    { const XF x[4] = {xf2(FID(sustr)), xf2(FID(svstr)), xf2(FID(bustr)), xf2(FID(bvstr))}; if (xchg(c, x, 4)) return 1; }
+    if (bench) { k_lmd_vmix(c, nstp); const XF x[1] = {xf3(c, FID(Akv))}; if (xchg(c, x, 1)) return 1; } else k_ana_vmix(c);
     k_omega(c);
     k_set_zeta(c);
-    k_pre_step3d(c, nrhs, nstp, nnew, iic, ntf); k_prsgrd(c, nrhs); k_t3dmix2(c, nrhs, nstp, nnew); k_rhs3d_tile(c, nrhs); k_uv3dmix2(c, nrhs, nnew);
+    k_pre_step3d(c, nrhs, nstp, nnew, iic, ntf);
+    { XF x[HALO_MAXF]; int n = 0; for (int it = 1; it <= c->D.b.NT; ++it) x[n++] = xf3(c, FID(t), 3, it); if (xchg(c, x, n)) return 1; }   // pre_step3d.F:1171
+    k_prsgrd(c, nrhs); k_t3dmix2(c, nrhs, nstp, nnew); k_rhs3d_tile(c, nrhs); k_uv3dmix2(c, nrhs, nnew);
     if (roms_b200_step2d_loop(c, nstp, nnew, iic, ntf, &c->indx1)) return 1;
     k_set_depth(c);
     k_step3d_uv(c, nrhs, nstp, nnew, iic, ntf);
+    { const XF x[8] = {xf3(c, FID(u), nnew), xf3(c, FID(v), nnew), xf3(c, FID(Huon)), xf3(c, FID(Hvom)),       // step3d_uv.F:1805-1824
+                       xf2(FID(ubar), 1), xf2(FID(ubar), 2), xf2(FID(vbar), 1), xf2(FID(vbar), 2)}; if (xchg(c, x, 8)) return 1; }
     k_omega(c);
     k_step3d_t(c, nrhs, nstp, nnew);
+    { XF x[HALO_MAXF]; int n = 0; for (int it = 1; it <= c->D.b.NT; ++it) x[n++] = xf3(c, FID(t), nnew, it); if (xchg(c, x, n)) return 1; }   // step3d_t.F:1920
     c->iic += 1; c->time += c->D.p.dt;
   }
   LEAVE();

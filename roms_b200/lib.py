@@ -270,3 +270,41 @@ class Driver:
 
     def __del__(self):
         self.finalize()
+
+
+def comm_unique_id():
+    L = Lib.get().L
+    buf = C.create_string_buffer(128)
+    L.roms_b200_comm_unique_id.argtypes = [C.c_char_p]
+    if L.roms_b200_comm_unique_id(buf):
+        raise RuntimeError("ncclGetUniqueId failed")
+    return buf.raw
+
+
+def _driver_comm_init(self, rank, nranks, id128):
+    L = self.L
+    L.roms_b200_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+    rc = L.roms_b200_comm_init(self.ctx.h, rank, nranks, id128)
+    if rc:
+        raise RuntimeError("roms_b200_comm_init failed rc=%d" % rc)
+
+
+def _driver_bounds(self):
+    b = Bounds()
+    self.L.roms_b200_driver_bounds.argtypes = [C.c_void_p, C.POINTER(Bounds)]
+    self.L.roms_b200_driver_bounds(self.d, C.byref(b))
+    return b
+
+
+def _ctx_download_interior(self, name, l=1, m=1, nk=1):
+    b = self._bounds
+    wi, wj = b.Iend - b.Istr + 1, b.Jend - b.Jstr + 1
+    out = np.empty((nk, wj, wi))
+    self.L.roms_b200_download_interior.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    self._chk(self.L.roms_b200_download_interior(self.h, self.fid(name), l, m, out.ctypes.data), "download_interior")
+    return out
+
+
+Driver.comm_init = _driver_comm_init
+Driver.bounds = _driver_bounds
+Context.download_interior = _ctx_download_interior
