@@ -163,8 +163,9 @@ int roms_b200_time_step3d_t(roms_b200_ctx* ctx, int nrhs, int nstp, int nnew, in
 int roms_b200_comm_unique_id(char* id128);
 int roms_b200_comm_init(roms_b200_ctx* ctx, int rank, int nranks, const char* id128);
 int roms_b200_comm_destroy(roms_b200_ctx* ctx);
-/* copy the interior (Istr:Iend,Jstr:Jend[,k]) of one (l,m) volume of a field into a dense host buffer */
-int roms_b200_download_interior(roms_b200_ctx* ctx, int field, int l, int m, double* host);
+/* copy the interior (Istr:Iend,Jstr:Jend) of `nplanes` consecutive (i,j) planes of a field, starting at
+ * storage plane `plane0`, into a dense host buffer (nplanes, Jend-Jstr+1, Iend-Istr+1) */
+int roms_b200_download_interior(roms_b200_ctx* ctx, int field, int plane0, int nplanes, double* host);
 
 /* CUDA-event stopwatch on the context's launch stream, and an L2 flush (writes `mbytes` MiB) */
 int roms_b200_timer_start(roms_b200_ctx* ctx);

@@ -257,7 +257,7 @@ int host_set_data(roms_b200_driver* d, double tdays) {
     const double Tair = 4.0, Hair = 0.8, cloud = 0.6;
     for (int j = j0; j <= j1; ++j) for (int i = i0; i <= i1; ++i) {
       const int iw = wrap_i(i, b.Lm);                 // periodic image of the interior value
-      const double LatRad = d->latr(std::min(std::max(iw, 0), b.Lm + 1), j) * deg2rad, lon = (360.0 / (double)b.Lm) * ((double)iw - 0.5);
+      const double LatRad = (-70.0 + (20.0 / (double)b.Mm) * ((double)j - 0.5)) * deg2rad, lon = (360.0 / (double)b.Lm) * ((double)iw - 0.5);
       const double cff1 = std::sin(LatRad) * std::sin(Dangle), cff2 = std::cos(LatRad) * std::cos(Dangle);
       double sr = 0.0;
       const double zenith = cff1 + cff2 * std::cos(Hangle - lon * deg2rad);

@@ -140,11 +140,12 @@ int roms_b200_download(roms_b200_ctx* c, int f, double* host) {
   CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
-int roms_b200_download_interior(roms_b200_ctx* c, int f, int l, int m, double* host) {
+int roms_b200_download_interior(roms_b200_ctx* c, int f, int plane0, int nplanes, double* host) {
   if (f < 0 || f >= ROMS_B200_NFIELDS) return 1;
   const Dev& D = c->D; const roms_b200_bounds& b = D.b;
-  const int nk = D.nk[f], wi = b.Iend - b.Istr + 1, wj = b.Jend - b.Jstr + 1;
-  const double* base = D.f[f] + D.nij * nk * ((size_t)(l - 1) + (size_t)D.nl[f] * (m - 1));
+  const int nk = nplanes, wi = b.Iend - b.Istr + 1, wj = b.Jend - b.Jstr + 1;
+  if ((size_t)(plane0 + nplanes) * D.nij > c->fsize[f]) return 1;
+  const double* base = D.f[f] + D.nij * (size_t)plane0;
   for (int k = 0; k < nk; ++k) {
     const double* src = base + D.nij * k + (b.Istr - b.LBi) + (size_t)D.ni * (b.Jstr - b.LBj);
     CUDA_OK(cudaMemcpy2DAsync(host + (size_t)k * wi * wj, wi * sizeof(double), src, D.ni * sizeof(double), wi * sizeof(double), wj,

@@ -296,12 +296,29 @@ def _driver_bounds(self):
     return b
 
 
-def _ctx_download_interior(self, name, l=1, m=1, nk=1):
+def field_shapes(N, NT=2, NAT=2):
+    """name -> (kLB, nk, nl, nm) from the X-macro table of include/roms_b200.h."""
+    hdr = open(os.path.join(ROOT, "include", "roms_b200.h")).read()
+    block = hdr[hdr.index("#define ROMS_B200_FIELDS(X)"):hdr.index("enum roms_b200_field")]
+    sym = {"N": N, "Np1": N + 1, "NT": NT, "NAT": NAT}
+    out = {}
+    for name, klb, nk, nl, nm in re.findall(r"X\((\w+),(-?\w+),(\w+),(\w+),(\w+)\)", block):
+        out[name] = (int(klb),) + tuple(sym[x] if x in sym else int(x) for x in (nk, nl, nm))
+    return out
+
+
+def _ctx_download_interior(self, name, l=1, m=1, nk=None):
+    """Interior of volume (l,m) of a 3-D field, or of plane l of an (i,j,level) field."""
     b = self._bounds
+    klb, fnk, fnl, fnm = field_shapes(b.N, b.NT, b.NAT)[name]
+    if fnl == 1 and fnm == 1 and fnk <= 3 and name in ("zeta", "ubar", "vbar", "rzeta", "rubar", "rvbar", "diff2", "stflx", "btflx", "stflux", "btflux"):
+        plane0, nplanes = l - 1, 1
+    else:
+        plane0, nplanes = fnk * ((l - 1) + fnl * (m - 1)), fnk
     wi, wj = b.Iend - b.Istr + 1, b.Jend - b.Jstr + 1
-    out = np.empty((nk, wj, wi))
+    out = np.empty((nplanes, wj, wi))
     self.L.roms_b200_download_interior.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
-    self._chk(self.L.roms_b200_download_interior(self.h, self.fid(name), l, m, out.ctypes.data), "download_interior")
+    self._chk(self.L.roms_b200_download_interior(self.h, self.fid(name), plane0, nplanes, out.ctypes.data), "download_interior")
     return out
 
 
