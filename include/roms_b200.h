@@ -98,6 +98,9 @@ typedef struct roms_b200_ctx roms_b200_ctx;
 int roms_b200_tile_bounds(int Lm, int Mm, int N, int NT, int NAT, int NtileI, int NtileJ, int tile,
                           int EWperiodic, int NSperiodic, int distributed, roms_b200_bounds* out);
 
+/* W,E,S,N neighbour ranks of a tile (Utility/mp_exchange.F:73-197 tile_neighbors); -1 = none */
+int roms_b200_tile_neighbors(const roms_b200_bounds* b, int* wesn);
+
 /* ---- lifetime (replaces nothing in the reference; called from ROMS_initialize
  *      after ROMS_allocate_arrays, Drivers/nl_roms.h:180, and from ROMS_finalize) */
 int roms_b200_create(const roms_b200_bounds* b, const roms_b200_params* p, int device, roms_b200_ctx** out);

@@ -65,6 +65,17 @@ int orc_get_vec(void* h, const char* name, double* out) {
 }
 void orc_get_ksbl(void* h, int* out) { Model* M = (Model*)h; std::memcpy(out, M->ksbl.data(), M->ksbl.size() * sizeof(int)); }
 // tile bounds as ints, in the order of include/roms_b200.h: roms_b200_bounds
+// the ints of one tile in the order: Istr Iend Jstr Jend IstrR IendR JstrR JendR IstrU JstrV IstrP IendP JstrP JendP
+// IstrT IendT JstrT JendT IstrB IendB JstrB JendB IstrM JstrM Istrm3 Istrm2 Istrm1 IstrUm2 IstrUm1 Iendp1 Iendp2 Iendp2i Iendp3
+// Jstrm3 Jstrm2 Jstrm1 JstrVm2 JstrVm1 Jendp1 Jendp2 Jendp2i Jendp3 W E S N
+void orc_get_tile(void* h, int tile, int* o) {
+  const Tile& T = ((Model*)h)->tiles[tile];
+  const int v[] = {T.Istr, T.Iend, T.Jstr, T.Jend, T.IstrR, T.IendR, T.JstrR, T.JendR, T.IstrU, T.JstrV, T.IstrP, T.IendP, T.JstrP, T.JendP,
+                   T.IstrT, T.IendT, T.JstrT, T.JendT, T.IstrB, T.IendB, T.JstrB, T.JendB, T.IstrM, T.JstrM, T.Istrm3, T.Istrm2, T.Istrm1,
+                   T.IstrUm2, T.IstrUm1, T.Iendp1, T.Iendp2, T.Iendp2i, T.Iendp3, T.Jstrm3, T.Jstrm2, T.Jstrm1, T.JstrVm2, T.JstrVm1,
+                   T.Jendp1, T.Jendp2, T.Jendp2i, T.Jendp3, T.W, T.E, T.S, T.N};
+  for (size_t q = 0; q < sizeof(v) / sizeof(int); ++q) o[q] = v[q];
+}
 int orc_ntiles(void* h) { return (int)((Model*)h)->tiles.size(); }
 
 }  // extern "C"

@@ -4,6 +4,10 @@
 #include <algorithm>
 #include <stdexcept>
 #include <thread>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 
 namespace orc {
 
@@ -369,6 +373,53 @@ void initial(Model& M) {
   M.iic = M.ntstart;
 }
 
+// Persistent worker pool for the tile loops (the reference's OpenMP team, nl_roms.h:304-310):
+// worker w takes tiles w, w+nt, ... of the current loop; the loop end is a barrier.
+namespace {
+struct Pool {
+  std::vector<std::thread> th; std::mutex mu; std::condition_variable cv_go, cv_done;
+  const std::function<void(const Tile&)>* fn = nullptr; const std::vector<Tile>* tiles = nullptr;
+  long gen = 0; int pending = 0, nt = 0; bool stop = false;
+  void worker(int w, long seen) {
+    for (;;) {
+      std::unique_lock<std::mutex> lk(mu);
+      cv_go.wait(lk, [&] { return stop || gen != seen; });
+      if (stop) return;
+      seen = gen;
+      auto f = fn; auto tl = tiles; const int n = nt;
+      lk.unlock();
+      for (size_t t = w; t < tl->size(); t += n) (*f)((*tl)[t]);
+      lk.lock();
+      if (--pending == 0) cv_done.notify_one();
+    }
+  }
+  void ensure(int n) {
+    if ((int)th.size() == n) return;
+    shutdown();
+    stop = false; nt = n;
+    for (int w = 0; w < n; ++w) th.emplace_back(&Pool::worker, this, w, gen);
+  }
+  void run(const std::vector<Tile>& tl, const std::function<void(const Tile&)>& f) {
+    std::unique_lock<std::mutex> lk(mu);
+    fn = &f; tiles = &tl; pending = nt; ++gen;
+    cv_go.notify_all();
+    cv_done.wait(lk, [&] { return pending == 0; });
+  }
+  void shutdown() {
+    { std::lock_guard<std::mutex> lk(mu); stop = true; }
+    cv_go.notify_all();
+    for (auto& t : th) t.join();
+    th.clear();
+  }
+  ~Pool() { shutdown(); }
+};
+Pool g_pool;
+}  // namespace
+static void pool_run(Model& M, const std::function<void(const Tile&)>& f) {
+  g_pool.ensure(std::min<int>(M.nthreads, (int)M.tiles.size()));
+  g_pool.run(M.tiles, f);
+}
+
 // ---------------------------------------------------------------------------
 // One baroclinic step, Nonlinear/main3d.F:216-1148, as named phases so that a
 // test can stop between any two reference tile loops.
@@ -377,11 +428,8 @@ void main3d_phase(Model& M, const std::string& ph) {
   // loop end is the barrier -- the reference's shared-memory (OpenMP) mode,
   // Drivers/nl_roms.h:304-310 + main3d.F `!$OMP BARRIER` between tile loops.
   auto par = [&](auto fn) {
-    const int nt = std::min<int>(M.nthreads, (int)M.tiles.size());
-    std::vector<std::thread> th;
-    for (int w = 0; w < nt; ++w)
-      th.emplace_back([&, w]() { for (size_t t = w; t < M.tiles.size(); t += nt) fn(M.tiles[t]); });
-    for (auto& x : th) x.join();
+    std::function<void(const Tile&)> f = fn;
+    pool_run(M, f);
   };
   auto fwd = [&](auto fn) { if (M.nthreads > 1) { par(fn); return; } for (size_t t = 0; t < M.tiles.size(); ++t) fn(M.tiles[t]); };
   auto rev = [&](auto fn) { if (M.nthreads > 1) { par(fn); return; } for (size_t t = M.tiles.size(); t-- > 0;) fn(M.tiles[t]); };

@@ -425,20 +425,25 @@ static void lmd_finish_tile(Model& M, const Tile& T) {
     Akt(i, j, k, 1) = Akt(i, j, k, 1) + lmd_nu0c * nu_sxc;
     Akt(i, j, k, 2) = Akt(i, j, k, 2) + lmd_nu0c * nu_sxc;
   }
-  // lmd_vmix.F:540-640: edge copies (the E-W ones are overwritten by the periodic wrap in bc_w3d)
+  // lmd_vmix.F:563-640: edge copies.  The reference does the W/E copies even on a periodic axis; in its
+  // serial (1x1) and MPI builds they are then overwritten by the periodic exchange inside bc_w3d_tile, so
+  // the state after lmd_finish holds the periodic images.  With several shared-memory tiles the outcome
+  // would depend on the tile order (a west tile running after its east neighbour clobbers A(0,j)); that
+  // artifact is not restated: on a periodic axis the W/E copies are skipped.
+  const bool ew_copy = !M.EWperiodic;
   for (int k = 0; k <= N; ++k) {
-    if (T.W) for (int j = T.Jstr; j <= T.Jend; ++j) { for (int it = 1; it <= M.NAT; ++it) Akt(T.Istr - 1, j, k, it) = Akt(T.Istr, j, k, it); Akv(T.Istr - 1, j, k) = Akv(T.Istr, j, k); }
-    if (T.E) for (int j = T.Jstr; j <= T.Jend; ++j) { for (int it = 1; it <= M.NAT; ++it) Akt(T.Iend + 1, j, k, it) = Akt(T.Iend, j, k, it); Akv(T.Iend + 1, j, k) = Akv(T.Iend, j, k); }
+    if (ew_copy && T.W) for (int j = T.Jstr; j <= T.Jend; ++j) { for (int it = 1; it <= M.NAT; ++it) Akt(T.Istr - 1, j, k, it) = Akt(T.Istr, j, k, it); Akv(T.Istr - 1, j, k) = Akv(T.Istr, j, k); }
+    if (ew_copy && T.E) for (int j = T.Jstr; j <= T.Jend; ++j) { for (int it = 1; it <= M.NAT; ++it) Akt(T.Iend + 1, j, k, it) = Akt(T.Iend, j, k, it); Akv(T.Iend + 1, j, k) = Akv(T.Iend, j, k); }
     if (T.S) for (int i = T.Istr; i <= T.Iend; ++i) { for (int it = 1; it <= M.NAT; ++it) Akt(i, T.Jstr - 1, k, it) = Akt(i, T.Jstr, k, it); Akv(i, T.Jstr - 1, k) = Akv(i, T.Jstr, k); }
     if (T.N) for (int i = T.Istr; i <= T.Iend; ++i) { for (int it = 1; it <= M.NAT; ++it) Akt(i, T.Jend + 1, k, it) = Akt(i, T.Jend, k, it); Akv(i, T.Jend + 1, k) = Akv(i, T.Jend, k); }
     auto corner = [&](int ic, int jc, int ia, int ja, int ib, int jb) {
       for (int it = 1; it <= M.NAT; ++it) Akt(ic, jc, k, it) = 0.5 * (Akt(ia, ja, k, it) + Akt(ib, jb, k, it));
       Akv(ic, jc, k) = 0.5 * (Akv(ia, ja, k) + Akv(ib, jb, k));
     };
-    if (T.S && T.W) corner(T.Istr - 1, T.Jstr - 1, T.Istr, T.Jstr - 1, T.Istr - 1, T.Jstr);
-    if (T.S && T.E) corner(T.Iend + 1, T.Jstr - 1, T.Iend, T.Jstr - 1, T.Iend + 1, T.Jstr);
-    if (T.N && T.W) corner(T.Istr - 1, T.Jend + 1, T.Istr, T.Jend + 1, T.Istr - 1, T.Jend);
-    if (T.N && T.E) corner(T.Iend + 1, T.Jend + 1, T.Iend, T.Jend + 1, T.Iend + 1, T.Jend);
+    if (ew_copy && T.S && T.W) corner(T.Istr - 1, T.Jstr - 1, T.Istr, T.Jstr - 1, T.Istr - 1, T.Jstr);
+    if (ew_copy && T.S && T.E) corner(T.Iend + 1, T.Jstr - 1, T.Iend, T.Jstr - 1, T.Iend + 1, T.Jstr);
+    if (ew_copy && T.N && T.W) corner(T.Istr - 1, T.Jend + 1, T.Istr, T.Jend + 1, T.Istr - 1, T.Jend);
+    if (ew_copy && T.N && T.E) corner(T.Iend + 1, T.Jend + 1, T.Iend, T.Jend + 1, T.Iend + 1, T.Jend);
   }
   bc_w3d(M, T, Akv);
   for (int it = 1; it <= M.NAT; ++it) bc_w3d(M, T, Akt.vol(it));

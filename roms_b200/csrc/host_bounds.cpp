@@ -65,3 +65,16 @@ extern "C" int roms_b200_tile_bounds(int Lm, int Mm, int N, int NT, int NAT, int
   }
   return 0;
 }
+
+// tile_neighbors (Utility/mp_exchange.F:73-197): ranks of the W,E,S,N neighbours of this tile
+// (rank = Jtile*NtileI+Itile); -1 where there is none.  E-W wraps periodically; an axis with a
+// single tile has no neighbour (the periodic images are written locally).
+extern "C" int roms_b200_tile_neighbors(const roms_b200_bounds* b, int* wesn) {
+  if (!b || !wesn) return 1;
+  const int It = b->Itile, Jt = b->Jtile, NI = b->NtileI, NJ = b->NtileJ;
+  wesn[0] = (NI > 1 && (b->EWperiodic || It > 0)) ? Jt * NI + (It - 1 + NI) % NI : -1;
+  wesn[1] = (NI > 1 && (b->EWperiodic || It < NI - 1)) ? Jt * NI + (It + 1) % NI : -1;
+  wesn[2] = (NJ > 1 && (b->NSperiodic || Jt > 0)) ? ((Jt - 1 + NJ) % NJ) * NI + It : -1;
+  wesn[3] = (NJ > 1 && (b->NSperiodic || Jt < NJ - 1)) ? ((Jt + 1) % NJ) * NI + It : -1;
+  return 0;
+}

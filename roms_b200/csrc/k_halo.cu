@@ -113,12 +113,7 @@ int roms_b200_comm_init(roms_b200_ctx* c, int rank, int nranks, const char* id12
   ncclComm_p comm = nullptr;
   NCCL_OK(g_nccl.CommInitRank(&comm, nranks, id, rank));
   c->comm = comm; c->rank = rank; c->nranks = nranks;
-  // tile_neighbors (mp_exchange.F:118-197): E-W periodic wrap, N-S closed
-  const int It = b.Itile, Jt = b.Jtile, NI = b.NtileI, NJ = b.NtileJ;
-  c->nbW = (NI > 1) ? Jt * NI + (It - 1 + NI) % NI : -1;
-  c->nbE = (NI > 1) ? Jt * NI + (It + 1) % NI : -1;
-  c->nbS = (Jt > 0) ? (Jt - 1) * NI + It : -1;
-  c->nbN = (Jt < NJ - 1) ? (Jt + 1) * NI + It : -1;
+  { int nb[4]; roms_b200_tile_neighbors(&b, nb); c->nbW = nb[0]; c->nbE = nb[1]; c->nbS = nb[2]; c->nbN = nb[3]; }
   // buffers: up to HALO_MAXPLANES planes of the larger strip
   const size_t strip = (size_t)c->D.halo * (size_t)((c->D.ni > c->D.nj) ? c->D.ni : c->D.nj);
   c->halo_cap = strip * HALO_MAXPLANES;

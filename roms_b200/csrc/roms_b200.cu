@@ -248,20 +248,28 @@ int roms_b200_step2d_loop(roms_b200_ctx* c, int nstp, int nnew, int iic, int ntf
   const int mode = (iic == ntfirst) ? 0 : (iic == ntfirst + 1 ? 1 : 2);
   if (!c->use_graph) { if (fast_loop_launch(c, nstp, nnew, iic, ntfirst, indx1)) return 1; LEAVE(); }
   // the launch sequence is a pure function of (indx1 at entry, nstp, AB start-up mode)
-  cudaGraphExec_t& ge = c->graph2d[((*indx1 - 1) & 1) * 6 + ((nstp - 1) & 1) * 3 + mode];
-  if (!ge) {
-    cudaGraph_t gph;
-    const long l0 = c->launches;
-    int tmp = *indx1;
-    CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    fast_loop_launch(c, nstp, nnew, iic, ntfirst, &tmp);
-    CUDA_OK(cudaStreamEndCapture(c->stream, &gph));
-    CUDA_OK(cudaGraphInstantiate(&ge, gph, 0));
-    CUDA_OK(cudaGraphDestroy(gph));
-    c->launches = l0;
+  const int key = ((*indx1 - 1) & 1) * 6 + ((nstp - 1) & 1) * 3 + mode;
+  if (!c->graph2d[key]) {
+    // build this graph; for the steady-state form (mode 2) build all four (indx1,nstp) variants at once so
+    // that no instantiation falls into a later (timed) step.  Capture records but does not execute.
+    for (int ix = 1; ix <= 2; ++ix) for (int ns = 1; ns <= 2; ++ns) {
+      const int kk = (ix - 1) * 6 + (ns - 1) * 3 + mode;
+      if (c->graph2d[kk] || (mode != 2 && kk != key)) continue;
+      cudaGraph_t gph;
+      const long l0 = c->launches;
+      int tmp = ix;
+      CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = fast_loop_launch(c, ns, 3 - ns, iic, ntfirst, &tmp);
+      CUDA_OK(cudaStreamEndCapture(c->stream, &gph));
+      if (rc) return 1;
+      CUDA_OK(cudaGraphInstantiate(&c->graph2d[kk], gph, 0));
+      CUDA_OK(cudaGraphDestroy(gph));
+      c->graph_launches[kk] = c->launches - l0;
+      c->launches = l0;
+    }
   }
-  CUDA_OK(cudaGraphLaunch(ge, c->stream));
-  c->launches += 2 * c->D.p.nfast + 1;
+  CUDA_OK(cudaGraphLaunch(c->graph2d[key], c->stream));
+  c->launches += c->graph_launches[key];
   // advance indx1 exactly as the reference does: it flips once per completed sub-step pair
   int x = *indx1;
   for (int q = 0; q < c->D.p.nfast; ++q) x = 3 - x;
