@@ -1,0 +1,243 @@
+!  roms_b200/fortran/roms_b200_mod.F90
+!
+!  ISO_C_BINDING interfaces of libroms_b200.so (include/roms_b200.h) for the
+!  Fortran host (the unmodified myroms/roms sources).  NOT compiled in this
+!  repository's image (no Fortran compiler there); INTEGRATION.md shows how it
+!  is wired in with a new cpp option B200_KERNELS next to NONLINEAR.
+!
+!  Every kernel entry point replaces the `CALL X_tile (ng, tile, ...)` line of
+!  the public wrapper `X (ng, tile)`; the wrapper keeps its wclock_on/off
+!  profiling hooks (e.g. ROMS/Nonlinear/step3d_t.F:67,113).
+!
+      MODULE roms_b200_mod
+      USE, INTRINSIC :: ISO_C_BINDING
+      implicit none
+      PUBLIC
+!
+!  Opaque device-mirror handle, one per (ng, tile) = one per MPI rank.
+!
+      type(c_ptr), save :: b200_ctx = c_null_ptr
+!
+!  BOUNDS(ng)%X(tile) integers, same order as `roms_b200_bounds`.
+!
+      TYPE, BIND(C) :: roms_b200_bounds
+        integer(c_int) :: Lm, Mm, N, NT, NAT
+        integer(c_int) :: LBi, UBi, LBj, UBj
+        integer(c_int) :: Istr, Iend, Jstr, Jend
+        integer(c_int) :: IstrR, IendR, JstrR, JendR
+        integer(c_int) :: IstrU, JstrV
+        integer(c_int) :: IstrP, IendP, JstrP, JendP
+        integer(c_int) :: IstrT, IendT, JstrT, JendT
+        integer(c_int) :: IstrB, IendB, JstrB, JendB
+        integer(c_int) :: IstrM, JstrM
+        integer(c_int) :: Istrm3, Istrm2, Istrm1, IstrUm2, IstrUm1
+        integer(c_int) :: Iendp1, Iendp2, Iendp2i, Iendp3
+        integer(c_int) :: Jstrm3, Jstrm2, Jstrm1, JstrVm2, JstrVm1
+        integer(c_int) :: Jendp1, Jendp2, Jendp2i, Jendp3
+        integer(c_int) :: Western_Edge, Eastern_Edge
+        integer(c_int) :: Southern_Edge, Northern_Edge
+        integer(c_int) :: EWperiodic, NSperiodic
+        integer(c_int) :: NtileI, NtileJ, Itile, Jtile
+      END TYPE roms_b200_bounds
+!
+!  mod_scalars / mod_param values the _tile routines read from modules.
+!
+      TYPE, BIND(C) :: roms_b200_params
+        integer(c_int) :: app
+        real(c_double) :: dt, dtfast
+        integer(c_int) :: ndtfast, nfast
+        real(c_double) :: rho0, g, gamma2, hc
+        real(c_double) :: R0, T0, S0, Tcoef, Scoef
+        real(c_double) :: Akt_bak(2), Akv_bak
+        real(c_double) :: blk_ZQ, blk_ZT, blk_ZW, dstart
+      END TYPE roms_b200_params
+
+      INTERFACE
+!
+!  Lifetime and host <-> device mirror.
+!
+        integer(c_int) FUNCTION roms_b200_create (b, p, device, ctx)    &
+     &                          BIND(C, name='roms_b200_create')
+          IMPORT
+          type(roms_b200_bounds), intent(in) :: b
+          type(roms_b200_params), intent(in) :: p
+          integer(c_int), value :: device
+          type(c_ptr), intent(out) :: ctx
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_destroy (ctx)                 &
+     &                          BIND(C, name='roms_b200_destroy')
+          IMPORT
+          type(c_ptr), value :: ctx
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_field_id (name)               &
+     &                          BIND(C, name='roms_b200_field_id')
+          IMPORT
+          character(kind=c_char), intent(in) :: name(*)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_upload (ctx, field, host)     &
+     &                          BIND(C, name='roms_b200_upload')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: field
+          type(c_ptr), value :: host          ! c_loc(OCEAN(ng)%t) ...
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_download (ctx, field, host)   &
+     &                          BIND(C, name='roms_b200_download')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: field
+          type(c_ptr), value :: host
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_set_scoord (ctx, sc_r, Cs_r,  &
+     &                                               sc_w, Cs_w)        &
+     &                          BIND(C, name='roms_b200_set_scoord')
+          IMPORT
+          type(c_ptr), value :: ctx
+          real(c_double), intent(in) :: sc_r(*), Cs_r(*), sc_w(*), Cs_w(*)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_set_weights (ctx, nfast, w1,  &
+     &                                                w2)               &
+     &                          BIND(C, name='roms_b200_set_weights')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nfast
+          real(c_double), intent(in) :: w1(*), w2(*)
+        END FUNCTION
+!
+!  Per-tile kernels (argument = the hidden module inputs of X_tile).
+!
+        integer(c_int) FUNCTION roms_b200_set_massflux (ctx, nrhs)      &
+     &                          BIND(C, name='roms_b200_set_massflux')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nrhs
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_rho_eos (ctx, nrhs)           &
+     &                          BIND(C, name='roms_b200_rho_eos')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nrhs
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_omega (ctx)                   &
+     &                          BIND(C, name='roms_b200_omega')
+          IMPORT
+          type(c_ptr), value :: ctx
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_set_zeta (ctx)                &
+     &                          BIND(C, name='roms_b200_set_zeta')
+          IMPORT
+          type(c_ptr), value :: ctx
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_set_depth (ctx)               &
+     &                          BIND(C, name='roms_b200_set_depth')
+          IMPORT
+          type(c_ptr), value :: ctx
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_bulk_flux (ctx, nrhs)         &
+     &                          BIND(C, name='roms_b200_bulk_flux')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nrhs
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_set_vbc (ctx, nrhs)           &
+     &                          BIND(C, name='roms_b200_set_vbc')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nrhs
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_lmd_vmix (ctx, nstp)          &
+     &                          BIND(C, name='roms_b200_lmd_vmix')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nstp
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_ana_vmix (ctx)                &
+     &                          BIND(C, name='roms_b200_ana_vmix')
+          IMPORT
+          type(c_ptr), value :: ctx
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_rhs3d (ctx, nrhs, nstp, nnew, &
+     &                                          iic, ntfirst)           &
+     &                          BIND(C, name='roms_b200_rhs3d')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nrhs, nstp, nnew, iic, ntfirst
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_pre_step3d (ctx, nrhs, nstp,  &
+     &                                   nnew, iic, ntfirst)            &
+     &                          BIND(C, name='roms_b200_pre_step3d')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nrhs, nstp, nnew, iic, ntfirst
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_prsgrd (ctx, nrhs)            &
+     &                          BIND(C, name='roms_b200_prsgrd')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nrhs
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_step2d (ctx, krhs, kstp, knew,&
+     &                     nstp, nnew, iif, predictor, iic, ntfirst)    &
+     &                          BIND(C, name='roms_b200_step2d')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: krhs, kstp, knew, nstp, nnew
+          integer(c_int), value :: iif, predictor, iic, ntfirst
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_step3d_uv (ctx, nrhs, nstp,   &
+     &                                   nnew, iic, ntfirst)            &
+     &                          BIND(C, name='roms_b200_step3d_uv')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nrhs, nstp, nnew, iic, ntfirst
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_step3d_t (ctx, nrhs, nstp,    &
+     &                                             nnew)                &
+     &                          BIND(C, name='roms_b200_step3d_t')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nrhs, nstp, nnew
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_diag (ctx, nstp, out3)        &
+     &                          BIND(C, name='roms_b200_diag')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nstp
+          real(c_double), intent(out) :: out3(3)
+        END FUNCTION
+!
+!  NCCL communicator (replaces mp_exchange2d/3d/4d): id from rank 0 via
+!  mpi_bcast, then every rank calls comm_init.
+!
+        integer(c_int) FUNCTION roms_b200_comm_unique_id (id128)        &
+     &                          BIND(C, name='roms_b200_comm_unique_id')
+          IMPORT
+          character(kind=c_char) :: id128(128)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_comm_init (ctx, rank, nranks, &
+     &                                              id128)              &
+     &                          BIND(C, name='roms_b200_comm_init')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: rank, nranks
+          character(kind=c_char), intent(in) :: id128(128)
+        END FUNCTION
+      END INTERFACE
+
+      CONTAINS
+!
+!  Map a non-zero return code to the reference's error convention
+!  (exit_flag=8, "fatal algorithm result", mod_scalars.F:548-561).
+!
+      SUBROUTINE b200_check (rc, line, file)
+      USE mod_scalars, ONLY : exit_flag
+      integer(c_int), intent(in) :: rc
+      integer, intent(in) :: line
+      character (len=*), intent(in) :: file
+      IF (rc.ne.0) THEN
+        exit_flag=8
+        PRINT *, 'roms_b200 kernel failed, rc = ', rc, ' at ', file, line
+      END IF
+      END SUBROUTINE b200_check
+
+      END MODULE roms_b200_mod
