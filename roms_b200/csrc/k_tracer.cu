@@ -205,6 +205,9 @@ int k_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew) {
   static const bool use_v3 = (getenv("ROMS_B200_STEP3D_T_V3") != nullptr);   // phase-separated shared-memory version
   int k_step3d_t_v4(roms_b200_ctx* c, int nnew);
   if (use_v3) return k_step3d_t_v3(c, nnew);
+  static const bool use_v5 = (getenv("ROMS_B200_STEP3D_T_V5") != nullptr);   // TMA-staged tiles
+  int k_step3d_t_v5(roms_b200_ctx* c, int nnew);
+  if (use_v5) { const int rc = k_step3d_t_v5(c, nnew); if (rc != 2) return rc; }
   if (!use_v1) return k_step3d_t_v4(c, nnew);
   const roms_b200_bounds& b = c->D.b;
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT;
