@@ -200,13 +200,10 @@ int k_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew) {
   (void)nrhs; (void)nstp;
   static const bool use_v1 = (getenv("ROMS_B200_STEP3D_T_V1") != nullptr);   // first (local-memory) version, kept for A/B timing
   static const bool use_v2 = (getenv("ROMS_B200_STEP3D_T_V2") != nullptr);   // fused-sweep shared-memory version
-  int k_step3d_t_v3(roms_b200_ctx* c, int nnew);
   if (use_v2) return k_step3d_t_v2(c, nnew);
   static const bool use_v3 = (getenv("ROMS_B200_STEP3D_T_V3") != nullptr);   // phase-separated shared-memory version
-  int k_step3d_t_v4(roms_b200_ctx* c, int nnew);
   if (use_v3) return k_step3d_t_v3(c, nnew);
   static const bool use_v5 = (getenv("ROMS_B200_STEP3D_T_V5") != nullptr);   // TMA-staged tiles
-  int k_step3d_t_v5(roms_b200_ctx* c, int nnew);
   if (use_v5) { const int rc = k_step3d_t_v5(c, nnew); if (rc != 2) return rc; }
   if (!use_v1) return k_step3d_t_v4(c, nnew);
   const roms_b200_bounds& b = c->D.b;

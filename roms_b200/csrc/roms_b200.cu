@@ -102,7 +102,7 @@ int roms_b200_destroy(roms_b200_ctx* c) {
   cudaFree((void*)c->D.sc_r); cudaFree((void*)c->D.w1); cudaFree(c->D.P); cudaFree(c->D.scratch2); cudaFree(c->D.red); cudaFree(c->D.ksbl);
   cudaFreeHost(c->h_red);
   roms_b200_comm_destroy(c);
-  { void k_step3d_t_v5_forget(roms_b200_ctx*); k_step3d_t_v5_forget(c); }
+  k_step3d_t_v5_forget(c);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
