@@ -205,6 +205,8 @@ int k_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew) {
   if (use_v3) return k_step3d_t_v3(c, nnew);
   static const bool use_v5 = (getenv("ROMS_B200_STEP3D_T_V5") != nullptr);   // TMA-staged tiles
   if (use_v5) { const int rc = k_step3d_t_v5(c, nnew); if (rc != 2) return rc; }
+  static const bool use_v4 = (getenv("ROMS_B200_STEP3D_T_V4") != nullptr);   // one-thread-per-column checkpointed Thomas
+  if (!use_v1 && !use_v4) { const int rc = k_step3d_t_v6(c, nnew); if (rc != 2) return rc; }      // production: 2.5-D j-march (k_step3d_t6.cu)
   if (!use_v1) return k_step3d_t_v4(c, nnew);
   const roms_b200_bounds& b = c->D.b;
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT;
