@@ -85,6 +85,7 @@ int roms_b200_create(const roms_b200_bounds* b, const roms_b200_params* p, int d
   c->nred_blocks = D.nj;
   if (dev_alloc(&D.red, (size_t)3 * D.nj)) return 4;
   if (dev_alloc(&D.ksbl, D.nij)) return 4;
+  if (dev_alloc(&D.err, 1)) return 4;
   CUDA_OK(cudaMallocHost((void**)&c->h_red, sizeof(double) * 3 * D.nj));
   // initialise_mixing (mod_mixing.F:1430-1530) background values are the host's job (upload Akv,Akt,...)
   c->iic = 0; c->ntfirst = 1; c->nstp = 1; c->nnew = 1; c->nrhs = 1; c->indx1 = 1; c->time = 0.0;
@@ -99,7 +100,7 @@ int roms_b200_destroy(roms_b200_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (int a = 0; a < 12; ++a) if (c->graph2d[a]) cudaGraphExecDestroy(c->graph2d[a]);
   for (int f = 0; f < ROMS_B200_NFIELDS; ++f) cudaFree(c->D.f[f]);
-  cudaFree((void*)c->D.sc_r); cudaFree((void*)c->D.w1); cudaFree(c->D.P); cudaFree(c->D.scratch2); cudaFree(c->D.red); cudaFree(c->D.ksbl);
+  cudaFree((void*)c->D.sc_r); cudaFree((void*)c->D.w1); cudaFree(c->D.P); cudaFree(c->D.scratch2); cudaFree(c->D.red); cudaFree(c->D.ksbl); cudaFree(c->D.err);
   cudaFreeHost(c->h_red);
   roms_b200_comm_destroy(c);
   k_step3d_t_v5_forget(c);
@@ -156,7 +157,13 @@ int roms_b200_download_interior(roms_b200_ctx* c, int f, int plane0, int nplanes
   return 0;
 }
 void* roms_b200_device_ptr(roms_b200_ctx* c, int f) { return (f < 0 || f >= ROMS_B200_NFIELDS) ? nullptr : (void*)c->D.f[f]; }
-int roms_b200_sync(roms_b200_ctx* c) { CUDA_OK(cudaStreamSynchronize(c->stream)); CUDA_OK(cudaGetLastError()); return 0; }
+int roms_b200_sync(roms_b200_ctx* c) {
+  CUDA_OK(cudaStreamSynchronize(c->stream)); CUDA_OK(cudaGetLastError());
+  int err = 0;                                   // device-side "fatal algorithm result" word -> exit_flag=8 (mod_scalars.F:548-561)
+  CUDA_OK(cudaMemcpy(&err, c->D.err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) { fprintf(stderr, "roms_b200: device error word 0x%x (non-finite or out-of-range reciprocal operand: blown-up state)\n", err); return 8; }
+  return 0;
+}
 long roms_b200_launch_count(const roms_b200_ctx* c) { return c->launches; }
 
 #define ENTER(c) do { if (!(c)) return 1; CUDA_OK(cudaSetDevice((c)->device)); } while (0)
