@@ -147,48 +147,57 @@ __device__ __forceinline__ double q_FCw(const V3& q, const V3& W, int i, int j, 
   if (k == N - 1) return (c1 * (q(i, j, N - 1) + q(i, j, N)) - c2 * (q(i, j, N - 2) + q(i, j, N))) * wt;
   return (c1 * (q(i, j, k) + q(i, j, k + 1)) - c2 * (q(i, j, k - 1) + q(i, j, k + 2))) * wt;
 }
+// One thread per (i,j,k,component): Coriolis, curvilinear, U3 horizontal and C4 vertical advection have no vertical recurrence
+// (the vertical flux at w-level k-1 is re-evaluated).  The vertical integrals rufrc/rvfrc (rhs3d.F:1707-1916) are summed in
+// the reference's order by rhs3d_sum_kernel (one thread per column and component).
 __global__ void __launch_bounds__(256) rhs3d_kernel(const Dev D, Box bx, int nrhs) {
   IJ_FROM_BOX(bx);
-  const roms_b200_bounds& b = D.b; const int N = b.N;
+  const roms_b200_bounds& b = D.b; const int N = b.N, k = 1 + blockIdx.z % N, comp = blockIdx.z / N;
   RQ Q{v3l(D, FID(u), nrhs), v3l(D, FID(v), nrhs), v3(D, FID(Hz)), v3(D, FID(Huon)), v3(D, FID(Hvom)), v3(D, FID(W)),
        v2(D, FID(fomn)), v2(D, FID(dndx)), v2(D, FID(dmde)), D.p.app == ROMS_B200_APP_BENCHMARK,
        b.Southern_Edge && !b.NSperiodic, b.Northern_Edge && !b.NSperiodic, b.Jstr, b.Jend};
-  const bool doU = (i >= b.IstrU && i <= b.Iend && j >= b.Jstr && j <= b.Jend);
-  const bool doV = (i >= b.Istr && i <= b.Iend && j >= b.JstrV && j <= b.Jend);
-  if (doU) {
+  if (comp == 0) {
+    if (!(i >= b.IstrU && i <= b.Iend && j >= b.Jstr && j <= b.Jend)) return;
     V3 ru = v3l(D, FID(ru), nrhs);
-    double sum = 0.0, FCm = 0.0;
-    for (int k = 1; k <= N; ++k) {
-      double r = ru(i, j, k), a0, a1, dmy;
-      q_cor(Q, i, j, k, a0, dmy); q_cor(Q, i - 1, j, k, a1, dmy);
-      r = r + 0.5 * (a0 + a1);
-      if (Q.curv) { q_curv(Q, i, j, k, a0, dmy); q_curv(Q, i - 1, j, k, a1, dmy); r = r + 0.5 * (a0 + a1); }
-      const double c1 = q_UFx(Q, i, j, k) - q_UFx(Q, i - 1, j, k), c2 = q_UFe(Q, i, j + 1, k) - q_UFe(Q, i, j, k);
-      r = r - (c1 + c2);
-      const double FCk = q_FCw(Q.u, Q.W, i, j, k, N, 1, 0);
-      r = r - (FCk - FCm); FCm = FCk;
-      ru(i, j, k) = r;
-      sum = (k == 1) ? r : sum + r;
-    }
+    double r = ru(i, j, k), a0, a1, dmy;
+    q_cor(Q, i, j, k, a0, dmy); q_cor(Q, i - 1, j, k, a1, dmy);
+    r = r + 0.5 * (a0 + a1);
+    if (Q.curv) { q_curv(Q, i, j, k, a0, dmy); q_curv(Q, i - 1, j, k, a1, dmy); r = r + 0.5 * (a0 + a1); }
+    const double c1 = q_UFx(Q, i, j, k) - q_UFx(Q, i - 1, j, k), c2 = q_UFe(Q, i, j + 1, k) - q_UFe(Q, i, j, k);
+    r = r - (c1 + c2);
+    const double FCk = q_FCw(Q.u, Q.W, i, j, k, N, 1, 0), FCm = q_FCw(Q.u, Q.W, i, j, k - 1, N, 1, 0);
+    r = r - (FCk - FCm);
+    ru(i, j, k) = r;
+  } else {
+    if (!(i >= b.Istr && i <= b.Iend && j >= b.JstrV && j <= b.Jend)) return;
+    V3 rv = v3l(D, FID(rv), nrhs);
+    double r = rv(i, j, k), a0, a1, dmy;
+    q_cor(Q, i, j, k, dmy, a0); q_cor(Q, i, j - 1, k, dmy, a1);
+    r = r - 0.5 * (a0 + a1);
+    if (Q.curv) { q_curv(Q, i, j, k, dmy, a0); q_curv(Q, i, j - 1, k, dmy, a1); r = r - 0.5 * (a0 + a1); }
+    const double c1 = q_VFx(Q, i + 1, j, k) - q_VFx(Q, i, j, k), c2 = q_VFe(Q, i, j, k) - q_VFe(Q, i, j - 1, k);
+    r = r - (c1 + c2);
+    const double FCk = q_FCw(Q.v, Q.W, i, j, k, N, 0, 1), FCm = q_FCw(Q.v, Q.W, i, j, k - 1, N, 0, 1);
+    r = r - (FCk - FCm);
+    rv(i, j, k) = r;
+  }
+}
+__global__ void __launch_bounds__(128) rhs3d_sum_kernel(const Dev D, Box bx, int nrhs) {
+  IJ_FROM_BOX(bx);
+  const roms_b200_bounds& b = D.b; const int N = b.N, comp = blockIdx.z;
+  if (comp == 0) {
+    if (!(i >= b.IstrU && i <= b.Iend && j >= b.Jstr && j <= b.Jend)) return;
+    V3 ru = v3l(D, FID(ru), nrhs);
+    double sum = ru(i, j, 1);
+    for (int k = 2; k <= N; ++k) sum = sum + ru(i, j, k);
     const double cff = v2(D, FID(om_u))(i, j) * v2(D, FID(on_u))(i, j);
     const double s1 = v2(D, FID(sustr))(i, j) * cff, s2 = -v2(D, FID(bustr))(i, j) * cff;
     v2(D, FID(rufrc))(i, j) = sum + s1 + s2;
-  }
-  if (doV) {
+  } else {
+    if (!(i >= b.Istr && i <= b.Iend && j >= b.JstrV && j <= b.Jend)) return;
     V3 rv = v3l(D, FID(rv), nrhs);
-    double sum = 0.0, FCm = 0.0;
-    for (int k = 1; k <= N; ++k) {
-      double r = rv(i, j, k), a0, a1, dmy;
-      q_cor(Q, i, j, k, dmy, a0); q_cor(Q, i, j - 1, k, dmy, a1);
-      r = r - 0.5 * (a0 + a1);
-      if (Q.curv) { q_curv(Q, i, j, k, dmy, a0); q_curv(Q, i, j - 1, k, dmy, a1); r = r - 0.5 * (a0 + a1); }
-      const double c1 = q_VFx(Q, i + 1, j, k) - q_VFx(Q, i, j, k), c2 = q_VFe(Q, i, j, k) - q_VFe(Q, i, j - 1, k);
-      r = r - (c1 + c2);
-      const double FCk = q_FCw(Q.v, Q.W, i, j, k, N, 0, 1);
-      r = r - (FCk - FCm); FCm = FCk;
-      rv(i, j, k) = r;
-      sum = (k == 1) ? r : sum + r;
-    }
+    double sum = rv(i, j, 1);
+    for (int k = 2; k <= N; ++k) sum = sum + rv(i, j, k);
     const double cff = v2(D, FID(om_v))(i, j) * v2(D, FID(on_v))(i, j);
     const double s1 = v2(D, FID(svstr))(i, j) * cff, s2 = -v2(D, FID(bvstr))(i, j) * cff;
     v2(D, FID(rvfrc))(i, j) = sum + s1 + s2;
@@ -196,8 +205,10 @@ __global__ void __launch_bounds__(256) rhs3d_kernel(const Dev D, Box bx, int nrh
 }
 int k_rhs3d_tile(roms_b200_ctx* c, int nrhs) {
   const roms_b200_bounds& b = c->D.b;
-  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8);
-  rhs3d_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx, nrhs); c->launches++;
+  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = 2 * b.N;
+  rhs3d_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs); c->launches++;
+  dim3 blk2(32, 4); dim3 g2 = grid2(bx, blk2); g2.z = 2;
+  rhs3d_sum_kernel<<<g2, blk2, 0, c->stream>>>(c->D, bx, nrhs); c->launches++;
   return 0;
 }
 

@@ -10,21 +10,21 @@
 // a benchmark-size tile (~50 planes x 277 KB) stays resident in the 126 MB L2.
 #include "common.cuh"
 
+// Block tile: 32 x 4 points.  Drhs, DUon, DVom (step2d_LF_AM3.h:664-702) are evaluated ONCE per point of the tile plus the
+// halo the 4th-order fluxes reach (3 west/south, 2 east/north) into shared memory; everything downstream reads them there
+// (the first layout re-evaluated them per use: ~100 DUon/DVom per thread).  Same operations on the same operands -> same bits.
+constexpr int S2_TX = 32, S2_TY = 4, S2_TW = S2_TX + 5, S2_TH = S2_TY + 5;
 struct S2 {
   V2 zk, zs, ub, vb;                      // zeta(:,:,krhs), zeta(:,:,kstp), ubar/vbar(:,:,krhs)
   V2 h, pm, pn, on_u, om_v, rhoA, rhoS, rzs, rzp;   // rzeta(:,:,kstp), rzeta(:,:,ptsk)
   double fac, dtfast; int mode;           // mode: 0 iif==1, 1 predictor, 2 corrector
   int S, N, Jstr, Jend;
+  const double *tDr, *tDU, *tDV;          // shared-memory tiles, element (i,j) at (i-ti0) + S2_TW*(j-tj0)
+  int ti0, tj0;
 };
-__device__ __forceinline__ double Drhs(const S2& s, int i, int j) { return s.zk(i, j) + s.h(i, j); }
-__device__ __forceinline__ double DUon(const S2& s, int i, int j) {
-  const double cff = 0.5 * s.on_u(i, j); const double cff1 = cff * (Drhs(s, i, j) + Drhs(s, i - 1, j));
-  return s.ub(i, j) * cff1;
-}
-__device__ __forceinline__ double DVom(const S2& s, int i, int j) {
-  const double cff = 0.5 * s.om_v(i, j); const double cff1 = cff * (Drhs(s, i, j) + Drhs(s, i, j - 1));
-  return s.vb(i, j) * cff1;
-}
+__device__ __forceinline__ double Drhs(const S2& s, int i, int j) { return s.tDr[(i - s.ti0) + S2_TW * (j - s.tj0)]; }
+__device__ __forceinline__ double DUon(const S2& s, int i, int j) { return s.tDU[(i - s.ti0) + S2_TW * (j - s.tj0)]; }
+__device__ __forceinline__ double DVom(const S2& s, int i, int j) { return s.tDV[(i - s.ti0) + S2_TW * (j - s.tj0)]; }
 struct Zst { double rhs_zeta, zn, Dnew, zwrk, gzeta, gzeta2, gzetaSA; };
 // step2d_LF_AM3.h:899-980
 __device__ __forceinline__ Zst zstate(const S2& s, int i, int j) {
@@ -113,8 +113,9 @@ __device__ __forceinline__ void c_curv(const S2& s, const V2D& m, int i, int j, 
 
 struct Step2dArgs { int krhs, kstp, knew, nstp, nnew, iif, pred, stepmode; };  // stepmode: 0 iic==ntfirst, 1 ntfirst+1, 2 later
 
-__global__ void __launch_bounds__(128) step2d_kernel(const Dev D, Box bx, Step2dArgs a) {
-  IJ_FROM_BOX(bx);
+__global__ void __launch_bounds__(S2_TX * S2_TY) step2d_kernel(const Dev D, Box bx, Step2dArgs a) {
+  __shared__ double tDr[S2_TW * S2_TH], tDU[S2_TW * S2_TH], tDV[S2_TW * S2_TH];
+  const int i = bx.i0 + blockIdx.x * S2_TX + threadIdx.x, j = bx.j0 + blockIdx.y * S2_TY + threadIdx.y;
   const roms_b200_bounds& b = D.b;
   const int krhs = a.krhs, kstp = a.kstp, knew = a.knew, iif = a.iif, ptsk = 3 - kstp;
   const bool PRED = a.pred != 0;
@@ -122,7 +123,34 @@ __global__ void __launch_bounds__(128) step2d_kernel(const Dev D, Box bx, Step2d
        v2(D, FID(h)), v2(D, FID(pm)), v2(D, FID(pn)), v2(D, FID(on_u)), v2(D, FID(om_v)), v2(D, FID(rhoA)), v2(D, FID(rhoS)),
        v2l(D, FID(rzeta), kstp > 2 ? 1 : kstp), v2l(D, FID(rzeta), ptsk < 1 ? 1 : ptsk),
        1000.0 / D.p.rho0, D.p.dtfast, (iif == 1) ? 0 : (PRED ? 1 : 2),
-       b.Southern_Edge && !b.NSperiodic, b.Northern_Edge && !b.NSperiodic, b.Jstr, b.Jend};
+       b.Southern_Edge && !b.NSperiodic, b.Northern_Edge && !b.NSperiodic, b.Jstr, b.Jend,
+       tDr, tDU, tDV, bx.i0 + (int)blockIdx.x * S2_TX - 3, bx.j0 + (int)blockIdx.y * S2_TY - 3};
+  {
+    // ---- shared tiles: Drhs on [I0-3,I1+2]x[J0-3,J1+2], then DUon/DVom where Drhs(i-1)/(j-1) exist (:664-702)
+    const int tid = threadIdx.y * S2_TX + threadIdx.x;
+    for (int q = tid; q < S2_TW * S2_TH; q += S2_TX * S2_TY) {
+      const int ii = s.ti0 + q % S2_TW, jj = s.tj0 + q / S2_TW;
+      const bool in = (ii >= b.LBi && ii <= b.UBi && jj >= b.LBj && jj <= b.UBj);
+      tDr[q] = in ? (s.zk(ii, jj) + s.h(ii, jj)) : 0.0;
+    }
+    __syncthreads();
+    for (int q = tid; q < S2_TW * S2_TH; q += S2_TX * S2_TY) {
+      const int qi = q % S2_TW, qj = q / S2_TW, ii = s.ti0 + qi, jj = s.tj0 + qj;
+      const bool in = (ii >= b.LBi && ii <= b.UBi && jj >= b.LBj && jj <= b.UBj);
+      double du = 0.0, dv = 0.0;
+      if (in && qi >= 1 && ii - 1 >= b.LBi) {
+        const double cff = 0.5 * s.on_u(ii, jj); const double cff1 = cff * (tDr[q] + tDr[q - 1]);
+        du = s.ub(ii, jj) * cff1;
+      }
+      if (in && qj >= 1 && jj - 1 >= b.LBj) {
+        const double cff = 0.5 * s.om_v(ii, jj); const double cff1 = cff * (tDr[q] + tDr[q - S2_TW]);
+        dv = s.vb(ii, jj) * cff1;
+      }
+      tDU[q] = du; tDV[q] = dv;
+    }
+    __syncthreads();
+  }
+  if (i > bx.i1 || j > bx.j1) return;
   // ---- fast-time averaging (:742-810)
   {
     V2 Zt = v2(D, FID(Zt_avg1)), DU1 = v2(D, FID(DU_avg1)), DU2 = v2(D, FID(DU_avg2)), DV1 = v2(D, FID(DV_avg1)), DV2 = v2(D, FID(DV_avg2));
@@ -237,7 +265,7 @@ __global__ void __launch_bounds__(128) step2d_kernel(const Dev D, Box bx, Step2d
 int k_step2d(roms_b200_ctx* c, int krhs, int kstp, int knew, int nstp, int nnew, int iif, int pred, int iic, int ntfirst) {
   const roms_b200_bounds& b = c->D.b;
   Step2dArgs a{krhs, kstp, knew, nstp, nnew, iif, pred, (iic == ntfirst) ? 0 : (iic == ntfirst + 1 ? 1 : 2)};
-  Box bx{b.IstrR, b.IendR, b.JstrR, b.JendR}; dim3 blk(32, 4);
+  Box bx{b.IstrR, b.IendR, b.JstrR, b.JendR}; dim3 blk(S2_TX, S2_TY);
   step2d_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx, a); c->launches++;
   return 0;
 }

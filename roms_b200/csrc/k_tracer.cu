@@ -54,9 +54,12 @@ __device__ __forceinline__ double swfrac(int Jindex, double Z) {
 }
 
 // ---- pre_step3d_tile, tracer part: pre_step3d.F:329-344,406-932,1152-1168 -----
+// One thread per (i,j,k,tracer).  Nothing here is a vertical recurrence: the vertical flux differences only need the
+// flux at w-level k-1, which the thread re-evaluates (same operations on the same operands -> same bits as the column
+// march of the reference), so all levels run in parallel (30x more warps on a BENCHMARK-size tile).
 __global__ void __launch_bounds__(256) pre_step3d_t_kernel(const Dev D, Box bx, int nstp, int nnew, int first) {
   IJ_FROM_BOX(bx);
-  const int itrc = 1 + blockIdx.z, N = D.b.N; const double dt = D.p.dt;
+  const int N = D.b.N, k = 1 + blockIdx.z % N, itrc = 1 + blockIdx.z / N; const double dt = D.p.dt;
   const Edges e = edges(D);
   V3 Hz = v3(D, FID(Hz)), Huon = v3(D, FID(Huon)), Hvom = v3(D, FID(Hvom)), W = v3(D, FID(W)), z_r = v3(D, FID(z_r));
   V3 tn = v3l(D, FID(t), nstp, itrc), tw = v3l(D, FID(t), nnew, itrc), t3 = v3l(D, FID(t), 3, itrc);
@@ -65,83 +68,75 @@ __global__ void __launch_bounds__(256) pre_step3d_t_kernel(const Dev D, Box bx, 
   const double Gamma = 1.0 / 6.0;
   double cff, cff1, cff2;
   if (first) { cff = 0.5 * dt; cff1 = 1.0; cff2 = 0.0; } else { cff = (1.0 - Gamma) * dt; cff1 = 0.5 + Gamma; cff2 = 0.5 - Gamma; }
-  // horizontal predictor level by level, then the vertical part with artificial continuity
-  double FCm = 0.0;                      // FC(k-1)
   const double cpm = cff * pmn_pm * pmn_pn;
-  for (int k = 1; k <= N; ++k) {
+  const double hz = Hz(i, j, k), tnk = tn(i, j, k);
+  {
+    // horizontal predictor, then the vertical part with artificial continuity
     const double FXi = fluxX_u3(tn, Huon, i, j, k), FXp = fluxX_u3(tn, Huon, i + 1, j, k);
     const double FEj = fluxE_u3(tn, Hvom, i, j, k, e), FEp = fluxE_u3(tn, Hvom, i, j + 1, k, e);
-    const double hz = Hz(i, j, k);
-    double t3h = hz * (cff1 * tn(i, j, k) + cff2 * tw(i, j, k)) - cpm * (FXp - FXi + FEp - FEj);
-    const double FCk = fluxZ_c4(tn, W, i, j, k, N);
+    double t3h = hz * (cff1 * tnk + cff2 * tw(i, j, k)) - cpm * (FXp - FXi + FEp - FEj);
+    const double FCk = fluxZ_c4(tn, W, i, j, k, N), FCm = fluxZ_c4(tn, W, i, j, k - 1, N);
     const double DC = 1.0 / (hz - cpm * (Huon(i + 1, j, k) - Huon(i, j, k) + Hvom(i, j + 1, k) - Hvom(i, j, k) + (W(i, j, k) - W(i, j, k - 1))));
     t3h = DC * (t3h - cpm * (FCk - FCm));
     st_tbc(D, t3, i, j, k, t3h, e);
-    FCm = FCk;
   }
   // t(nnew) = Hz*t(nstp) + explicit vertical terms (pre_step3d.F:863-932)
   const double cff3 = dt * (1.0 - 1.0 /*lambda*/);
   const bool bench = (D.p.app == ROMS_B200_APP_BENCHMARK);
-  const double btf = v2l(D, FID(btflx), itrc)(i, j), stf = v2l(D, FID(stflx), itrc)(i, j);
   double srf = 0.0, zwN = 0.0; int Jw = 1; V3 gh = v3l(D, FID(ghats), min(D.b.NAT, itrc)); V3 z_w = v3(D, FID(z_w));
-  if (bench) { srf = v2(D, FID(srflx))(i, j); zwN = z_w(i, j, N); Jw = (int)v2(D, FID(Jwtype))(i, j); }
-  double Fm = dt * btf;                  // FC(0)
-  for (int k = 1; k <= N; ++k) {
-    double Fk;
-    if (k < N) {
-      const double c = 1.0 / (z_r(i, j, k + 1) - z_r(i, j, k));
-      Fk = cff3 * c * Akt(i, j, k) * (tn(i, j, k + 1) - tn(i, j, k));
-      if (bench) {
-        if (itrc <= D.b.NAT) Fk = Fk - dt * Akt(i, j, k) * gh(i, j, k);
-        if (itrc == 1) Fk = Fk + dt * srf * swfrac(Jw, zwN - z_w(i, j, k));
-      }
-    } else Fk = dt * stf;
-    const double a = Hz(i, j, k) * tn(i, j, k), bdiff = Fk - Fm;
-    tw(i, j, k) = a + bdiff;
-    Fm = Fk;
-  }
+  if (bench && itrc == 1) { srf = v2(D, FID(srflx))(i, j); zwN = z_w(i, j, N); Jw = (int)v2(D, FID(Jwtype))(i, j); }
+  auto vflx = [&](int kk) -> double {                 // FC at w-level kk (0: bottom flux, N: surface flux)
+    if (kk == 0) return dt * v2l(D, FID(btflx), itrc)(i, j);
+    if (kk == N) return dt * v2l(D, FID(stflx), itrc)(i, j);
+    const double c = 1.0 / (z_r(i, j, kk + 1) - z_r(i, j, kk));
+    double F = cff3 * c * Akt(i, j, kk) * (tn(i, j, kk + 1) - tn(i, j, kk));
+    if (bench) {
+      if (itrc <= D.b.NAT) F = F - dt * Akt(i, j, kk) * gh(i, j, kk);
+      if (itrc == 1) F = F + dt * srf * swfrac(Jw, zwN - z_w(i, j, kk));
+    }
+    return F;
+  };
+  const double Fk = vflx(k), Fm = vflx(k - 1);
+  const double a = hz * tnk, bdiff = Fk - Fm;
+  tw(i, j, k) = a + bdiff;
 }
 
 // ---- pre_step3d_tile, momentum part: pre_step3d.F:943-1144 ------------------------
+// One thread per (i,j,k,component); the flux at w-level k-1 is re-evaluated instead of carried.
 __global__ void __launch_bounds__(256) pre_step3d_uv_kernel(const Dev D, Box bx, int nrhs, int nstp, int nnew, int mode) {
   IJ_FROM_BOX(bx);
-  const roms_b200_bounds& b = D.b; const int N = b.N; const double dt = D.p.dt;
+  const roms_b200_bounds& b = D.b; const int N = b.N, k = 1 + blockIdx.z % N, comp = blockIdx.z / N; const double dt = D.p.dt;
   V3 Hz = v3(D, FID(Hz)), z_r = v3(D, FID(z_r)), Akv = v3(D, FID(Akv));
   V2 pm = v2(D, FID(pm)), pn = v2(D, FID(pn));
   const int indx = 3 - nrhs;
   const double cff3 = dt * (1.0 - 1.0 /*lambda*/);
-  for (int comp = 0; comp < 2; ++comp) {
-    const int di = comp == 0 ? 1 : 0, dj = 1 - di;   // neighbour offset of the staggered point
-    if (comp == 0 && !(i >= b.IstrU && i <= b.Iend && j >= b.Jstr && j <= b.Jend)) continue;
-    if (comp == 1 && !(i >= b.Istr && i <= b.Iend && j >= b.JstrV && j <= b.Jend)) continue;
-    V3 q = v3l(D, comp == 0 ? FID(u) : FID(v), nstp), qn = v3l(D, comp == 0 ? FID(u) : FID(v), nnew);
-    V3 r1 = v3l(D, comp == 0 ? FID(ru) : FID(rv), nrhs), r2 = v3l(D, comp == 0 ? FID(ru) : FID(rv), indx);
-    const double bstr = v2(D, comp == 0 ? FID(bustr) : FID(bvstr))(i, j), sstr = v2(D, comp == 0 ? FID(sustr) : FID(svstr))(i, j);
-    const double DC0 = (dt * 0.25) * (pm(i, j) + pm(i - di, j - dj)) * (pn(i, j) + pn(i - di, j - dj));
-    double Fm = dt * bstr;
-    for (int k = 1; k <= N; ++k) {
-      double Fk;
-      if (k < N) {
-        const double c = 1.0 / (z_r(i, j, k + 1) + z_r(i - di, j - dj, k + 1) - z_r(i, j, k) - z_r(i - di, j - dj, k));
-        Fk = cff3 * c * (q(i, j, k + 1) - q(i, j, k)) * (Akv(i, j, k) + Akv(i - di, j - dj, k));
-      } else Fk = dt * sstr;
-      const double a = q(i, j, k) * 0.5 * (Hz(i, j, k) + Hz(i - di, j - dj, k));
-      const double d = Fk - Fm;
-      double val;
-      if (mode == 0) val = a + d;
-      else if (mode == 1) { const double c3 = 0.5 * DC0; val = a - c3 * r2(i, j, k) + d; }
-      else val = a + DC0 * ((5.0 / 12.0) * r1(i, j, k) - (16.0 / 12.0) * r2(i, j, k)) + d;
-      qn(i, j, k) = val;
-      Fm = Fk;
-    }
-  }
+  const int di = comp == 0 ? 1 : 0, dj = 1 - di;   // neighbour offset of the staggered point
+  if (comp == 0 && !(i >= b.IstrU && i <= b.Iend && j >= b.Jstr && j <= b.Jend)) return;
+  if (comp == 1 && !(i >= b.Istr && i <= b.Iend && j >= b.JstrV && j <= b.Jend)) return;
+  V3 q = v3l(D, comp == 0 ? FID(u) : FID(v), nstp), qn = v3l(D, comp == 0 ? FID(u) : FID(v), nnew);
+  V3 r1 = v3l(D, comp == 0 ? FID(ru) : FID(rv), nrhs), r2 = v3l(D, comp == 0 ? FID(ru) : FID(rv), indx);
+  const double DC0 = (dt * 0.25) * (pm(i, j) + pm(i - di, j - dj)) * (pn(i, j) + pn(i - di, j - dj));
+  auto vflx = [&](int kk) -> double {
+    if (kk == 0) return dt * v2(D, comp == 0 ? FID(bustr) : FID(bvstr))(i, j);
+    if (kk == N) return dt * v2(D, comp == 0 ? FID(sustr) : FID(svstr))(i, j);
+    const double c = 1.0 / (z_r(i, j, kk + 1) + z_r(i - di, j - dj, kk + 1) - z_r(i, j, kk) - z_r(i - di, j - dj, kk));
+    return cff3 * c * (q(i, j, kk + 1) - q(i, j, kk)) * (Akv(i, j, kk) + Akv(i - di, j - dj, kk));
+  };
+  const double Fk = vflx(k), Fm = vflx(k - 1);
+  const double a = q(i, j, k) * 0.5 * (Hz(i, j, k) + Hz(i - di, j - dj, k));
+  const double d = Fk - Fm;
+  double val;
+  if (mode == 0) val = a + d;
+  else if (mode == 1) { const double c3 = 0.5 * DC0; val = a - c3 * r2(i, j, k) + d; }
+  else val = a + DC0 * ((5.0 / 12.0) * r1(i, j, k) - (16.0 / 12.0) * r2(i, j, k)) + d;
+  qn(i, j, k) = val;
 }
 
 int k_pre_step3d(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntfirst) {
   const roms_b200_bounds& b = c->D.b;
-  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT;
+  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT * b.N;
   pre_step3d_t_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nstp, nnew, iic == ntfirst ? 1 : 0); c->launches++;
-  g.z = 1;
+  g.z = 2 * b.N;
   const int mode = (iic == ntfirst) ? 0 : (iic == ntfirst + 1 ? 1 : 2);
   pre_step3d_uv_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs, nstp, nnew, mode); c->launches++;
   return 0;
@@ -282,15 +277,20 @@ __device__ __forceinline__ double g_FS(const GeoQ& G, const V2& d2, int i, int j
   FS = FS + cff * (c1 * (c1 * tz - tx_a) + c2 * (c2 * tz - tx_b) + c3 * (c3 * tz - tx_c) + c4 * (c4 * tz - tx_d));
   return FS;
 }
+// One thread per (i,j,chunk of GEO_KCH levels,tracer): nothing in this operator is a vertical recurrence, so chunks of levels
+// run in parallel; FS(k-1) is carried inside a chunk and re-evaluated at its first level (same operations -> same bits).
+// (One level per thread doubles the expensive FS work and was measured slower: 168 vs 129 us on 512x64x30.)
+constexpr int GEO_KCH = 5;
 __global__ void __launch_bounds__(256) t3dmix2_geo_kernel(const Dev D, Box bx, int nrhs, int nnew) {
   IJ_FROM_BOX(bx);
-  const int N = D.b.N, itrc = 1 + blockIdx.z; const double dt = D.p.dt;
+  const int N = D.b.N, nch = (N + GEO_KCH - 1) / GEO_KCH, k0 = 1 + GEO_KCH * (blockIdx.z % nch), itrc = 1 + blockIdx.z / nch; const double dt = D.p.dt;
+  const int k1 = min(k0 + GEO_KCH - 1, N);
   V3 Hz = v3(D, FID(Hz)), tw = v3l(D, FID(t), nnew, itrc);
   GeoQ G{v3(D, FID(z_r)), v3l(D, FID(t), nrhs, itrc), v2(D, FID(pm)), v2(D, FID(pn)), N};
   V2 d2 = v2l(D, FID(diff2), itrc), on_u = v2(D, FID(on_u)), om_v = v2(D, FID(om_v));
   const double cff = dt * G.pm(i, j) * G.pn(i, j);
-  double FSm = 0.0;                      // FS at w-level k-1
-  for (int k = 1; k <= N; ++k) {
+  double FSm = g_FS(G, d2, i, j, k0 - 1);        // FS at w-level k-1
+  for (int k = k0; k <= k1; ++k) {
     const double FX0 = g_FX(G, Hz, d2, on_u, i, j, k), FX1 = g_FX(G, Hz, d2, on_u, i + 1, j, k);
     const double FE0 = g_FE(G, Hz, d2, om_v, i, j, k), FE1 = g_FE(G, Hz, d2, om_v, i, j + 1, k);
     const double FSk = g_FS(G, d2, i, j, k);
@@ -304,7 +304,7 @@ int k_t3dmix2(roms_b200_ctx* c, int nrhs, int nstp, int nnew) {
   const roms_b200_bounds& b = c->D.b;
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT;
   if (c->D.p.app == ROMS_B200_APP_UPWELLING) t3dmix2_s_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs, nnew);
-  else t3dmix2_geo_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs, nnew);
+  else { g.z = b.NT * ((b.N + GEO_KCH - 1) / GEO_KCH); t3dmix2_geo_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs, nnew); }
   c->launches++;
   return 0;
 }
