@@ -113,7 +113,9 @@ __device__ __forceinline__ void c_curv(const S2& s, const V2D& m, int i, int j, 
 
 struct Step2dArgs { int krhs, kstp, knew, nstp, nnew, iif, pred, stepmode; };  // stepmode: 0 iic==ntfirst, 1 ntfirst+1, 2 later
 
-__global__ void __launch_bounds__(S2_TX * S2_TY) step2d_kernel(const Dev D, Box bx, Step2dArgs a) {
+// Threads (x,y) = point of the tile, z = momentum component: z=0 advances zeta, the fast-time averages and ubar,
+// z=1 advances vbar (both evaluate the free-surface state they need from the shared tiles).
+__global__ void __launch_bounds__(S2_TX * S2_TY * 2) step2d_kernel(const Dev D, Box bx, Step2dArgs a) {
   __shared__ double tDr[S2_TW * S2_TH], tDU[S2_TW * S2_TH], tDV[S2_TW * S2_TH];
   const int i = bx.i0 + blockIdx.x * S2_TX + threadIdx.x, j = bx.j0 + blockIdx.y * S2_TY + threadIdx.y;
   const roms_b200_bounds& b = D.b;
@@ -127,14 +129,14 @@ __global__ void __launch_bounds__(S2_TX * S2_TY) step2d_kernel(const Dev D, Box 
        tDr, tDU, tDV, bx.i0 + (int)blockIdx.x * S2_TX - 3, bx.j0 + (int)blockIdx.y * S2_TY - 3};
   {
     // ---- shared tiles: Drhs on [I0-3,I1+2]x[J0-3,J1+2], then DUon/DVom where Drhs(i-1)/(j-1) exist (:664-702)
-    const int tid = threadIdx.y * S2_TX + threadIdx.x;
-    for (int q = tid; q < S2_TW * S2_TH; q += S2_TX * S2_TY) {
+    const int tid = (threadIdx.z * S2_TY + threadIdx.y) * S2_TX + threadIdx.x;
+    for (int q = tid; q < S2_TW * S2_TH; q += S2_TX * S2_TY * 2) {
       const int ii = s.ti0 + q % S2_TW, jj = s.tj0 + q / S2_TW;
       const bool in = (ii >= b.LBi && ii <= b.UBi && jj >= b.LBj && jj <= b.UBj);
       tDr[q] = in ? (s.zk(ii, jj) + s.h(ii, jj)) : 0.0;
     }
     __syncthreads();
-    for (int q = tid; q < S2_TW * S2_TH; q += S2_TX * S2_TY) {
+    for (int q = tid; q < S2_TW * S2_TH; q += S2_TX * S2_TY * 2) {
       const int qi = q % S2_TW, qj = q / S2_TW, ii = s.ti0 + qi, jj = s.tj0 + qj;
       const bool in = (ii >= b.LBi && ii <= b.UBi && jj >= b.LBj && jj <= b.UBj);
       double du = 0.0, dv = 0.0;
@@ -151,8 +153,9 @@ __global__ void __launch_bounds__(S2_TX * S2_TY) step2d_kernel(const Dev D, Box 
     __syncthreads();
   }
   if (i > bx.i1 || j > bx.j1) return;
+  const int mycomp = threadIdx.z;
   // ---- fast-time averaging (:742-810)
-  {
+  if (mycomp == 0) {
     V2 Zt = v2(D, FID(Zt_avg1)), DU1 = v2(D, FID(DU_avg1)), DU2 = v2(D, FID(DU_avg2)), DV1 = v2(D, FID(DV_avg1)), DV2 = v2(D, FID(DV_avg2));
     const bool last = (iif == D.p.nfast + 1) && PRED;    // auxiliary pass: periodic images of the averages (:821-855)
     const bool inR = (i >= b.IstrR && i <= b.IendR && j >= b.JstrR && j <= b.JendR);
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(S2_TX * S2_TY) step2d_kernel(const Dev D, Box 
   const bool south = s.S && j == b.Jstr, north = s.N && j == b.Jend;
   // ---- free surface (:899-1072)
   const Zst z0 = zstate(s, i, j);
-  {
+  if (mycomp == 0) {
     V2 zn = v2l(D, FID(zeta), knew);
     st(D, zn, i, j, z0.zn);
     if (south) st(D, zn, i, j - 1, z0.zn);           // zetabc_tile closed: zero gradient (zetabc.F:353-358,437-442)
@@ -194,9 +197,8 @@ __global__ void __launch_bounds__(S2_TX * S2_TY) step2d_kernel(const Dev D, Box 
         v2(D, FID(pmon_p)), v2(D, FID(pnom_p)), v2(D, FID(om_r)), v2(D, FID(on_r)), v2(D, FID(om_p)), v2(D, FID(on_p))};
   const bool curv = (D.p.app == ROMS_B200_APP_BENCHMARK);
   const double cg = 0.5 * D.p.g, c3 = 1.0 / 3.0;
-  for (int comp = 0; comp < 2; ++comp) {
-    if (comp == 0 && !doU) continue;
-    if (comp == 1 && !doV) continue;
+  const int comp = mycomp;
+  if (comp == 0 ? doU : doV) {
     const int di = comp == 0 ? 1 : 0, dj = 1 - di;
     const Zst zm = zstate(s, i - di, j - dj);
     const double hm = s.h(i - di, j - dj), h0 = s.h(i, j);
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(S2_TX * S2_TY) step2d_kernel(const Dev D, Box 
       if (north) st(D, qn, i, j + 1, D.p.gamma2 * val);
     }
   }
-  {                                                   // v2dbc_im.F:253-258,395-400 (no normal flow)
+  if (mycomp == 1) {                                  // v2dbc_im.F:253-258,395-400 (no normal flow)
     V2 vn = v2l(D, FID(vbar), knew);
     if (south) st(D, vn, i, b.Jstr, 0.0);
     if (north) st(D, vn, i, b.Jend + 1, 0.0);
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(S2_TX * S2_TY) step2d_kernel(const Dev D, Box 
 int k_step2d(roms_b200_ctx* c, int krhs, int kstp, int knew, int nstp, int nnew, int iif, int pred, int iic, int ntfirst) {
   const roms_b200_bounds& b = c->D.b;
   Step2dArgs a{krhs, kstp, knew, nstp, nnew, iif, pred, (iic == ntfirst) ? 0 : (iic == ntfirst + 1 ? 1 : 2)};
-  Box bx{b.IstrR, b.IendR, b.JstrR, b.JendR}; dim3 blk(S2_TX, S2_TY);
+  Box bx{b.IstrR, b.IendR, b.JstrR, b.JendR}; dim3 blk(S2_TX, S2_TY, 2);
   step2d_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx, a); c->launches++;
   return 0;
 }
