@@ -276,10 +276,10 @@ __global__ void __launch_bounds__(128) step3d_uv1_kernel(const Dev D, Box bx, in
   V3 Hz = v3(D, FID(Hz)), Akv = v3(D, FID(Akv)); V2 pm = v2(D, FID(pm)), pn = v2(D, FID(pn));
   const bool S = b.Southern_Edge && !b.NSperiodic, Nn = b.Northern_Edge && !b.NSperiodic;
   double q[RB_MAXN + 2], Hzk[RB_MAXN + 2], oHz[RB_MAXN + 2], CF[RB_MAXN + 1], DC[RB_MAXN + 1];
-  for (int comp = 0; comp < 2; ++comp) {
+  const int comp = blockIdx.z;              // u and v columns on separate threads
+  if ((comp == 0 && (i >= b.IstrU && i <= b.Iend && j >= b.Jstr && j <= b.Jend)) ||
+      (comp == 1 && (i >= b.Istr && i <= b.Iend && j >= b.JstrV && j <= b.Jend))) {
     const int di = comp == 0 ? 1 : 0, dj = 1 - di;
-    if (comp == 0 && !(i >= b.IstrU && i <= b.Iend && j >= b.Jstr && j <= b.Jend)) continue;
-    if (comp == 1 && !(i >= b.Istr && i <= b.Iend && j >= b.JstrV && j <= b.Jend)) continue;
     V3 qn = v3l(D, comp == 0 ? FID(u) : FID(v), nnew), r = v3l(D, comp == 0 ? FID(ru) : FID(rv), nrhs);
     const double DC0 = cffab * (pm(i, j) + pm(i - di, j - dj)) * (pn(i, j) + pn(i - di, j - dj));
     for (int k = 1; k <= N; ++k) {
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(128) step3d_uv1_kernel(const Dev D, Box bx, in
     }
   }
   // v3dbc_im.F:171-178,250-257: zero normal flow at the closed walls
-  if (i >= b.Istr && i <= b.Iend) {
+  if (comp == 1 && i >= b.Istr && i <= b.Iend) {
     V3 vn = v3l(D, FID(v), nnew);
     if (S && j == b.Jstr) for (int k = 1; k <= N; ++k) vn(i, b.Jstr, k) = 0.0;
     if (Nn && j == b.Jend) for (int k = 1; k <= N; ++k) vn(i, b.Jend + 1, k) = 0.0;
@@ -340,10 +340,10 @@ __global__ void __launch_bounds__(128) step3d_uv2_kernel(const Dev D, Box bx, in
   const roms_b200_bounds& b = D.b; const int N = b.N;
   V3 Hz = v3(D, FID(Hz));
   double DC[RB_MAXN + 1], qk[RB_MAXN + 1], hq[RB_MAXN + 1];
-  for (int comp = 0; comp < 2; ++comp) {
+  const int comp = blockIdx.z;
+  if ((comp == 0 && (i >= b.IstrP && i <= b.IendT && j >= b.JstrT && j <= b.JendT)) ||
+      (comp == 1 && (i >= b.IstrT && i <= b.IendT && j >= b.Jstr && j <= b.JendT))) {
     const int di = comp == 0 ? 1 : 0, dj = 1 - di;
-    if (comp == 0 && !(i >= b.IstrP && i <= b.IendT && j >= b.JstrT && j <= b.JendT)) continue;
-    if (comp == 1 && !(i >= b.IstrT && i <= b.IendT && j >= b.Jstr && j <= b.JendT)) continue;
     V3 qn = v3l(D, comp == 0 ? FID(u) : FID(v), nnew), Hq = v3(D, comp == 0 ? FID(Huon) : FID(Hvom));
     const double met = v2(D, comp == 0 ? FID(on_u) : FID(om_v))(i, j);
     const double Davg1 = v2(D, comp == 0 ? FID(DU_avg1) : FID(DV_avg1))(i, j), Davg2 = v2(D, comp == 0 ? FID(DU_avg2) : FID(DV_avg2))(i, j);
@@ -384,8 +384,10 @@ int k_step3d_uv(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntf
   double cffab;
   if (iic == ntfirst) cffab = 0.25 * dt; else if (iic == ntfirst + 1) cffab = 0.25 * dt * 3.0 / 2.0; else cffab = 0.25 * dt * 23.0 / 12.0;
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 4);
-  step3d_uv1_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx, nrhs, nnew, cffab); c->launches++;
+  dim3 g1 = grid2(bx, blk); g1.z = 2;
+  step3d_uv1_kernel<<<g1, blk, 0, c->stream>>>(c->D, bx, nrhs, nnew, cffab); c->launches++;
   Box b2{b.IstrT, b.IendT, b.JstrT, b.JendT};
-  step3d_uv2_kernel<<<grid2(b2, blk), blk, 0, c->stream>>>(c->D, b2, nnew); c->launches++;
+  dim3 g2 = grid2(b2, blk); g2.z = 2;
+  step3d_uv2_kernel<<<g2, blk, 0, c->stream>>>(c->D, b2, nnew); c->launches++;
   return 0;
 }
