@@ -19,6 +19,7 @@
  */
 #ifndef ROMS_B200_H
 #define ROMS_B200_H
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -141,6 +142,16 @@ int roms_b200_step3d_uv(roms_b200_ctx* ctx, int nrhs, int nstp, int nnew, int ii
 int roms_b200_step3d_t(roms_b200_ctx* ctx, int nrhs, int nstp, int nnew);      /* step3d_t.F:120      */
 /* diag_tile reductions: out[0]=avgke, out[1]=avgpe, out[2]=volume (diag.F:225-322) */
 int roms_b200_diag(roms_b200_ctx* ctx, int nstp, double* out3);
+
+/* diag in two halves (launch + asynchronous D2H of the partial sums ; wait + final sums + mp_reduce) so that the host can
+ * evaluate the next step's set_data while the device works: diag.F:225-322,405 */
+int roms_b200_diag_begin(roms_b200_ctx* ctx, int nstp);
+int roms_b200_diag_end(roms_b200_ctx* ctx, double* out3);
+/* pinned host staging buffers and an upload that does not block the host (the buffer must stay untouched until the next
+ * roms_b200_sync / roms_b200_diag_end): the sync points of `set_data` (Nonlinear/set_data.F) */
+int roms_b200_host_alloc(size_t bytes, void** p);
+int roms_b200_host_free(void* p);
+int roms_b200_upload_async(roms_b200_ctx* ctx, int field, const double* pinned_host);
 
 /* ---- whole fast loop and whole baroclinic step on the device mirror.
  * roms_b200_step2d_loop runs main3d.F:810-918 (2*nfast+1 step2d calls) and

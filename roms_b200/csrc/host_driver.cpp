@@ -39,6 +39,7 @@ struct roms_b200_driver {
   std::vector<double> sc_r, Cs_r, sc_w, Cs_w, w1, w2;
   int nfast;
   double last_diag[3];
+  double* pin[2][2];        // pinned staging of the time-dependent forcing: [slot][field], double-buffered across steps
 };
 
 extern "C" {
@@ -242,7 +243,9 @@ int host_grid(roms_b200_driver* d) {
 
 // set_data.F analytical branches that change in time, evaluated on the host (2-D) exactly as the
 // Fortran host does, then uploaded: ana_srflux (BENCHMARK), ana_smflux (UPWELLING).
-int host_set_data(roms_b200_driver* d, double tdays) {
+// slot < 0: blocking upload from pageable memory; slot 0/1: evaluate into the pinned buffer of that slot only (the caller
+// enqueues the asynchronous upload with push_forcing when the previous step has been launched)
+int host_set_data(roms_b200_driver* d, double tdays, int slot = -1) {
   const roms_b200_bounds& b = d->b; const roms_b200_config& c = d->cfg;
   const bool dist = (b.NtileI * b.NtileJ > 1);
   const int j0 = std::max(b.LBj, 0), j1 = std::min(b.UBj, b.Mm + 1);
@@ -268,12 +271,23 @@ int host_set_data(roms_b200_driver* d, double tdays) {
       }
       d->srflx(i, j) = (1.0 - 0.06) * sr;
     }
+    if (slot >= 0) { std::memcpy(d->pin[slot][0], d->srflx.d.data(), d->srflx.d.size() * sizeof(double)); return 0; }
     return up(d, "srflx", d->srflx);
   }
   double windamp;
   if ((tdays - 0.0) <= 2.0) windamp = -0.1 * std::sin(pi * (tdays - 0.0) / 4.0) / c.rho0; else windamp = -0.1 / c.rho0;
   for (int j = j0; j <= j1; ++j) for (int i = i0; i <= i1; ++i) { d->sustr(i, j) = windamp; d->svstr(i, j) = 0.0; }
+  if (slot >= 0) {
+    std::memcpy(d->pin[slot][0], d->sustr.d.data(), d->sustr.d.size() * sizeof(double));
+    std::memcpy(d->pin[slot][1], d->svstr.d.data(), d->svstr.d.size() * sizeof(double));
+    return 0;
+  }
   return up(d, "sustr", d->sustr) | up(d, "svstr", d->svstr);
+}
+int push_forcing(roms_b200_driver* d, int slot) {
+  if (d->cfg.app == ROMS_B200_APP_BENCHMARK) return roms_b200_upload_async(d->ctx, roms_b200_field_id("srflx"), d->pin[slot][0]);
+  return roms_b200_upload_async(d->ctx, roms_b200_field_id("sustr"), d->pin[slot][0]) |
+         roms_b200_upload_async(d->ctx, roms_b200_field_id("svstr"), d->pin[slot][1]);
 }
 }  // namespace
 
@@ -327,13 +341,23 @@ int roms_b200_ROMS_run(roms_b200_driver* d, int nsteps, int host_forcing, double
   int rc = 0;
   if (!host_forcing) rc = roms_b200_main3d(d->ctx, nsteps, 1, 0);
   else {
+    // Software pipeline over steps: the host evaluates set_data of step s+1 into the other pinned slot while the device
+    // runs step s; uploads and the diag read-back are asynchronous copies on the launch stream (same data, same order).
+    if (!d->pin[0][0]) {
+      const size_t bytes = d->srflx.d.size() * sizeof(double);
+      for (int a = 0; a < 2; ++a) for (int f = 0; f < 2; ++f) rc |= roms_b200_host_alloc(bytes, (void**)&d->pin[a][f]);
+    }
+    int st[6], slot = 0; double time;
+    roms_b200_get_stepping(d->ctx, st, &time);
+    rc |= host_set_data(d, time / 86400.0, slot);
     for (int s = 0; s < nsteps && !rc; ++s) {
-      int st[6]; double time;
-      roms_b200_get_stepping(d->ctx, st, &time);
-      rc |= host_set_data(d, time / 86400.0);
+      rc |= push_forcing(d, slot);
       rc |= roms_b200_main3d(d->ctx, 1, 0, 0);
       roms_b200_get_stepping(d->ctx, st, &time);
-      rc |= roms_b200_diag(d->ctx, st[3] /* the level just completed is nnew of that step */, d->last_diag);
+      rc |= roms_b200_diag_begin(d->ctx, st[3] /* the level just completed is nnew of that step */);
+      if (s + 1 < nsteps) rc |= host_set_data(d, time / 86400.0, slot ^ 1);
+      rc |= roms_b200_diag_end(d->ctx, d->last_diag);
+      slot ^= 1;
     }
     if (diag3) std::memcpy(diag3, d->last_diag, sizeof(d->last_diag));
   }
@@ -347,6 +371,7 @@ int roms_b200_driver_nfast(roms_b200_driver* d) { return d->nfast; }
 // Drivers/nl_roms.h:320-430 (ROMS_finalize)
 int roms_b200_ROMS_finalize(roms_b200_driver* d) {
   if (!d) return 0;
+  for (int a = 0; a < 2; ++a) for (int f = 0; f < 2; ++f) roms_b200_host_free(d->pin[a][f]);
   roms_b200_destroy(d->ctx);
   delete d;
   return 0;

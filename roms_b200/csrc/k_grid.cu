@@ -337,10 +337,20 @@ __global__ void diag_kernel(const Dev D, int nstp, double* __restrict__ partial)
   }
   if (threadIdx.x == 0) for (int q = 0; q < 3; ++q) partial[3 * blockIdx.x + q] = s[q][0];
 }
-int k_diag(roms_b200_ctx* c, int nstp, double* out3) {
+// diag in two halves so that a host driver can overlap its own work with the step: begin = reduction kernel + asynchronous
+// D2H of the per-row partial sums into pinned memory; end = wait, final sums in a fixed order, mp_reduce across tiles.
+int k_diag_begin(roms_b200_ctx* c, int nstp) {
   const roms_b200_bounds& b = c->D.b; const int nb = b.Jend - b.Jstr + 1;
   diag_kernel<<<nb, 256, 0, c->stream>>>(c->D, nstp, c->D.red); c->launches++;
   CUDA_OK(cudaMemcpyAsync(c->h_red, c->D.red, sizeof(double) * 3 * nb, cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+int k_diag(roms_b200_ctx* c, int nstp, double* out3) {
+  if (k_diag_begin(c, nstp)) return 1;
+  return k_diag_end(c, out3);
+}
+int k_diag_end(roms_b200_ctx* c, double* out3) {
+  const roms_b200_bounds& b = c->D.b; const int nb = b.Jend - b.Jstr + 1;
   CUDA_OK(cudaStreamSynchronize(c->stream));
   double ke = 0, pe = 0, vol = 0;
   for (int q = 0; q < nb; ++q) { ke += c->h_red[3 * q]; pe += c->h_red[3 * q + 1]; vol += c->h_red[3 * q + 2]; }

@@ -194,6 +194,16 @@ int roms_b200_step2d(roms_b200_ctx* c, int krhs, int kstp, int knew, int nstp, i
 int roms_b200_step3d_uv(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntfirst) { ENTER(c); k_step3d_uv(c, nrhs, nstp, nnew, iic, ntfirst); LEAVE(); }
 int roms_b200_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew) { ENTER(c); k_step3d_t(c, nrhs, nstp, nnew); LEAVE(); }
 int roms_b200_diag(roms_b200_ctx* c, int nstp, double* out3) { ENTER(c); if (k_diag(c, nstp, out3)) return 1; LEAVE(); }
+int roms_b200_diag_begin(roms_b200_ctx* c, int nstp) { ENTER(c); if (k_diag_begin(c, nstp)) return 1; LEAVE(); }
+int roms_b200_diag_end(roms_b200_ctx* c, double* out3) { ENTER(c); if (k_diag_end(c, out3)) return 1; LEAVE(); }
+int roms_b200_host_alloc(size_t bytes, void** p) { CUDA_OK(cudaMallocHost(p, bytes)); return 0; }
+int roms_b200_host_free(void* p) { if (p) cudaFreeHost(p); return 0; }
+int roms_b200_upload_async(roms_b200_ctx* c, int f, const double* pinned_host) {
+  ENTER(c);
+  if (f < 0 || f >= ROMS_B200_NFIELDS) return 1;
+  CUDA_OK(cudaMemcpyAsync(c->D.f[f], pinned_host, c->fsize[f] * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  LEAVE();
+}
 int roms_b200_set_data(roms_b200_ctx* c, double tdays) { ENTER(c); k_set_data(c, tdays); LEAVE(); }
 int roms_b200_ana_initial(roms_b200_ctx* c) { ENTER(c); k_ana_initial(c); LEAVE(); }
 int roms_b200_ini_fields(roms_b200_ctx* c, int nstp, int kstp) { ENTER(c); k_ini_fields(c, nstp, kstp); LEAVE(); }
