@@ -177,6 +177,11 @@ int roms_b200_time_step3d_t(roms_b200_ctx* ctx, int nrhs, int nstp, int nnew, in
 int roms_b200_comm_unique_id(char* id128);
 int roms_b200_comm_init(roms_b200_ctx* ctx, int rank, int nranks, const char* id128);
 int roms_b200_comm_destroy(roms_b200_ctx* ctx);
+/* NVLink peer mailboxes (default halo transport once connected; NCCL remains for the diag all-reduce and as
+ * ROMS_B200_HALO_NCCL=1 fallback).  Every rank exports a 64-byte CUDA IPC handle; the host all-gathers them
+ * (MPI_Allgather / torch.distributed) and passes the table (nranks x 64 bytes, indexed by rank = tile id). */
+int roms_b200_p2p_handle(roms_b200_ctx* ctx, char* handle64);
+int roms_b200_p2p_connect(roms_b200_ctx* ctx, const char* handles, int nranks);
 /* copy the interior (Istr:Iend,Jstr:Jend) of `nplanes` consecutive (i,j) planes of a field, starting at
  * storage plane `plane0`, into a dense host buffer (nplanes, Jend-Jstr+1, Iend-Istr+1) */
 int roms_b200_download_interior(roms_b200_ctx* ctx, int field, int plane0, int nplanes, double* host);

@@ -11,6 +11,14 @@
 // context's stream (pack kernel -> ncclGroup{Send,Recv} -> unpack kernel), so it
 // is captured in the fast-loop CUDA graph together with the step2d launches.
 // NCCL is dlopen'ed: single-GPU use never needs it.
+//
+// Second transport (default when the host connected the peers, roms_b200_p2p_*): NVLink peer MAILBOXES.  Every rank
+// exports one device allocation through CUDA IPC; a neighbour maps it and one exchange kernel per phase stores the
+// boundary strips straight into the receivers' mailboxes over NVLink (no staging, no NCCL proxy/launch), raises the
+// "strip complete" flags there, spins on its own flags and unpacks.  One kernel per phase instead of pack + ncclGroup +
+// unpack: the latency-bound 2-D swaps of the barotropic loop cost about one kernel launch plus one NVLink round trip.  Sequence numbers live on the device, so the
+// exchange is replayable inside the fast-loop CUDA graph; mailboxes are double-buffered by sequence parity (a sender can
+// only be two exchanges ahead after it has seen the receiver's flag of the previous one).
 #include "common.cuh"
 #include <dlfcn.h>
 #include <cstring>
@@ -91,9 +99,137 @@ __global__ void halo_unpack_kernel(const Dev D, HaloList L, int phase, int w, co
     }
   }
 }
+
+// ---- NVLink peer mailboxes ----------------------------------------------------------------------------------
+// exported allocation: [16 flags (dir*2+slot) as u64, padded to 256 B][16 data regions (dir*2+slot) of `cap` doubles]
+// dir = the side the strip ARRIVES from: 0 W, 1 E, 2 S, 3 N, 4 SW, 5 SE, 6 NW, 7 NE.
+// Unlike the two-phase scheme of mp_exchange (W/E, then S/N over the full i-range so that corners propagate), all eight
+// neighbours are served in ONE exchange: the corner blocks travel as their own (w x w) messages.  W/E strips span the rows
+// [Jstr..Jend], extended to the array edge where the tile has no S/N neighbour (physical boundary rows); S/N strips
+// likewise in i -- so after the exchange the halo frame holds exactly what the two phases would have produced.
+constexpr size_t P2P_HDR = 256;
+constexpr int P2P_NDIR = 8;
+__host__ __device__ inline int p2p_opp(int d) { return d < 4 ? (d ^ 1) : (11 - d); }     // W<->E, S<->N, SW<->NE, SE<->NW
+struct P2PView { unsigned long long* flags; double* data; size_t cap; };
+__host__ __device__ inline P2PView p2p_view(void* mem, size_t cap) {
+  return P2PView{(unsigned long long*)mem, (double*)((char*)mem + P2P_HDR), cap};
+}
+struct Rect { int o, w, h; };              // element offset of the first point in an (i,j) plane, width (i), height (j)
+struct P2PArgs {
+  void* mine; void* peer[P2P_NDIR];        // my mailbox ; the mailboxes of the 8 neighbours (null: none)
+  Rect snd[P2P_NDIR], rcv[P2P_NDIR];       // what I send towards direction d / where the strip arriving from direction d goes
+  size_t cap; unsigned long long* seq; unsigned int* ticket;
+};
+// ONE kernel per exchange: (1) store my boundary strips and corner blocks into the neighbours' mailboxes over NVLink,
+// (2) the last block to finish packing raises the "complete" flags at the neighbours, (3) every block waits for the flag
+// of the direction it unpacks, (4) unpack into my halo, (5) the last block commits the sequence number.  All blocks are
+// co-resident (a few hundred blocks of 256 threads at most), so the spin in (3) cannot starve blocks still packing.
+// Work items = (plane, direction); the grid is at most 4 blocks per SM so that every block is resident.
+__global__ void __launch_bounds__(256) halo_xchg_p2p_kernel(const Dev D, HaloList L, const __grid_constant__ P2PArgs a) {
+  const int ni = D.ni;
+  const unsigned long long s = a.seq[0] + 1;          // this exchange's sequence number
+  const int slot = (int)(s & 1);
+  const P2PView me = p2p_view(a.mine, a.cap);
+  const int nitems = L.total_planes * P2P_NDIR;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int d = item % P2P_NDIR, plane = item / P2P_NDIR;
+    void* peer = a.peer[d];
+    if (!peer) continue;
+    int f = 0, p = plane;
+    while (p >= L.nplanes[f]) { p -= L.nplanes[f]; ++f; }
+    const double* fld = L.base[f] + (size_t)p * D.nij;
+    const Rect r = a.snd[d];
+    const int n = r.w * r.h;
+    double* out = p2p_view(peer, a.cap).data + (size_t)(p2p_opp(d) * 2 + slot) * a.cap + (size_t)plane * n;
+    for (int x = threadIdx.x; x < n; x += blockDim.x) out[x] = fld[r.o + (x % r.w) + (size_t)ni * (x / r.w)];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) {                            // all blocks have packed and fenced
+      a.ticket[0] = 0;
+#pragma unroll
+      for (int q = 0; q < P2P_NDIR; ++q)
+        if (a.peer[q]) { volatile unsigned long long* fl = p2p_view(a.peer[q], a.cap).flags + (p2p_opp(q) * 2 + slot); *fl = s; }
+      __threadfence_system();
+    }
+  }
+  if (threadIdx.x < P2P_NDIR && a.peer[threadIdx.x]) {
+    volatile unsigned long long* fl = me.flags + (threadIdx.x * 2 + slot);
+    while (*fl < s) { }
+    __threadfence_system();
+  }
+  __syncthreads();
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int d = item % P2P_NDIR, plane = item / P2P_NDIR;
+    if (!a.peer[d]) continue;
+    int f = 0, p = plane;
+    while (p >= L.nplanes[f]) { p -= L.nplanes[f]; ++f; }
+    double* fld = L.base[f] + (size_t)p * D.nij;
+    const Rect r = a.rcv[d];
+    const int n = r.w * r.h;
+    const double* in = me.data + (size_t)(d * 2 + slot) * a.cap + (size_t)plane * n;
+    for (int x = threadIdx.x; x < n; x += blockDim.x) fld[r.o + (x % r.w) + (size_t)ni * (x / r.w)] = __ldcv(in + x);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(a.ticket + 1, 1u) == gridDim.x - 1) { a.ticket[1] = 0; __threadfence(); a.seq[0] = s; }
+  }
+}
 }  // namespace
 
 extern "C" {
+
+// ---- NVLink peer mailboxes: set-up.  Every rank calls p2p_handle, the host all-gathers the 64-byte handles
+// (MPI_Allgather / torch.distributed.all_gather), every rank calls p2p_connect with the table (nranks x 64 bytes).
+int roms_b200_p2p_handle(roms_b200_ctx* c, char* handle64) {
+  if (!c) return 1;
+  CUDA_OK(cudaSetDevice(c->device));
+  const size_t strip = (size_t)c->D.halo * (size_t)((c->D.ni > c->D.nj) ? c->D.ni : c->D.nj);
+  c->halo_cap = strip * HALO_MAXPLANES;
+  const size_t bytes = P2P_HDR + 2 * P2P_NDIR * c->halo_cap * sizeof(double);
+  if (!c->p2p_mem) {
+    CUDA_OK(cudaMalloc(&c->p2p_mem, bytes));
+    CUDA_OK(cudaMemset(c->p2p_mem, 0, bytes));
+    CUDA_OK(cudaMalloc((void**)&c->p2p_seq, 2 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMemset(c->p2p_seq, 0, 2 * sizeof(unsigned long long)));
+    CUDA_OK(cudaMalloc((void**)&c->p2p_ticket, 2 * sizeof(unsigned int)));
+    CUDA_OK(cudaMemset(c->p2p_ticket, 0, 2 * sizeof(unsigned int)));
+  }
+  cudaIpcMemHandle_t h;
+  CUDA_OK(cudaIpcGetMemHandle(&h, c->p2p_mem));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+int roms_b200_p2p_connect(roms_b200_ctx* c, const char* handles, int nranks) {
+  if (!c || !c->p2p_mem) return 1;
+  CUDA_OK(cudaSetDevice(c->device));
+  const roms_b200_bounds& b = c->D.b;
+  if (nranks != b.NtileI * b.NtileJ) return 1;
+  int nb[4]; roms_b200_tile_neighbors(&b, nb);
+  const int me = b.Jtile * b.NtileI + b.Itile, NI = b.NtileI;
+  // diagonal neighbours: the W/E neighbour of my S/N neighbour (tile_neighbors, mp_exchange.F:118-197, applied twice)
+  auto col = [&](int r) { return r % NI; };
+  auto row = [&](int r) { return r / NI; };
+  int r8[P2P_NDIR] = {nb[0], nb[1], nb[2], nb[3], -1, -1, -1, -1};
+  if (nb[2] >= 0 && nb[0] >= 0) r8[4] = row(nb[2]) * NI + col(nb[0]);
+  if (nb[2] >= 0 && nb[1] >= 0) r8[5] = row(nb[2]) * NI + col(nb[1]);
+  if (nb[3] >= 0 && nb[0] >= 0) r8[6] = row(nb[3]) * NI + col(nb[0]);
+  if (nb[3] >= 0 && nb[1] >= 0) r8[7] = row(nb[3]) * NI + col(nb[1]);
+  for (int q = 0; q < P2P_NDIR; ++q) {
+    c->p2p_peer[q] = nullptr; c->p2p_rank[q] = r8[q];
+    if (r8[q] < 0 || r8[q] == me) { c->p2p_rank[q] = -1; continue; }
+    for (int r = 0; r < q; ++r) if (r8[r] == r8[q] && c->p2p_peer[r]) c->p2p_peer[q] = c->p2p_peer[r];   // same peer on several sides: map once
+    if (c->p2p_peer[q]) continue;
+    cudaIpcMemHandle_t h; memcpy(&h, handles + (size_t)64 * r8[q], 64);
+    CUDA_OK(cudaIpcOpenMemHandle(&c->p2p_peer[q], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  c->rank = me; c->nranks = nranks; c->nbW = nb[0]; c->nbE = nb[1]; c->nbS = nb[2]; c->nbN = nb[3];
+  c->p2p_on = (getenv("ROMS_B200_HALO_NCCL") == nullptr);
+  return 0;
+}
 
 int roms_b200_comm_unique_id(char* id128) {
   if (load_nccl()) return 1;
@@ -121,6 +257,16 @@ int roms_b200_comm_init(roms_b200_ctx* c, int rank, int nranks, const char* id12
   return 0;
 }
 int roms_b200_comm_destroy(roms_b200_ctx* c) {
+  if (c && c->p2p_mem) {
+    cudaDeviceSynchronize();
+    for (int q = 0; q < P2P_NDIR; ++q) {
+      bool dup = false;
+      for (int r = 0; r < q; ++r) if (c->p2p_peer[r] == c->p2p_peer[q]) dup = true;
+      if (c->p2p_peer[q] && !dup) cudaIpcCloseMemHandle(c->p2p_peer[q]);
+    }
+    for (int q = 0; q < P2P_NDIR; ++q) c->p2p_peer[q] = nullptr;
+    cudaFree(c->p2p_mem); cudaFree(c->p2p_seq); cudaFree(c->p2p_ticket); c->p2p_mem = nullptr; c->p2p_on = 0;
+  }
   if (c && c->comm) { g_nccl.CommDestroy((ncclComm_p)c->comm); c->comm = nullptr; for (int q = 0; q < 4; ++q) cudaFree(c->hbuf[q]); }
   return 0;
 }
@@ -136,12 +282,39 @@ int halo_exchange(roms_b200_ctx* c, double* const* bases, const int* nplanes, in
   for (int f = nf; f < HALO_MAXF; ++f) { L.base[f] = nullptr; L.nplanes[f] = 1 << 30; }
   if (L.total_planes > HALO_MAXPLANES) return 1;
   const int w = c->D.halo;
+  if (c->p2p_on) {
+    const roms_b200_bounds& b = c->D.b; const int ni = c->D.ni;
+    const bool hW = c->p2p_rank[0] >= 0, hE = c->p2p_rank[1] >= 0, hS = c->p2p_rank[2] >= 0, hN = c->p2p_rank[3] >= 0;
+    if (!(hW || hE || hS || hN)) return 0;
+    // i-range of the S/N strips and j-range of the W/E strips: the interior, extended to the array edge where there is no
+    // neighbour on that side (physical boundary rows / locally maintained periodic images)
+    const int ia = hW ? b.Istr : b.LBi, ib = hE ? b.Iend : b.UBi, ja = hS ? b.Jstr : b.LBj, jb = hN ? b.Jend : b.UBj;
+    auto rect = [&](int i0, int i1, int j0, int j1) { return Rect{(i0 - b.LBi) + ni * (j0 - b.LBj), i1 - i0 + 1, j1 - j0 + 1}; };
+    P2PArgs a{};
+    a.mine = c->p2p_mem; a.cap = c->halo_cap; a.seq = c->p2p_seq; a.ticket = c->p2p_ticket;
+    for (int q = 0; q < P2P_NDIR; ++q) a.peer[q] = (c->p2p_rank[q] >= 0) ? c->p2p_peer[q] : nullptr;
+    const int iW0 = b.Istr, iW1 = b.Istr + w - 1, iE0 = b.Iend - w + 1, iE1 = b.Iend, jS0 = b.Jstr, jS1 = b.Jstr + w - 1, jN0 = b.Jend - w + 1, jN1 = b.Jend;
+    a.snd[0] = rect(iW0, iW1, ja, jb);            a.rcv[0] = rect(b.Istr - w, b.Istr - 1, ja, jb);
+    a.snd[1] = rect(iE0, iE1, ja, jb);            a.rcv[1] = rect(b.Iend + 1, b.Iend + w, ja, jb);
+    a.snd[2] = rect(ia, ib, jS0, jS1);            a.rcv[2] = rect(ia, ib, b.Jstr - w, b.Jstr - 1);
+    a.snd[3] = rect(ia, ib, jN0, jN1);            a.rcv[3] = rect(ia, ib, b.Jend + 1, b.Jend + w);
+    a.snd[4] = rect(iW0, iW1, jS0, jS1);          a.rcv[4] = rect(b.Istr - w, b.Istr - 1, b.Jstr - w, b.Jstr - 1);
+    a.snd[5] = rect(iE0, iE1, jS0, jS1);          a.rcv[5] = rect(b.Iend + 1, b.Iend + w, b.Jstr - w, b.Jstr - 1);
+    a.snd[6] = rect(iW0, iW1, jN0, jN1);          a.rcv[6] = rect(b.Istr - w, b.Istr - 1, b.Jend + 1, b.Jend + w);
+    a.snd[7] = rect(iE0, iE1, jN0, jN1);          a.rcv[7] = rect(b.Iend + 1, b.Iend + w, b.Jend + 1, b.Jend + w);
+    static int nsm = 0;
+    if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
+    int nblk = L.total_planes * P2P_NDIR; if (nblk > 4 * nsm) nblk = 4 * nsm;     // all blocks resident (256 threads each)
+    halo_xchg_p2p_kernel<<<nblk, 256, 0, c->stream>>>(c->D, L, a); c->launches++;
+    return 0;
+  }
   ncclComm_p comm = (ncclComm_p)c->comm;
   for (int phase = 0; phase < 2; ++phase) {
     const int lo = phase == 0 ? c->nbW : c->nbS, hi = phase == 0 ? c->nbE : c->nbN;
     if (lo < 0 && hi < 0) continue;
     const size_t n = (size_t)w * (phase == 0 ? c->D.nj : c->D.ni), cnt = n * L.total_planes;
     dim3 g((unsigned)((n + 255) / 256), (unsigned)L.total_planes);
+
     double *sLo = c->hbuf[0], *sHi = c->hbuf[1], *rLo = c->hbuf[2], *rHi = c->hbuf[3];
     halo_pack_kernel<<<g, 256, 0, c->stream>>>(c->D, L, phase, w, sLo, sHi); c->launches++;
     NCCL_OK(g_nccl.GroupStart());

@@ -289,6 +289,24 @@ def _driver_comm_init(self, rank, nranks, id128):
         raise RuntimeError("roms_b200_comm_init failed rc=%d" % rc)
 
 
+def _driver_p2p_handle(self):
+    L = self.L
+    buf = C.create_string_buffer(64)
+    L.roms_b200_p2p_handle.argtypes = [C.c_void_p, C.c_char_p]
+    rc = L.roms_b200_p2p_handle(self.ctx.h, buf)
+    if rc:
+        raise RuntimeError("roms_b200_p2p_handle failed rc=%d" % rc)
+    return buf.raw
+
+
+def _driver_p2p_connect(self, handles, nranks):
+    L = self.L
+    L.roms_b200_p2p_connect.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    rc = L.roms_b200_p2p_connect(self.ctx.h, handles, nranks)
+    if rc:
+        raise RuntimeError("roms_b200_p2p_connect failed rc=%d" % rc)
+
+
 def _driver_bounds(self):
     b = Bounds()
     self.L.roms_b200_driver_bounds.argtypes = [C.c_void_p, C.POINTER(Bounds)]
@@ -323,5 +341,7 @@ def _ctx_download_interior(self, name, l=1, m=1, nk=None):
 
 
 Driver.comm_init = _driver_comm_init
+Driver.p2p_handle = _driver_p2p_handle
+Driver.p2p_connect = _driver_p2p_connect
 Driver.bounds = _driver_bounds
 Context.download_interior = _ctx_download_interior

@@ -35,6 +35,12 @@ def main():
     cfg.NtileI, cfg.NtileJ = a.tiles
     d = rb.Driver(cfg, tile=rank, device=local)
     d.comm_init(rank, world, bytes(idt.cpu().numpy().tobytes()))
+    # NVLink peer mailboxes: all-gather the CUDA IPC handles (what MPI_Allgather does in a Fortran host)
+    hnd = torch.frombuffer(bytearray(d.p2p_handle()), dtype=torch.uint8).cuda()
+    allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    dist.all_gather(allh, hnd)
+    d.p2p_connect(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh), world)
+    dist.barrier()
     d.run(a.steps)
     d.ctx.sync()
     b = d.bounds()
