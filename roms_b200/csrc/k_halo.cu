@@ -304,7 +304,9 @@ int halo_exchange(roms_b200_ctx* c, double* const* bases, const int* nplanes, in
     a.snd[7] = rect(iE0, iE1, jN0, jN1);          a.rcv[7] = rect(b.Iend + 1, b.Iend + w, b.Jend + 1, b.Jend + w);
     static int nsm = 0;
     if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
-    int nblk = L.total_planes * P2P_NDIR; if (nblk > 4 * nsm) nblk = 4 * nsm;     // all blocks resident (256 threads each)
+    // one block per (plane, direction) item while they all fit on the GPU at once (a single block for the small 2-D swaps was
+    // measured much slower: the strip copies are latency-bound and want to run side by side)
+    int nblk = L.total_planes * P2P_NDIR; if (nblk > 4 * nsm) nblk = 4 * nsm;
     halo_xchg_p2p_kernel<<<nblk, 256, 0, c->stream>>>(c->D, L, a); c->launches++;
     return 0;
   }

@@ -9,6 +9,8 @@
 // baroclinic step are captured in a CUDA graph (roms_b200.cu).  All 2-D state of
 // a benchmark-size tile (~50 planes x 277 KB) stays resident in the 126 MB L2.
 #include "common.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 // Block tile: 32 x 4 points.  Drhs, DUon, DVom (step2d_LF_AM3.h:664-702) are evaluated ONCE per point of the tile plus the
 // halo the 4th-order fluxes reach (3 west/south, 2 east/north) into shared memory; everything downstream reads them there
@@ -115,8 +117,11 @@ struct Step2dArgs { int krhs, kstp, knew, nstp, nnew, iif, pred, stepmode; };  /
 
 // Threads (x,y) = point of the tile, z = momentum component: z=0 advances zeta, the fast-time averages and ubar,
 // z=1 advances vbar (both evaluate the free-surface state they need from the shared tiles).
-__global__ void __launch_bounds__(S2_TX * S2_TY * 2) step2d_kernel(const Dev D, Box bx, Step2dArgs a) {
+struct Boxes { Box b[4]; };               // blockIdx.z selects the box (the frame of a tile is up to four strips)
+__global__ void __launch_bounds__(S2_TX * S2_TY * 2) step2d_kernel(const Dev D, const Boxes bxs, Step2dArgs a) {
   __shared__ double tDr[S2_TW * S2_TH], tDU[S2_TW * S2_TH], tDV[S2_TW * S2_TH];
+  const Box bx = bxs.b[blockIdx.z];
+  if (bx.i0 + (int)blockIdx.x * S2_TX > bx.i1 || bx.j0 + (int)blockIdx.y * S2_TY > bx.j1) return;   // whole block outside this box
   const int i = bx.i0 + blockIdx.x * S2_TX + threadIdx.x, j = bx.j0 + blockIdx.y * S2_TY + threadIdx.y;
   const roms_b200_bounds& b = D.b;
   const int krhs = a.krhs, kstp = a.kstp, knew = a.knew, iif = a.iif, ptsk = 3 - kstp;
@@ -264,10 +269,46 @@ __global__ void __launch_bounds__(S2_TX * S2_TY * 2) step2d_kernel(const Dev D, 
   }
 }
 
+static inline void launch_boxes(roms_b200_ctx* c, cudaStream_t st, const Box* bx, int n, const Step2dArgs& a) {
+  Boxes B{}; int gx = 1, gy = 1;
+  for (int q = 0; q < n; ++q) {
+    B.b[q] = bx[q];
+    gx = std::max(gx, (bx[q].i1 - bx[q].i0 + S2_TX) / S2_TX); gy = std::max(gy, (bx[q].j1 - bx[q].j0 + S2_TY) / S2_TY);
+  }
+  step2d_kernel<<<dim3(gx, gy, n), dim3(S2_TX, S2_TY, 2), 0, st>>>(c->D, B, a); c->launches++;
+}
+// With neighbours, the sub-step is split so that the halo exchange of the frame overlaps the interior stencil: the frame
+// (the strips of width `halo` the neighbours need) runs on the launch stream and is followed by the exchange; the interior
+// runs on a second stream.  Every point is advanced by one thread from levels it only reads, so the split changes no bits.
 int k_step2d(roms_b200_ctx* c, int krhs, int kstp, int knew, int nstp, int nnew, int iif, int pred, int iic, int ntfirst) {
   const roms_b200_bounds& b = c->D.b;
   Step2dArgs a{krhs, kstp, knew, nstp, nnew, iif, pred, (iic == ntfirst) ? 0 : (iic == ntfirst + 1 ? 1 : 2)};
-  Box bx{b.IstrR, b.IendR, b.JstrR, b.JendR}; dim3 blk(S2_TX, S2_TY, 2);
-  step2d_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx, a); c->launches++;
+  const Box full{b.IstrR, b.IendR, b.JstrR, b.JendR};
+  static const bool overlap = (getenv("ROMS_B200_OVERLAP") != nullptr);   // measured slower (2-stream graph nodes cost more than the exchange they hide): opt-in
+  const bool hW = c->comm && c->nbW >= 0, hE = c->comm && c->nbE >= 0, hS = c->comm && c->nbS >= 0, hN = c->comm && c->nbN >= 0;
+  const int w = c->D.halo;
+  c->forked = 0;
+  if (!overlap || !(hW || hE || hS || hN) || (b.Iend - b.Istr + 1) <= 2 * w + 1 || (b.Jend - b.Jstr + 1) <= 2 * w + 1) {
+    launch_boxes(c, c->stream, &full, 1, a);
+    return 0;
+  }
+  const int xa = hW ? b.Istr + w - 1 : full.i0 - 1, xb = hE ? b.Iend - w + 1 : full.i1 + 1;
+  const int ya = hS ? b.Jstr + w - 1 : full.j0 - 1, yb = hN ? b.Jend - w + 1 : full.j1 + 1;
+  Box fr[4]; int nf = 0;
+  if (hW) fr[nf++] = Box{full.i0, xa, full.j0, full.j1};
+  if (hE) fr[nf++] = Box{xb, full.i1, full.j0, full.j1};
+  if (hS) fr[nf++] = Box{xa + 1, xb - 1, full.j0, ya};
+  if (hN) fr[nf++] = Box{xa + 1, xb - 1, yb, full.j1};
+  const Box inner{xa + 1, xb - 1, ya + 1, yb - 1};
+  CUDA_OK(cudaEventRecord(c->ev_fork, c->stream));            // everything before this sub-step is complete
+  CUDA_OK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+  launch_boxes(c, c->stream2, &inner, 1, a);
+  CUDA_OK(cudaEventRecord(c->ev_join, c->stream2));
+  launch_boxes(c, c->stream, fr, nf, a);
+  c->forked = 1;
+  return 0;
+}
+int k_step2d_join(roms_b200_ctx* c) {
+  if (c->forked) { CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev_join, 0)); c->forked = 0; }
   return 0;
 }

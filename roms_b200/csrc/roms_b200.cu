@@ -69,6 +69,9 @@ int roms_b200_create(const roms_b200_bounds* b, const roms_b200_params* p, int d
     }
   }
   CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   for (int f = 0; f < ROMS_B200_NFIELDS; ++f) {
     const int nk = resolve(kFields[f].nk, *b), nl = resolve(kFields[f].nl, *b), nm = resolve(kFields[f].nm, *b);
     D.kLB[f] = kFields[f].kLB; D.nk[f] = nk; D.nl[f] = nl;
@@ -104,7 +107,7 @@ int roms_b200_destroy(roms_b200_ctx* c) {
   cudaFreeHost(c->h_red);
   roms_b200_comm_destroy(c);
   k_step3d_t_v5_forget(c);
-  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->stream); cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
   delete c;
   return 0;
 }
@@ -189,7 +192,7 @@ int roms_b200_rhs3d(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int
   LEAVE();
 }
 int roms_b200_step2d(roms_b200_ctx* c, int krhs, int kstp, int knew, int nstp, int nnew, int iif, int pred, int iic, int ntfirst) {
-  ENTER(c); k_step2d(c, krhs, kstp, knew, nstp, nnew, iif, pred, iic, ntfirst); LEAVE();
+  ENTER(c); k_step2d(c, krhs, kstp, knew, nstp, nnew, iif, pred, iic, ntfirst); if (k_step2d_join(c)) return 1; LEAVE();
 }
 int roms_b200_step3d_uv(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntfirst) { ENTER(c); k_step3d_uv(c, nrhs, nstp, nnew, iic, ntfirst); LEAVE(); }
 int roms_b200_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew) { ENTER(c); k_step3d_t(c, nrhs, nstp, nnew); LEAVE(); }
@@ -247,6 +250,7 @@ static int fast_loop_launch(roms_b200_ctx* c, int nstp, int nnew, int iic, int n
       if (c->comm) {      // mp_exchange2d calls of step2d_LF_AM3.h:842,1013,1068,3043 aggregated into one message
         if (iif == nfast + 1) { const XF x[3] = {xf2(FID(Zt_avg1)), xf2(FID(DU_avg1)), xf2(FID(DV_avg1))}; if (xchg(c, x, 3)) return 1; }
         else { const XF x[4] = {xf2(FID(zeta), knew), xf2(FID(ubar), knew), xf2(FID(vbar), knew), xf2(FID(rzeta), krhs)}; if (xchg(c, x, 4)) return 1; }
+        if (k_step2d_join(c)) return 1;
       }
     }
     if (PRED) {
@@ -255,7 +259,7 @@ static int fast_loop_launch(roms_b200_ctx* c, int nstp, int nnew, int iic, int n
     }
     if (iif < nfast + 1) {
       k_step2d(c, krhs, kstp, knew, nstp, nnew, iif, 0, iic, ntfirst);
-      if (c->comm) { const XF x[3] = {xf2(FID(zeta), knew), xf2(FID(ubar), knew), xf2(FID(vbar), knew)}; if (xchg(c, x, 3)) return 1; }
+      if (c->comm) { const XF x[3] = {xf2(FID(zeta), knew), xf2(FID(ubar), knew), xf2(FID(vbar), knew)}; if (xchg(c, x, 3)) return 1; if (k_step2d_join(c)) return 1; }
     }
   }
   *indx1_io = indx1;
