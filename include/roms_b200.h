@@ -102,6 +102,11 @@ int roms_b200_tile_bounds(int Lm, int Mm, int N, int NT, int NAT, int NtileI, in
 /* W,E,S,N neighbour ranks of a tile (Utility/mp_exchange.F:73-197 tile_neighbors); -1 = none */
 int roms_b200_tile_neighbors(const roms_b200_bounds* b, int* wesn);
 
+/* Eight-neighbour single-phase halo plan of the NVLink mailbox transport: dir 0 W,1 E,2 S,3 N,4 SW,5 SE,6 NW,7 NE;
+ * ranks8[d] = neighbour tile or -1; snd/rcv[4*d..] = {i0,i1,j0,j1}: block sent towards d / destination of the block
+ * arriving from d (replaces the two phases of Utility/mp_exchange.F:520-532,761-773 by one exchange with corner messages) */
+int roms_b200_halo_plan(const roms_b200_bounds* b, int halo, int* ranks8, int* snd, int* rcv);
+
 /* ---- lifetime (replaces nothing in the reference; called from ROMS_initialize
  *      after ROMS_allocate_arrays, Drivers/nl_roms.h:180, and from ROMS_finalize) */
 int roms_b200_create(const roms_b200_bounds* b, const roms_b200_params* p, int device, roms_b200_ctx** out);

@@ -78,3 +78,33 @@ extern "C" int roms_b200_tile_neighbors(const roms_b200_bounds* b, int* wesn) {
   wesn[3] = (NJ > 1 && (b->NSperiodic || Jt < NJ - 1)) ? ((Jt + 1) % NJ) * NI + It : -1;
   return 0;
 }
+
+// Single-phase eight-neighbour halo plan of the NVLink mailbox transport (k_halo.cu).  dir: 0 W, 1 E, 2 S, 3 N, 4 SW, 5 SE,
+// 6 NW, 7 NE.  ranks8[d] = neighbour tile (or -1); snd/rcv[d] = {i0, i1, j0, j1} (Fortran indices) of what this tile sends
+// towards d / where the block arriving from d goes.  W/E strips span Jstr..Jend extended to the array edge where the tile has
+// no S/N neighbour (physical boundary rows), S/N strips likewise in i, corners are (w x w) blocks: after ONE exchange the halo
+// frame holds what the two phases of mp_exchange (W/E, then S/N over the full i-range; mp_exchange.F:520-532,761-773) produce.
+extern "C" int roms_b200_halo_plan(const roms_b200_bounds* b, int w, int* ranks8, int* snd, int* rcv) {
+  if (!b || !ranks8 || !snd || !rcv) return 1;
+  int nb[4];
+  roms_b200_tile_neighbors(b, nb);
+  const int NI = b->NtileI, me = b->Jtile * NI + b->Itile;
+  for (int q = 0; q < 4; ++q) ranks8[q] = (nb[q] == me) ? -1 : nb[q];
+  for (int q = 4; q < 8; ++q) ranks8[q] = -1;
+  if (ranks8[2] >= 0 && ranks8[0] >= 0) ranks8[4] = (ranks8[2] / NI) * NI + ranks8[0] % NI;
+  if (ranks8[2] >= 0 && ranks8[1] >= 0) ranks8[5] = (ranks8[2] / NI) * NI + ranks8[1] % NI;
+  if (ranks8[3] >= 0 && ranks8[0] >= 0) ranks8[6] = (ranks8[3] / NI) * NI + ranks8[0] % NI;
+  if (ranks8[3] >= 0 && ranks8[1] >= 0) ranks8[7] = (ranks8[3] / NI) * NI + ranks8[1] % NI;
+  const bool hW = ranks8[0] >= 0, hE = ranks8[1] >= 0, hS = ranks8[2] >= 0, hN = ranks8[3] >= 0;
+  const int ia = hW ? b->Istr : b->LBi, ib = hE ? b->Iend : b->UBi, ja = hS ? b->Jstr : b->LBj, jb = hN ? b->Jend : b->UBj;
+  const int iW0 = b->Istr, iW1 = b->Istr + w - 1, iE0 = b->Iend - w + 1, iE1 = b->Iend;
+  const int jS0 = b->Jstr, jS1 = b->Jstr + w - 1, jN0 = b->Jend - w + 1, jN1 = b->Jend;
+  const int gW0 = b->Istr - w, gW1 = b->Istr - 1, gE0 = b->Iend + 1, gE1 = b->Iend + w;
+  const int gS0 = b->Jstr - w, gS1 = b->Jstr - 1, gN0 = b->Jend + 1, gN1 = b->Jend + w;
+  const int S[8][4] = {{iW0, iW1, ja, jb}, {iE0, iE1, ja, jb}, {ia, ib, jS0, jS1}, {ia, ib, jN0, jN1},
+                       {iW0, iW1, jS0, jS1}, {iE0, iE1, jS0, jS1}, {iW0, iW1, jN0, jN1}, {iE0, iE1, jN0, jN1}};
+  const int R[8][4] = {{gW0, gW1, ja, jb}, {gE0, gE1, ja, jb}, {ia, ib, gS0, gS1}, {ia, ib, gN0, gN1},
+                       {gW0, gW1, gS0, gS1}, {gE0, gE1, gS0, gS1}, {gW0, gW1, gN0, gN1}, {gE0, gE1, gN0, gN1}};
+  for (int d = 0; d < 8; ++d) for (int q = 0; q < 4; ++q) { snd[4 * d + q] = S[d][q]; rcv[4 * d + q] = R[d][q]; }
+  return 0;
+}

@@ -209,15 +209,9 @@ int roms_b200_p2p_connect(roms_b200_ctx* c, const char* handles, int nranks) {
   const roms_b200_bounds& b = c->D.b;
   if (nranks != b.NtileI * b.NtileJ) return 1;
   int nb[4]; roms_b200_tile_neighbors(&b, nb);
-  const int me = b.Jtile * b.NtileI + b.Itile, NI = b.NtileI;
-  // diagonal neighbours: the W/E neighbour of my S/N neighbour (tile_neighbors, mp_exchange.F:118-197, applied twice)
-  auto col = [&](int r) { return r % NI; };
-  auto row = [&](int r) { return r / NI; };
-  int r8[P2P_NDIR] = {nb[0], nb[1], nb[2], nb[3], -1, -1, -1, -1};
-  if (nb[2] >= 0 && nb[0] >= 0) r8[4] = row(nb[2]) * NI + col(nb[0]);
-  if (nb[2] >= 0 && nb[1] >= 0) r8[5] = row(nb[2]) * NI + col(nb[1]);
-  if (nb[3] >= 0 && nb[0] >= 0) r8[6] = row(nb[3]) * NI + col(nb[0]);
-  if (nb[3] >= 0 && nb[1] >= 0) r8[7] = row(nb[3]) * NI + col(nb[1]);
+  const int me = b.Jtile * b.NtileI + b.Itile;
+  int r8[P2P_NDIR], sr[4 * P2P_NDIR], rr[4 * P2P_NDIR];
+  if (roms_b200_halo_plan(&b, c->D.halo, r8, sr, rr)) return 1;
   for (int q = 0; q < P2P_NDIR; ++q) {
     c->p2p_peer[q] = nullptr; c->p2p_rank[q] = r8[q];
     if (r8[q] < 0 || r8[q] == me) { c->p2p_rank[q] = -1; continue; }
@@ -284,24 +278,18 @@ int halo_exchange(roms_b200_ctx* c, double* const* bases, const int* nplanes, in
   const int w = c->D.halo;
   if (c->p2p_on) {
     const roms_b200_bounds& b = c->D.b; const int ni = c->D.ni;
-    const bool hW = c->p2p_rank[0] >= 0, hE = c->p2p_rank[1] >= 0, hS = c->p2p_rank[2] >= 0, hN = c->p2p_rank[3] >= 0;
-    if (!(hW || hE || hS || hN)) return 0;
-    // i-range of the S/N strips and j-range of the W/E strips: the interior, extended to the array edge where there is no
-    // neighbour on that side (physical boundary rows / locally maintained periodic images)
-    const int ia = hW ? b.Istr : b.LBi, ib = hE ? b.Iend : b.UBi, ja = hS ? b.Jstr : b.LBj, jb = hN ? b.Jend : b.UBj;
-    auto rect = [&](int i0, int i1, int j0, int j1) { return Rect{(i0 - b.LBi) + ni * (j0 - b.LBj), i1 - i0 + 1, j1 - j0 + 1}; };
+    int r8[P2P_NDIR], sr[4 * P2P_NDIR], rr[4 * P2P_NDIR];
+    if (roms_b200_halo_plan(&b, w, r8, sr, rr)) return 1;
+    bool any = false;
+    for (int q = 0; q < P2P_NDIR; ++q) any = any || c->p2p_rank[q] >= 0;
+    if (!any) return 0;
+    auto rect = [&](const int* r) { return Rect{(r[0] - b.LBi) + ni * (r[2] - b.LBj), r[1] - r[0] + 1, r[3] - r[2] + 1}; };
     P2PArgs a{};
     a.mine = c->p2p_mem; a.cap = c->halo_cap; a.seq = c->p2p_seq; a.ticket = c->p2p_ticket;
-    for (int q = 0; q < P2P_NDIR; ++q) a.peer[q] = (c->p2p_rank[q] >= 0) ? c->p2p_peer[q] : nullptr;
-    const int iW0 = b.Istr, iW1 = b.Istr + w - 1, iE0 = b.Iend - w + 1, iE1 = b.Iend, jS0 = b.Jstr, jS1 = b.Jstr + w - 1, jN0 = b.Jend - w + 1, jN1 = b.Jend;
-    a.snd[0] = rect(iW0, iW1, ja, jb);            a.rcv[0] = rect(b.Istr - w, b.Istr - 1, ja, jb);
-    a.snd[1] = rect(iE0, iE1, ja, jb);            a.rcv[1] = rect(b.Iend + 1, b.Iend + w, ja, jb);
-    a.snd[2] = rect(ia, ib, jS0, jS1);            a.rcv[2] = rect(ia, ib, b.Jstr - w, b.Jstr - 1);
-    a.snd[3] = rect(ia, ib, jN0, jN1);            a.rcv[3] = rect(ia, ib, b.Jend + 1, b.Jend + w);
-    a.snd[4] = rect(iW0, iW1, jS0, jS1);          a.rcv[4] = rect(b.Istr - w, b.Istr - 1, b.Jstr - w, b.Jstr - 1);
-    a.snd[5] = rect(iE0, iE1, jS0, jS1);          a.rcv[5] = rect(b.Iend + 1, b.Iend + w, b.Jstr - w, b.Jstr - 1);
-    a.snd[6] = rect(iW0, iW1, jN0, jN1);          a.rcv[6] = rect(b.Istr - w, b.Istr - 1, b.Jend + 1, b.Jend + w);
-    a.snd[7] = rect(iE0, iE1, jN0, jN1);          a.rcv[7] = rect(b.Iend + 1, b.Iend + w, b.Jend + 1, b.Jend + w);
+    for (int q = 0; q < P2P_NDIR; ++q) {
+      a.peer[q] = (c->p2p_rank[q] >= 0) ? c->p2p_peer[q] : nullptr;
+      a.snd[q] = rect(sr + 4 * q); a.rcv[q] = rect(rr + 4 * q);
+    }
     static int nsm = 0;
     if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
     // one block per (plane, direction) item while they all fit on the GPU at once (a single block for the small 2-D swaps was

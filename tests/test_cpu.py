@@ -175,3 +175,52 @@ def test_halo_plan_gloo_world2():
                             "127.0.0.1", "--master-port", "29533", script] + tiles.split(), capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         assert "HALO_OK" in r.stdout
+
+
+def test_halo_plan_eight_neighbours():
+    """The single-phase eight-neighbour plan of the NVLink mailbox transport (roms_b200_halo_plan), emulated on numpy for every
+    tile of several tilings: after ONE exchange every ghost cell of every tile (corners included) must hold the global field,
+    the block a tile sends towards d must have the shape of what the neighbour expects from the opposite side, and nothing
+    outside the halo frame may be touched (mp_exchange semantics, Utility/mp_exchange.F:290-773, E-W periodic / N-S closed)."""
+    L = rb.Lib.get().L
+    L.roms_b200_halo_plan.argtypes = [C.POINTER(rb.Bounds), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    Lm, Mm, w = 48, 24, 3
+    opp = [1, 0, 3, 2, 7, 6, 5, 4]
+
+    def G(i, j):                       # global analytic field, periodic in i
+        return ((i - 1) % Lm + 1) + 1000.0 * j
+
+    for nti, ntj in ((2, 1), (1, 2), (2, 2), (4, 2), (4, 1), (3, 3)):
+        tiles = []
+        for t in range(nti * ntj):
+            b = rb.tile_bounds(Lm, Mm, 4, NtileI=nti, NtileJ=ntj, tile=t, distributed=w)
+            r8, snd, rcv = (C.c_int * 8)(), (C.c_int * 32)(), (C.c_int * 32)()
+            assert L.roms_b200_halo_plan(C.byref(b), w, r8, snd, rcv) == 0
+            ni, nj = b.UBi - b.LBi + 1, b.UBj - b.LBj + 1
+            A = np.full((nj, ni), np.nan)
+            j0 = b.Jstr - (1 if b.Southern_Edge else 0)
+            j1 = b.Jend + (1 if b.Northern_Edge else 0)
+            for j in range(j0, j1 + 1):                    # interior + physical wall rows are "computed" locally
+                for i in range(b.Istr, b.Iend + 1):
+                    A[j - b.LBj, i - b.LBi] = G(i, j)
+            if nti == 1:                                   # single tile in i: periodic images are local (kernels' st())
+                for i in list(range(b.LBi, b.Istr)) + list(range(b.Iend + 1, b.UBi + 1)):
+                    A[:, i - b.LBi] = A[:, ((i - 1) % Lm + 1) - b.LBi]
+            tiles.append((b, list(r8), np.array(snd).reshape(8, 4), np.array(rcv).reshape(8, 4), A))
+        new = [t[4].copy() for t in tiles]
+        for t, (b, r8, snd, rcv, A) in enumerate(tiles):
+            for d in range(8):
+                if r8[d] < 0:
+                    continue
+                nbq = tiles[r8[d]]
+                assert nbq[1][opp[d]] == t, (nti, ntj, t, d)                  # neighbour relation is symmetric
+                s, r = snd[d], nbq[3][opp[d]]
+                assert (s[1] - s[0], s[3] - s[2]) == (r[1] - r[0], r[3] - r[2]), (nti, ntj, t, d)
+                blk = A[s[2] - b.LBj:s[3] - b.LBj + 1, s[0] - b.LBi:s[1] - b.LBi + 1]
+                nb_b = nbq[0]
+                new[r8[d]][r[2] - nb_b.LBj:r[3] - nb_b.LBj + 1, r[0] - nb_b.LBi:r[1] - nb_b.LBi + 1] = blk
+        for t, (b, r8, snd, rcv, A) in enumerate(tiles):
+            An = new[t]
+            for j in range(max(b.LBj, 0), min(b.UBj, Mm + 1) + 1):           # every physical row of the mirror, ghosts included
+                for i in range(b.Istr - w, b.Iend + w + 1):
+                    assert An[j - b.LBj, i - b.LBi] == G(i, j), (nti, ntj, t, i, j, An[j - b.LBj, i - b.LBi])
