@@ -222,6 +222,50 @@
           integer(c_int), value :: rank, nranks
           character(kind=c_char), intent(in) :: id128(128)
         END FUNCTION
+        integer(c_int) FUNCTION roms_b200_p2p_handle (ctx, handle64)    &
+     &                          BIND(C, name='roms_b200_p2p_handle')
+          IMPORT
+          type(c_ptr), value :: ctx
+          character(kind=c_char) :: handle64(64)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_p2p_connect (ctx, handles,    &
+     &                                                nranks)           &
+     &                          BIND(C, name='roms_b200_p2p_connect')
+          IMPORT
+          type(c_ptr), value :: ctx
+          character(kind=c_char), intent(in) :: handles(*)
+          integer(c_int), value :: nranks
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_upload_async (ctx, field,     &
+     &                                                 pinned_host)     &
+     &                          BIND(C, name='roms_b200_upload_async')
+          IMPORT
+          type(c_ptr), value :: ctx, pinned_host
+          integer(c_int), value :: field
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_host_alloc (bytes, p)         &
+     &                          BIND(C, name='roms_b200_host_alloc')
+          IMPORT
+          integer(c_size_t), value :: bytes
+          type(c_ptr) :: p
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_host_free (p)                 &
+     &                          BIND(C, name='roms_b200_host_free')
+          IMPORT
+          type(c_ptr), value :: p
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_diag_begin (ctx, nstp)        &
+     &                          BIND(C, name='roms_b200_diag_begin')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nstp
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_diag_end (ctx, out3)          &
+     &                          BIND(C, name='roms_b200_diag_end')
+          IMPORT
+          type(c_ptr), value :: ctx
+          real(c_double) :: out3(3)
+        END FUNCTION
       END INTERFACE
 
       CONTAINS
