@@ -125,3 +125,49 @@ def test_diag_reductions():
     sc = o.scalars()
     np.testing.assert_allclose(d, [sc["avgke"], sc["avgpe"], sc["volume"]], rtol=1e-12)
     ctx.close()
+
+
+# Shapes chosen to hit the corner cases of the tiled kernels: a ragged last i-stripe (Lm not a multiple of 32), fewer rows
+# than one j-chunk, every shared-memory ring configuration of step3d_t (N=8: two rows per slot; N=30: one row, 18 warps;
+# N=50: four levels per producer warp; N=64: six levels, the largest supported), partial last producer chunk (N=9, N=50),
+# a single stripe (Lm=20), step2d tiles cut by the domain edge.
+SHAPES = [(20, 6, 8), (33, 5, 9), (70, 9, 30), (45, 7, 50), (40, 6, 64)]
+TILE_PHASES = ["pre_step3d", "t3dmix2", "rhs3d_tile", "step2d_loop", "step3d_uv", "step3d_t"]
+
+
+@pytest.mark.parametrize("Lm,Mm,N", SHAPES)
+def test_tile_kernels_on_ragged_shapes(Lm, Mm, N):
+    """Bit-exact parity of the tiled / level-parallel kernels with the oracle on small ragged BENCHMARK grids (steps 2 and 3:
+    the second and the steady AB3 form), whole arrays including ghost points."""
+    o, ctx = make_pair(ol.BENCHMARK, Lm, Mm, N)
+    o.step(1)
+    for step in range(2):
+        for ph in ol.PHASES:
+            gpu = ph in TILE_PHASES
+            if gpu:
+                push(o, ctx)
+                indx1 = run_phase_gpu(o, ctx, ph)
+            o.phase(ph)
+            if gpu:
+                _check_phase(o, ctx, ph, bitwise=not (ph == "pre_step3d"))
+                if ph == "step2d_loop":
+                    assert indx1 == o.stepping()["indx1"]
+    ctx.close()
+
+
+def test_blown_up_state_raises_error_word():
+    """Error behaviour of the boundary: a state the reference's diag would reject (Hz = 0 -> 1/Hz not finite) must not be
+    silently 'fixed' by the branch-free reciprocal of step3d_t: the device error word is raised and roms_b200_sync returns
+    non-zero (the Fortran shim maps it to exit_flag=8, mod_scalars.F:548-561)."""
+    o, ctx = make_pair(ol.BENCHMARK, 70, 9, 30)
+    o.step(1)
+    push(o, ctx)
+    ctx.sync()                                   # healthy state: no error
+    hz = o.get("Hz").copy()
+    hz[:] = 0.0
+    ctx.upload("Hz", hz)
+    s = o.stepping()
+    ctx.call("step3d_t", s["nrhs"], s["nstp"], s["nnew"])
+    with pytest.raises(RuntimeError):
+        ctx.sync()
+    ctx.close()
