@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "../../include/roms_b200.h"
@@ -297,8 +298,10 @@ extern "C" {
 int roms_b200_ROMS_initialize(const roms_b200_config* cfg, int tile, int distributed, int device, roms_b200_driver** out) {
   roms_b200_driver* d = new roms_b200_driver();
   d->cfg = *cfg;
-  // distributed mirrors carry a halo of 3 (the fused step2d kernel reaches zeta(i-3); NghostPoints=3 in ROMS terms)
-  if (cfg->NtileI * cfg->NtileJ > 1) distributed = 3;
+  // distributed mirrors carry a halo of 6: the fused step2d kernel reaches zeta(i-3) (NghostPoints=3 in ROMS terms) and the
+  // deep-halo predictor of the fast loop is evaluated 3 points into the halo (k_step2d.cu); ROMS_B200_HALO_W=3 restores the
+  // minimum (one swap after every sub-step)
+  if (cfg->NtileI * cfg->NtileJ > 1) { const char* e = std::getenv("ROMS_B200_HALO_W"); distributed = e ? std::max(3, std::atoi(e)) : 6; }
   if (roms_b200_tile_bounds(cfg->Lm, cfg->Mm, cfg->N, cfg->NT, cfg->NAT, cfg->NtileI, cfg->NtileJ, tile, 1, 0, distributed, &d->b)) return 1;
   const int N = cfg->N;
   d->sc_r.resize(N + 1); d->Cs_r.resize(N + 1); d->sc_w.resize(N + 1); d->Cs_w.resize(N + 1);

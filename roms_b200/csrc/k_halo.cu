@@ -243,6 +243,7 @@ int roms_b200_comm_init(roms_b200_ctx* c, int rank, int nranks, const char* id12
   ncclComm_p comm = nullptr;
   NCCL_OK(g_nccl.CommInitRank(&comm, nranks, id, rank));
   c->comm = comm; c->rank = rank; c->nranks = nranks;
+  c->deep = (c->D.halo >= 6 && getenv("ROMS_B200_NO_DEEP_HALO") == nullptr) ? 1 : 0;
   { int nb[4]; roms_b200_tile_neighbors(&b, nb); c->nbW = nb[0]; c->nbE = nb[1]; c->nbS = nb[2]; c->nbN = nb[3]; }
   // buffers: up to HALO_MAXPLANES planes of the larger strip
   const size_t strip = (size_t)c->D.halo * (size_t)((c->D.ni > c->D.nj) ? c->D.ni : c->D.nj);

@@ -269,13 +269,13 @@ __global__ void __launch_bounds__(S2_TX * S2_TY * 2) step2d_kernel(const Dev D, 
   }
 }
 
-static inline void launch_boxes(roms_b200_ctx* c, cudaStream_t st, const Box* bx, int n, const Step2dArgs& a) {
+static inline void launch_boxes(roms_b200_ctx* c, cudaStream_t st, const Box* bx, int n, const Step2dArgs& a, const Dev* Duse = nullptr) {
   Boxes B{}; int gx = 1, gy = 1;
   for (int q = 0; q < n; ++q) {
     B.b[q] = bx[q];
     gx = std::max(gx, (bx[q].i1 - bx[q].i0 + S2_TX) / S2_TX); gy = std::max(gy, (bx[q].j1 - bx[q].j0 + S2_TY) / S2_TY);
   }
-  step2d_kernel<<<dim3(gx, gy, n), dim3(S2_TX, S2_TY, 2), 0, st>>>(c->D, B, a); c->launches++;
+  step2d_kernel<<<dim3(gx, gy, n), dim3(S2_TX, S2_TY, 2), 0, st>>>(Duse ? *Duse : c->D, B, a); c->launches++;
 }
 // With neighbours, the sub-step is split so that the halo exchange of the frame overlaps the interior stencil: the frame
 // (the strips of width `halo` the neighbours need) runs on the launch stream and is followed by the exchange; the interior
@@ -288,6 +288,21 @@ int k_step2d(roms_b200_ctx* c, int krhs, int kstp, int knew, int nstp, int nnew,
   const bool hW = c->comm && c->nbW >= 0, hE = c->comm && c->nbE >= 0, hS = c->comm && c->nbS >= 0, hN = c->comm && c->nbN >= 0;
   const int w = c->D.halo;
   c->forked = 0;
+  if (c->deep && pred && (hW || hE || hS || hN)) {
+    // Deep-halo predictor: every point is advanced from levels it only reads, so the predictor can also be evaluated on the
+    // 3 halo points next to each neighbour (the halo is >= 6 wide and was refreshed after the last corrector): the corrector
+    // then finds zeta/ubar/vbar(3), rzeta, rubar of its whole stencil locally and the swap after the predictor disappears
+    // (59 -> 30 swaps per fast loop; same operations on the same operands on both sides of a tile edge -> same bits).
+    const int e = 3;
+    Dev De = c->D; roms_b200_bounds& q = De.b;
+    if (hW) { q.Istr -= e; q.IstrU -= e; q.IstrR -= e; }
+    if (hE) { q.Iend += e; q.IendR += e; }
+    if (hS) { q.Jstr -= e; q.JstrV -= e; q.JstrR -= e; }
+    if (hN) { q.Jend += e; q.JendR += e; }
+    const Box ext{q.IstrR, q.IendR, q.JstrR, q.JendR};
+    launch_boxes(c, c->stream, &ext, 1, a, &De);
+    return 0;
+  }
   if (!overlap || !(hW || hE || hS || hN) || (b.Iend - b.Istr + 1) <= 2 * w + 1 || (b.Jend - b.Jstr + 1) <= 2 * w + 1) {
     launch_boxes(c, c->stream, &full, 1, a);
     return 0;

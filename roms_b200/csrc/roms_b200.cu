@@ -249,6 +249,7 @@ static int fast_loop_launch(roms_b200_ctx* c, int nstp, int nnew, int iic, int n
       k_step2d(c, krhs, kstp, knew, nstp, nnew, iif, 1, iic, ntfirst);
       if (c->comm) {      // mp_exchange2d calls of step2d_LF_AM3.h:842,1013,1068,3043 aggregated into one message
         if (iif == nfast + 1) { const XF x[3] = {xf2(FID(Zt_avg1)), xf2(FID(DU_avg1)), xf2(FID(DV_avg1))}; if (xchg(c, x, 3)) return 1; }
+        else if (c->deep) { }            // deep-halo predictor (k_step2d): its results exist on the 3 halo points the corrector reads
         else { const XF x[4] = {xf2(FID(zeta), knew), xf2(FID(ubar), knew), xf2(FID(vbar), knew), xf2(FID(rzeta), krhs)}; if (xchg(c, x, 4)) return 1; }
         if (k_step2d_join(c)) return 1;
       }
@@ -327,6 +328,7 @@ int roms_b200_main3d(roms_b200_ctx* c, int nsteps, int analytic_forcing, int wit
     k_pre_step3d(c, nrhs, nstp, nnew, iic, ntf);
     { XF x[HALO_MAXF]; int n = 0; for (int it = 1; it <= c->D.b.NT; ++it) x[n++] = xf3(c, FID(t), 3, it); if (xchg(c, x, n)) return 1; }   // pre_step3d.F:1171
     k_prsgrd(c, nrhs); k_t3dmix2(c, nrhs, nstp, nnew); k_rhs3d_tile(c, nrhs); k_uv3dmix2(c, nrhs, nnew);
+    if (c->deep) { const XF x[2] = {xf2(FID(rufrc)), xf2(FID(rvfrc))}; if (xchg(c, x, 2)) return 1; }   // read by the deep-halo predictor
     if (roms_b200_step2d_loop(c, nstp, nnew, iic, ntf, &c->indx1)) return 1;
     k_set_depth(c);
     k_step3d_uv(c, nrhs, nstp, nnew, iic, ntf);
