@@ -193,15 +193,12 @@ __global__ void __launch_bounds__(256) step3d_t_kernel(const Dev D, Box bx, int 
 }
 int k_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew) {
   (void)nrhs; (void)nstp;
-  static const bool use_v1 = (getenv("ROMS_B200_STEP3D_T_V1") != nullptr);   // first (local-memory) version, kept for A/B timing
-  static const bool use_v2 = (getenv("ROMS_B200_STEP3D_T_V2") != nullptr);   // fused-sweep shared-memory version
-  if (use_v2) return k_step3d_t_v2(c, nnew);
-  static const bool use_v3 = (getenv("ROMS_B200_STEP3D_T_V3") != nullptr);   // phase-separated shared-memory version
-  if (use_v3) return k_step3d_t_v3(c, nnew);
-  static const bool use_v5 = (getenv("ROMS_B200_STEP3D_T_V5") != nullptr);   // TMA-staged tiles
-  if (use_v5) { const int rc = k_step3d_t_v5(c, nnew); if (rc != 2) return rc; }
+  // production: the warp-specialised 2.5-D j-march of k_step3d_t6.cu; it declines (rc 2) closed W/E walls and N < 4, which fall
+  // back to the column march of k_step3d_t4.cu.  ROMS_B200_STEP3D_T_V4 / _V1 select the older layouts for A/B timing
+  // (the shared-memory column variants v2/v3 and the TMA-tensor variant v5 of the first session were slower or broken and are gone).
+  static const bool use_v1 = (getenv("ROMS_B200_STEP3D_T_V1") != nullptr);   // first (local-memory) version
   static const bool use_v4 = (getenv("ROMS_B200_STEP3D_T_V4") != nullptr);   // one-thread-per-column checkpointed Thomas
-  if (!use_v1 && !use_v4) { const int rc = k_step3d_t_v6(c, nnew); if (rc != 2) return rc; }      // production: 2.5-D j-march (k_step3d_t6.cu)
+  if (!use_v1 && !use_v4) { const int rc = k_step3d_t_v6(c, nnew); if (rc != 2) return rc; }
   if (!use_v1) return k_step3d_t_v4(c, nnew);
   const roms_b200_bounds& b = c->D.b;
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT;

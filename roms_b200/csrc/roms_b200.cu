@@ -106,7 +106,6 @@ int roms_b200_destroy(roms_b200_ctx* c) {
   cudaFree((void*)c->D.sc_r); cudaFree((void*)c->D.w1); cudaFree(c->D.P); cudaFree(c->D.scratch2); cudaFree(c->D.red); cudaFree(c->D.ksbl); cudaFree(c->D.err);
   cudaFreeHost(c->h_red);
   roms_b200_comm_destroy(c);
-  k_step3d_t_v5_forget(c);
   cudaStreamDestroy(c->stream); cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
   delete c;
   return 0;

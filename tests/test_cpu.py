@@ -184,13 +184,13 @@ def test_halo_plan_eight_neighbours():
     outside the halo frame may be touched (mp_exchange semantics, Utility/mp_exchange.F:290-773, E-W periodic / N-S closed)."""
     L = rb.Lib.get().L
     L.roms_b200_halo_plan.argtypes = [C.POINTER(rb.Bounds), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-    Lm, Mm, w = 48, 24, 3
+    Lm, Mm = 48, 24
     opp = [1, 0, 3, 2, 7, 6, 5, 4]
 
     def G(i, j):                       # global analytic field, periodic in i
         return ((i - 1) % Lm + 1) + 1000.0 * j
 
-    for nti, ntj in ((2, 1), (1, 2), (2, 2), (4, 2), (4, 1), (3, 3)):
+    for nti, ntj, w in ((2, 1, 3), (1, 2, 3), (2, 2, 3), (4, 2, 3), (4, 1, 6), (3, 3, 3), (2, 2, 6), (4, 2, 6)):   # w=6: deep-halo mirror
         tiles = []
         for t in range(nti * ntj):
             b = rb.tile_bounds(Lm, Mm, 4, NtileI=nti, NtileJ=ntj, tile=t, distributed=w)
