@@ -176,7 +176,7 @@ def run_ours(args, rank, world):
     ni, nj = cfg.Lm + 6 + (0 if cfg.Lm % 2 else 0), cfg.Mm + 3
     b = rb.tile_bounds(Lm, Mm, N)
     ni, nj = b.UBi - b.LBi + 1, b.UBj - b.LBj + 1
-    e2e = {"value": cells * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ni * nj * 8, "d2h_bytes_per_step": 3 * nj * 8,
+    e2e = {"value": cells * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ni * nj * 8, "d2h_bytes_per_step": (3 * (b.Iend - b.Istr + 1) + 9) * 8,
            "ms_per_step": 1e3 * e2e_s / args.steps, "last_diag": {"avgke": diag[0], "avgpe": diag[1], "volume": diag[2]}}
     d.finalize()
     peak, peak_kind = measured_peak()
@@ -187,7 +187,7 @@ def run_ours(args, rank, world):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (analytical BENCHMARK grid/initial state/forcing, random-free)",
-            "config": {"workload": "%s %dx%dx%d full main3d loop (rho_eos, bulk_flux, KPP, %d step2d sub-steps, rhs3d, step3d_uv, step3d_t)"
+            "config": {"workload": "%s %dx%dx%d full main3d loop (rho_eos, diag every step, bulk_flux, KPP, omega, wvelocity, %d step2d sub-steps, rhs3d, step3d_uv, step3d_t)"
                        % (args.workload, Lm, Mm, N, 2 * d.nfast + 1), "tiles": "1x1", "l2": "state 0.3 GB per step > 126 MB L2, no explicit flush",
                        "fmad": "false (parity build)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb}
@@ -266,7 +266,7 @@ def run_ours_multi(args, rank, world):
                            "l2": "state 0.3 GB per GPU per step > 126 MB L2, no explicit flush", "fmad": "false (parity build)"},
                 "clocks": clocks,
                 "e2e": {"value": cells * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ni * nj * 8 * world,
-                        "d2h_bytes_per_step": 3 * nj * 8 * world, "ms_per_step": 1e3 * e2e_s / args.steps},
+                        "d2h_bytes_per_step": (3 * (b.Iend - b.Istr + 1) + 9) * 8 * world, "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": launches * world, "roofline": roof, "cpu_baseline": None}
         print(json.dumps(line))
     dist.destroy_process_group()

@@ -80,7 +80,7 @@ typedef struct roms_b200_params {
   X(Hz,1,N,1,1) X(z_r,1,N,1,1) X(z_w,0,Np1,1,1) X(Huon,1,N,1,1) X(Hvom,1,N,1,1) \
   X(diff2,1,NT,1,1) X(Akv,0,Np1,1,1) X(bvf,0,Np1,1,1) X(Akt,0,Np1,NAT,1) X(ghats,0,Np1,NAT,1) \
   X(zeta,1,3,1,1) X(ubar,1,3,1,1) X(vbar,1,3,1,1) X(rzeta,1,2,1,1) X(rubar,1,2,1,1) X(rvbar,1,2,1,1) \
-  X(rho,1,N,1,1) X(pden,1,N,1,1) X(W,0,Np1,1,1) \
+  X(rho,1,N,1,1) X(pden,1,N,1,1) X(W,0,Np1,1,1) X(wvel,0,Np1,1,1) \
   X(u,1,N,2,1) X(v,1,N,2,1) X(ru,0,Np1,2,1) X(rv,0,Np1,2,1) X(t,1,N,3,NT) \
   X(stflx,1,NT,1,1) X(btflx,1,NT,1,1) X(stflux,1,NT,1,1) X(btflux,1,NT,1,1)
 
@@ -128,6 +128,7 @@ int roms_b200_sync(roms_b200_ctx* ctx);
 int roms_b200_set_massflux(roms_b200_ctx* ctx, int nrhs);                      /* set_massflux.F:73   */
 int roms_b200_rho_eos(roms_b200_ctx* ctx, int nrhs);                           /* rho_eos.F:111,576  */
 int roms_b200_omega(roms_b200_ctx* ctx);                                       /* omega.F:96          */
+int roms_b200_wvelocity(roms_b200_ctx* ctx, int ninp);                         /* wvelocity.F:63 (main3d.F:535, ninp=nstp) */
 int roms_b200_set_zeta(roms_b200_ctx* ctx);                                    /* set_zeta.F:59       */
 int roms_b200_set_depth(roms_b200_ctx* ctx);                                   /* set_depth.F:76      */
 int roms_b200_bulk_flux(roms_b200_ctx* ctx, int nrhs);                         /* bulk_flux.F:111     */
@@ -148,6 +149,15 @@ int roms_b200_step3d_t(roms_b200_ctx* ctx, int nrhs, int nstp, int nnew);      /
 /* diag_tile reductions: out[0]=avgke, out[1]=avgpe, out[2]=volume (diag.F:225-322) */
 int roms_b200_diag(roms_b200_ctx* ctx, int nstp, double* out3);
 
+/* Everything diag_tile reports (diag.F:209-411,512-542), of the last completed roms_b200_diag / roms_b200_diag_end:
+ * out[0..2] as above, out[3..6] = max_C, max_Cu, max_Cv, max_Cw (largest Courant number and its components),
+ * out[7..9] = max_Ci, max_Cj, max_Ck (its location; first point in the reference's scan order), out[10] = maxspeed,
+ * out[11] = maxrho, out[12] = exit_flag the reference would set (0 = NoError, 1 = blow-up: non-finite energies,
+ * maxspeed > max_speed = 20 m/s or maxrho > max_rho = 200 kg/m3, mod_scalars.F:573-574). */
+#define ROMS_B200_NDIAG 13
+int roms_b200_diag_full(roms_b200_ctx* ctx, int nstp, double* out13);
+int roms_b200_diag_last(const roms_b200_ctx* ctx, double* out13);
+
 /* diag in two halves (launch + asynchronous D2H of the partial sums ; wait + final sums + mp_reduce) so that the host can
  * evaluate the next step's set_data while the device works: diag.F:225-322,405 */
 int roms_b200_diag_begin(roms_b200_ctx* ctx, int nstp);
@@ -162,7 +172,10 @@ int roms_b200_upload_async(roms_b200_ctx* ctx, int field, const double* pinned_h
  * roms_b200_step2d_loop runs main3d.F:810-918 (2*nfast+1 step2d calls) and
  * updates *indx1 as the reference does.  roms_b200_main3d runs nsteps of
  * main3d.F:216-1148 with forcing taken from the mirror (upload it beforehand,
- * or let analytic_forcing!=0 evaluate ana_* on the device each step). */
+ * or let analytic_forcing!=0 evaluate ana_* on the device each step).
+ * with_diag: 0 = no diag; 1 = diag at the reference's place in every step (after rho_eos, main3d.F:300), the host waits for it;
+ * 2 = same place, but only launched (reductions and their D2H copy stay asynchronous): roms_b200_diag_end after the call
+ * returns the diag of the LAST step's start state -- the line the reference prints for that step. */
 int roms_b200_step2d_loop(roms_b200_ctx* ctx, int nstp, int nnew, int iic, int ntfirst, int* indx1);
 int roms_b200_main3d(roms_b200_ctx* ctx, int nsteps, int analytic_forcing, int with_diag);
 /* stepping state of the mirror-resident loop: iic, ntfirst, nstp, nnew, nrhs, indx1 ; time (s) */

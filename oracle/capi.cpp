@@ -63,6 +63,12 @@ int orc_get_vec(void* h, const char* name, double* out) {
   if (!v) return -1;
   std::memcpy(out, v->data(), v->size() * sizeof(double)); return (int)v->size();
 }
+// full diag: avgke avgpe volume max_C max_Cu max_Cv max_Cw max_Ci max_Cj max_Ck maxspeed maxrho exit_flag
+void orc_get_diag(void* h, double* o) {
+  Model* M = (Model*)h;
+  o[0] = M->avgke; o[1] = M->avgpe; o[2] = M->volume; o[3] = M->max_C; o[4] = M->max_Cu; o[5] = M->max_Cv; o[6] = M->max_Cw;
+  o[7] = M->max_Ci; o[8] = M->max_Cj; o[9] = M->max_Ck; o[10] = M->maxspeed; o[11] = M->maxrho; o[12] = M->exit_flag;
+}
 void orc_get_ksbl(void* h, int* out) { Model* M = (Model*)h; std::memcpy(out, M->ksbl.data(), M->ksbl.size() * sizeof(int)); }
 // tile bounds as ints, in the order of include/roms_b200.h: roms_b200_bounds
 // the ints of one tile in the order: Istr Iend Jstr Jend IstrR IendR JstrR JendR IstrU JstrV IstrP IendP JstrP JendP

@@ -129,7 +129,7 @@ Model::Model(const Config& cfg) : c(cfg) {
   add("diff2", 1, NT); add("Akv", 0, N + 1); add("bvf", 0, N + 1);
   add("Akt", 0, N + 1, NAT); add("ghats", 0, N + 1, NAT);
   add("zeta", 1, 3); add("ubar", 1, 3); add("vbar", 1, 3); add("rzeta", 1, 2); add("rubar", 1, 2); add("rvbar", 1, 2);
-  add("rho", 1, N); add("pden", 1, N); add("W", 0, N + 1);
+  add("rho", 1, N); add("pden", 1, N); add("W", 0, N + 1); add("wvel", 0, N + 1);
   add("u", 1, N, 2); add("v", 1, N, 2); add("ru", 0, N + 1, 2); add("rv", 0, N + 1, 2);
   add("t", 1, N, 3, NT);
   add("stflx", 1, NT); add("btflx", 1, NT); add("stflux", 1, NT); add("btflux", 1, NT);
@@ -144,7 +144,7 @@ Model::Model(const Config& cfg) : c(cfg) {
   B3(Hz); B3(z_r); B3(z_w); B3(Huon); B3(Hvom);
   B2(visc2_r); B2(visc2_p); B2(hsbl); B2(Jwtype); B3(diff2); B3(Akv); B3(bvf); B4(Akt); B4(ghats);
   B2(Zt_avg1); B2(DU_avg1); B2(DU_avg2); B2(DV_avg1); B2(DV_avg2); B2(rufrc); B2(rvfrc); B2(rhoA); B2(rhoS);
-  B3(zeta); B3(ubar); B3(vbar); B3(rzeta); B3(rubar); B3(rvbar); B3(rho); B3(pden); B3(W);
+  B3(zeta); B3(ubar); B3(vbar); B3(rzeta); B3(rubar); B3(rvbar); B3(rho); B3(pden); B3(W); B3(wvel);
   B4(u); B4(v); B4(ru); B4(rv); t = v5("t"); B2(alpha); B2(beta);
   B2(sustr); B2(svstr); B2(bustr); B2(bvstr); B2(srflx); B2(Uwind); B2(Vwind); B2(Tair); B2(Pair); B2(Hair);
   B2(cloud); B2(rain); B2(lrflx); B2(lhflx); B2(shflx); B3(stflx); B3(btflx); B3(stflux); B3(btflux);

@@ -448,6 +448,7 @@ void main3d_phase(Model& M, const std::string& ph) {
   else if (ph == "set_vbc") fwd([&](const Tile& T) { set_vbc(M, T); });
   else if (ph == "vmix") rev([&](const Tile& T) { if (M.c.app == BENCHMARK) lmd_vmix(M, T); else ana_vmix(M, T); });
   else if (ph == "omega") rev([&](const Tile& T) { omega(M, T); });
+  else if (ph == "wvelocity") rev([&](const Tile& T) { wvelocity(M, T, M.nstp); });   // main3d.F:535, same tile loop as omega
   else if (ph == "set_zeta") fwd([&](const Tile& T) { set_zeta(M, T); });
   else if (ph == "pre_step3d") rev([&](const Tile& T) { pre_step3d(M, T); });
   else if (ph == "prsgrd") rev([&](const Tile& T) { prsgrd32(M, T); });
@@ -484,7 +485,7 @@ void main3d_phase(Model& M, const std::string& ph) {
 // OpenMP barriers would impose if each sub-call were its own parallel region,
 // and the results are tile-independent either way because each sub-call only
 // writes its own interior.
-static const char* kPhases[] = {"begin", "set_massflux", "rho_eos", "diag", "bulk_flux", "set_vbc", "vmix", "omega",
+static const char* kPhases[] = {"begin", "set_massflux", "rho_eos", "diag", "bulk_flux", "set_vbc", "vmix", "omega", "wvelocity",
     "set_zeta", "pre_step3d", "prsgrd", "t3dmix2", "rhs3d_tile", "uv3dmix2", "step2d_loop", "set_depth",
     "step3d_uv", "omega2", "step3d_t", "end"};
 void main3d_step(Model& M) { for (const char* p : kPhases) main3d_phase(M, p); }

@@ -58,6 +58,51 @@ void omega(Model& M, const Tile& T) {
   bc_w3d(M, T, W);
 }
 
+// Nonlinear/wvelocity.F:151-283: "true" vertical velocity (m/s) at W-points from omega, called every step
+// after omega (main3d.F:535) with Ninp=nstp; read by diag's Courant search (diag.F:246-247).
+void wvelocity(Model& M, const Tile& T, int Ninp) {
+  const int N = M.N; F3 &z_r = M.z_r, &z_w = M.z_w, &W = M.W, &wvel = M.wvel; F4 &u = M.u, &v = M.v; F2 &pm = M.pm, &pn = M.pn;
+  // wvelocity.F:151-158 (periodic exchange of the time-averaged barotropic fluxes)
+  exchange_u2d(M, T, M.DU_avg1); exchange_v2d(M, T, M.DV_avg1);
+  S3 vert(T.IminS, T.ImaxS, T.JminS, T.JmaxS, 1, N);
+  S2 wrk(T.IminS, T.ImaxS, T.JminS, T.JmaxS);
+  // :171-192  (Ui + Vj)*GRADs(z)
+  for (int k = 1; k <= N; ++k) {
+    for (int j = T.Jstr; j <= T.Jend; ++j) {
+      for (int i = T.Istr; i <= T.Iend + 1; ++i)
+        wrk(i, j) = u(i, j, k, Ninp) * (z_r(i, j, k) - z_r(i - 1, j, k)) * (pm(i - 1, j) + pm(i, j));
+      for (int i = T.Istr; i <= T.Iend; ++i) vert(i, j, k) = 0.25 * (wrk(i, j) + wrk(i + 1, j));
+    }
+    for (int j = T.Jstr; j <= T.Jend + 1; ++j) for (int i = T.Istr; i <= T.Iend; ++i)
+      wrk(i, j) = v(i, j, k, Ninp) * (z_r(i, j, k) - z_r(i, j - 1, k)) * (pn(i, j - 1) + pn(i, j));
+    for (int j = T.Jstr; j <= T.Jend; ++j) for (int i = T.Istr; i <= T.Iend; ++i)
+      vert(i, j, k) = vert(i, j, k) + 0.25 * (wrk(i, j) + wrk(i, j + 1));
+  }
+  // :203-268
+  const double cff1 = 3.0 / 8.0, cff2 = 3.0 / 4.0, cff3 = 1.0 / 8.0, cff4 = 9.0 / 16.0, cff5 = 1.0 / 16.0;
+  for (int j = T.Jstr; j <= T.Jend; ++j) {
+    for (int i = T.Istr; i <= T.Iend; ++i)
+      wrk(i, j) = (M.DU_avg1(i, j) - M.DU_avg1(i + 1, j) + M.DV_avg1(i, j) - M.DV_avg1(i, j + 1)) / (z_w(i, j, N) - z_w(i, j, 0));
+    for (int i = T.Istr; i <= T.Iend; ++i) {
+      const double slope = (z_r(i, j, 1) - z_w(i, j, 0)) / (z_r(i, j, 2) - z_r(i, j, 1));
+      wvel(i, j, 0) = cff1 * (vert(i, j, 1) - slope * (vert(i, j, 2) - vert(i, j, 1))) + cff2 * vert(i, j, 1) - cff3 * vert(i, j, 2);
+      wvel(i, j, 1) = pm(i, j) * pn(i, j) * (W(i, j, 1) + wrk(i, j) * (z_w(i, j, 1) - z_w(i, j, 0))) +
+                      cff1 * vert(i, j, 1) + cff2 * vert(i, j, 2) - cff3 * vert(i, j, 3);
+    }
+    for (int k = 2; k <= N - 2; ++k) for (int i = T.Istr; i <= T.Iend; ++i)
+      wvel(i, j, k) = pm(i, j) * pn(i, j) * (W(i, j, k) + wrk(i, j) * (z_w(i, j, k) - z_w(i, j, 0))) +
+                      cff4 * (vert(i, j, k) + vert(i, j, k + 1)) - cff5 * (vert(i, j, k - 1) + vert(i, j, k + 2));
+    for (int i = T.Istr; i <= T.Iend; ++i) {
+      const double slope = (z_w(i, j, N) - z_r(i, j, N)) / (z_r(i, j, N) - z_r(i, j, N - 1));
+      wvel(i, j, N) = pm(i, j) * pn(i, j) * wrk(i, j) * (z_w(i, j, N) - z_w(i, j, 0)) +
+                      cff1 * (vert(i, j, N) + slope * (vert(i, j, N) - vert(i, j, N - 1))) + cff2 * vert(i, j, N) - cff3 * vert(i, j, N - 1);
+      wvel(i, j, N - 1) = pm(i, j) * pn(i, j) * (W(i, j, N - 1) + wrk(i, j) * (z_w(i, j, N - 1) - z_w(i, j, 0))) +
+                          cff1 * vert(i, j, N) + cff2 * vert(i, j, N - 1) - cff3 * vert(i, j, N - 2);
+    }
+  }
+  bc_w3d(M, T, wvel);   // :272-274
+}
+
 // Nonlinear/set_zeta.F:101-118
 void set_zeta(Model& M, const Tile& T) {
   for (int j = T.JstrR; j <= T.JendR; ++j) for (int i = T.IstrR; i <= T.IendR; ++i) {

@@ -139,6 +139,9 @@ struct Model {
   double time = 0.0, tdays = 0.0;
   // diagnostics (Nonlinear/diag.F)
   double avgke = 0, avgpe = 0, volume = 0;
+  double max_C = 0, max_Cu = 0, max_Cv = 0, max_Cw = 0, maxspeed = 0, maxrho = 0;   // diag.F:211-266
+  int max_Ci = 0, max_Cj = 0, max_Ck = 0;
+  int exit_flag = 0;                                                                  // mod_scalars.F:548-561 (1 = blow-up)
   int nthreads = 1;   // >1: tiles of one tile loop run concurrently (reference's OpenMP mode)
 
   // grid (mod_grid)
@@ -154,7 +157,7 @@ struct Model {
   // coupling (mod_coupling)
   F2 Zt_avg1, DU_avg1, DU_avg2, DV_avg1, DV_avg2, rufrc, rvfrc, rhoA, rhoS;
   // ocean (mod_ocean)
-  F3 zeta, ubar, vbar, rzeta, rubar, rvbar, rho, pden, W;
+  F3 zeta, ubar, vbar, rzeta, rubar, rvbar, rho, pden, W, wvel;
   F4 u, v, ru, rv;
   F5 t;
   F2 alpha, beta;
@@ -207,6 +210,7 @@ void set_depth(Model& M, const Tile& T, F2 Zt);
 void set_massflux(Model& M, const Tile& T);
 void rho_eos(Model& M, const Tile& T);
 void omega(Model& M, const Tile& T);
+void wvelocity(Model& M, const Tile& T, int Ninp);
 void set_zeta(Model& M, const Tile& T);
 void bulk_flux(Model& M, const Tile& T);
 void set_vbc(Model& M, const Tile& T);

@@ -716,33 +716,68 @@ void uv3dmix2(Model& M, const Tile& T) {
 
 void rhs3d(Model& M, const Tile& T) { pre_step3d(M, T); prsgrd32(M, T); t3dmix2(M, T); rhs3d_tile(M, T); uv3dmix2(M, T); }
 
-// Nonlinear/diag.F:225-322: volume-integrated kinetic / potential energy and volume
-// (max-Courant search :330-400 omitted: needs wvelocity, an output-only field).
+// Nonlinear/diag.F:209-411,512-542: volume-integrated kinetic / potential energy, volume, the maximum Courant number
+// with its location, maximum speed and density anomaly, blow-up test.  Per tile the horizontal sums are taken in the
+// reference's two stages (j collapsed per i, then along i, :296-322); tiles are combined in tile order (:363-384).
 void diag(Model& M) {
-  const int N = M.N, nstp = M.nstp; const double g = M.c.g;
-  double my_avgke = 0.0, my_avgpe = 0.0, my_volume = 0.0;
+  const int N = M.N, idia = M.nstp; const double g = M.c.g, dt = M.c.dt;
+  const double spval = 1.0e37, Large = 1.0e35;     // mod_scalars.F
+  double volume = 0.0, avgke = 0.0, avgpe = 0.0, maxspeed = -Large, maxrho = -Large;
+  double max_C = 0.0, max_Cu = 0.0, max_Cv = 0.0, max_Cw = 0.0; int max_Ci = 0, max_Cj = 0, max_Ck = 0;
   for (const Tile& T : M.tiles) {
-    std::vector<double> ke2d(T.ImaxS - T.IminS + 1), pe2d(ke2d.size());
+    S2 ke2d(T.IminS, T.ImaxS, T.JminS, T.JmaxS), pe2d(T.IminS, T.ImaxS, T.JminS, T.JmaxS);
+    double my_max_C = 0.0, my_max_Cu = 0.0, my_max_Cv = 0.0, my_max_Cw = 0.0; int my_max_Ci = 0, my_max_Cj = 0, my_max_Ck = 0;
+    double my_maxspeed = 0.0, my_maxrho = -spval;
     for (int j = T.Jstr; j <= T.Jend; ++j) {
       for (int i = T.Istr; i <= T.Iend; ++i) {
-        ke2d[i - T.IminS] = 0.0;
-        pe2d[i - T.IminS] = 0.5 * g * M.z_w(i, j, N) * M.z_w(i, j, N);
+        ke2d(i, j) = 0.0;
+        pe2d(i, j) = 0.5 * g * M.z_w(i, j, N) * M.z_w(i, j, N);
       }
-      double cff = g / M.c.rho0;
+      const double cff = g / M.c.rho0;
       for (int k = N; k >= 1; --k) for (int i = T.Istr; i <= T.Iend; ++i) {
-        ke2d[i - T.IminS] = ke2d[i - T.IminS] + M.Hz(i, j, k) * 0.25 *
-            (M.u(i, j, k, nstp) * M.u(i, j, k, nstp) + M.u(i + 1, j, k, nstp) * M.u(i + 1, j, k, nstp) +
-             M.v(i, j, k, nstp) * M.v(i, j, k, nstp) + M.v(i, j + 1, k, nstp) * M.v(i, j + 1, k, nstp));
-        pe2d[i - T.IminS] = pe2d[i - T.IminS] + cff * M.Hz(i, j, k) * (M.rho(i, j, k) + 1000.0) * (M.z_r(i, j, k) - M.z_w(i, j, 0));
-      }
-      for (int i = T.Istr; i <= T.Iend; ++i) {
-        my_volume = my_volume + M.omn(i, j) * (M.z_w(i, j, N) - M.z_w(i, j, 0));
-        my_avgke = my_avgke + M.omn(i, j) * ke2d[i - T.IminS];
-        my_avgpe = my_avgpe + M.omn(i, j) * pe2d[i - T.IminS];
+        const double u2v2 = M.u(i, j, k, idia) * M.u(i, j, k, idia) + M.u(i + 1, j, k, idia) * M.u(i + 1, j, k, idia) +
+                            M.v(i, j, k, idia) * M.v(i, j, k, idia) + M.v(i, j + 1, k, idia) * M.v(i, j + 1, k, idia);
+        ke2d(i, j) = ke2d(i, j) + M.Hz(i, j, k) * 0.25 * u2v2;
+        pe2d(i, j) = pe2d(i, j) + cff * M.Hz(i, j, k) * (M.rho(i, j, k) + 1000.0) * (M.z_r(i, j, k) - M.z_w(i, j, 0));
+        const double my_Cu = 0.5 * std::fabs(M.u(i, j, k, idia) + M.u(i + 1, j, k, idia)) * dt * M.pm(i, j);
+        const double my_Cv = 0.5 * std::fabs(M.v(i, j, k, idia) + M.v(i, j + 1, k, idia)) * dt * M.pn(i, j);
+        const double my_Cw = 0.5 * std::fabs(M.wvel(i, j, k - 1) + M.wvel(i, j, k)) * dt / M.Hz(i, j, k);
+        const double my_C = my_Cu + my_Cv + my_Cw;
+        if (my_C > my_max_C) {
+          my_max_C = my_C; my_max_Cu = my_Cu; my_max_Cv = my_Cv; my_max_Cw = my_Cw; my_max_Ci = i; my_max_Cj = j; my_max_Ck = k;
+        }
+        my_maxspeed = std::max(my_maxspeed, std::sqrt(0.5 * u2v2));
+        my_maxrho = std::max(my_maxrho, M.rho(i, j, k));
       }
     }
+    for (int i = T.Istr; i <= T.Iend; ++i) { pe2d(i, T.Jend + 1) = 0.0; pe2d(i, T.Jstr - 1) = 0.0; ke2d(i, T.Jstr - 1) = 0.0; }
+    for (int j = T.Jstr; j <= T.Jend; ++j) for (int i = T.Istr; i <= T.Iend; ++i) {
+      pe2d(i, T.Jend + 1) = pe2d(i, T.Jend + 1) + M.omn(i, j) * (M.z_w(i, j, N) - M.z_w(i, j, 0));
+      pe2d(i, T.Jstr - 1) = pe2d(i, T.Jstr - 1) + M.omn(i, j) * pe2d(i, j);
+      ke2d(i, T.Jstr - 1) = ke2d(i, T.Jstr - 1) + M.omn(i, j) * ke2d(i, j);
+    }
+    double my_volume = 0.0, my_avgpe = 0.0, my_avgke = 0.0;
+    for (int i = T.Istr; i <= T.Iend; ++i) {
+      my_volume = my_volume + pe2d(i, T.Jend + 1);
+      my_avgpe = my_avgpe + pe2d(i, T.Jstr - 1);
+      my_avgke = my_avgke + ke2d(i, T.Jstr - 1);
+    }
+    // global combination, diag.F:363-384
+    volume = volume + my_volume; avgke = avgke + my_avgke; avgpe = avgpe + my_avgpe;
+    maxspeed = std::max(maxspeed, my_maxspeed); maxrho = std::max(maxrho, my_maxrho);
+    if (my_max_C == max_C) {
+      max_Ci = std::min(max_Ci, my_max_Ci); max_Cj = std::min(max_Cj, my_max_Cj); max_Ck = std::min(max_Ck, my_max_Ck);
+    } else if (my_max_C > max_C) {
+      max_C = my_max_C; max_Cu = my_max_Cu; max_Cv = my_max_Cv; max_Cw = my_max_Cw;
+      max_Ci = my_max_Ci; max_Cj = my_max_Cj; max_Ck = my_max_Ck;
+    }
   }
-  M.volume = my_volume; M.avgke = my_avgke / my_volume; M.avgpe = my_avgpe / my_volume;
+  M.volume = volume; M.avgke = avgke / volume; M.avgpe = avgpe / volume;
+  M.max_C = max_C; M.max_Cu = max_Cu; M.max_Cv = max_Cv; M.max_Cw = max_Cw; M.max_Ci = max_Ci; M.max_Cj = max_Cj; M.max_Ck = max_Ck;
+  M.maxspeed = maxspeed; M.maxrho = maxrho;
+  // diag.F:512-542: the reference tests the printed (1pe8.1) energies for NaN/Inf/overflow characters; restated as a
+  // finiteness test.  max_speed = 20 m/s, max_rho = 200 kg/m3 (mod_scalars.F:573-574).
+  if (!std::isfinite(M.avgke) || !std::isfinite(M.avgpe) || maxspeed > 20.0 || maxrho > 200.0) M.exit_flag = 1;
 }
 
 }  // namespace orc

@@ -342,8 +342,12 @@ int roms_b200_ROMS_initialize(const roms_b200_config* cfg, int tile, int distrib
 // (the reference's NINFO=1 behaviour); host_forcing==0: everything stays on the device.
 int roms_b200_ROMS_run(roms_b200_driver* d, int nsteps, int host_forcing, double* diag3) {
   int rc = 0;
-  if (!host_forcing) rc = roms_b200_main3d(d->ctx, nsteps, 1, 0);
-  else {
+  if (nsteps <= 0) return 0;
+  if (!host_forcing) {
+    // diag is launched at its place in every step (NINFO=1 as shipped, roms_benchmark1.in:264) but only the last one is read
+    rc = roms_b200_main3d(d->ctx, nsteps, 1, 2);
+    rc |= roms_b200_diag_end(d->ctx, d->last_diag);
+  } else {
     // Software pipeline over steps: the host evaluates set_data of step s+1 into the other pinned slot while the device
     // runs step s; uploads and the diag read-back are asynchronous copies on the launch stream (same data, same order).
     if (!d->pin[0][0]) {
@@ -355,15 +359,21 @@ int roms_b200_ROMS_run(roms_b200_driver* d, int nsteps, int host_forcing, double
     rc |= host_set_data(d, time / 86400.0, slot);
     for (int s = 0; s < nsteps && !rc; ++s) {
       rc |= push_forcing(d, slot);
-      rc |= roms_b200_main3d(d->ctx, 1, 0, 0);
+      rc |= roms_b200_main3d(d->ctx, 1, 0, 2);        // diag launched inside the step, after rho_eos (main3d.F:300)
       roms_b200_get_stepping(d->ctx, st, &time);
-      rc |= roms_b200_diag_begin(d->ctx, st[3] /* the level just completed is nnew of that step */);
       if (s + 1 < nsteps) rc |= host_set_data(d, time / 86400.0, slot ^ 1);
       rc |= roms_b200_diag_end(d->ctx, d->last_diag);
+      double full[ROMS_B200_NDIAG];
+      roms_b200_diag_last(d->ctx, full);
+      if (!rc && full[12] != 0.0) {                   // diag.F:512-542: exit_flag=1, time stepping stops (main3d.F:362)
+        fprintf(stderr, "roms_b200: blow-up detected by diag at step %d (avgke %g, avgpe %g, maxspeed %g, maxrho %g)\n",
+                st[0] - 1, full[0], full[1], full[10], full[11]);
+        rc = 1;
+      }
       slot ^= 1;
     }
-    if (diag3) std::memcpy(diag3, d->last_diag, sizeof(d->last_diag));
   }
+  if (diag3) std::memcpy(diag3, d->last_diag, sizeof(d->last_diag));
   return rc;
 }
 

@@ -4,6 +4,7 @@
 // follows the reference operation order so results are bit-identical to a
 // non-fast-math build (compiled with -fmad=false).
 #include "common.cuh"
+#include <cmath>
 
 // ---- set_depth_tile, Nonlinear/set_depth.F:192-245 (Vtransform=2) -----------
 __global__ void set_depth_kernel(const Dev D, Box bx) {
@@ -78,6 +79,57 @@ int k_omega(roms_b200_ctx* c) {
   const roms_b200_bounds& b = c->D.b;
   Box bx{c->D.oI0, c->D.oI1, c->D.oJ0, c->D.oJ1}; dim3 blk(64, 2);
   omega_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx); c->launches++;
+  return 0;
+}
+
+// ---- wvelocity_tile, Nonlinear/wvelocity.F:171-274 (+ bc_w3d): "true" vertical velocity at W-points --------
+// One thread per water column: the s-surface contribution vert(k) (4 staggered products per level) into a private
+// array, then the cubic shift to W-points.  Same operation order as the reference, point by point.
+__global__ void wvelocity_kernel(const Dev D, Box bx, int ninp) {
+  IJ_FROM_BOX(bx);
+  const int N = D.b.N; const roms_b200_bounds& b = D.b;
+  V3 u = v3l(D, FID(u), ninp), v = v3l(D, FID(v), ninp), z_r = v3(D, FID(z_r)), z_w = v3(D, FID(z_w)), W = v3(D, FID(W)), wvel = v3(D, FID(wvel));
+  V2 pm = v2(D, FID(pm)), pn = v2(D, FID(pn)), DU = v2(D, FID(DU_avg1)), DV = v2(D, FID(DV_avg1));
+  const bool south = b.Southern_Edge && j == b.Jstr, north = b.Northern_Edge && j == b.Jend;
+  const double pmW = pm(i - 1, j) + pm(i, j), pmE = pm(i, j) + pm(i + 1, j), pnS = pn(i, j - 1) + pn(i, j), pnN = pn(i, j) + pn(i, j + 1);
+  double vert[RB_MAXN + 1];
+  for (int k = 1; k <= N; ++k) {
+    const double zc = z_r(i, j, k);
+    const double wW = u(i, j, k) * (zc - z_r(i - 1, j, k)) * pmW, wE = u(i + 1, j, k) * (z_r(i + 1, j, k) - zc) * pmE;
+    const double wS = v(i, j, k) * (zc - z_r(i, j - 1, k)) * pnS, wN = v(i, j + 1, k) * (z_r(i, j + 1, k) - zc) * pnN;
+    double vt = 0.25 * (wW + wE);
+    vt = vt + 0.25 * (wS + wN);
+    vert[k] = vt;
+  }
+  const double cff1 = 3.0 / 8.0, cff2 = 3.0 / 4.0, cff3 = 1.0 / 8.0, cff4 = 9.0 / 16.0, cff5 = 1.0 / 16.0;
+  const double zw0 = z_w(i, j, 0), zwN = z_w(i, j, N);
+  const double wrk = (DU(i, j) - DU(i + 1, j) + DV(i, j) - DV(i, j + 1)) / (zwN - zw0);
+  const double pmn = pm(i, j) * pn(i, j);
+  auto put = [&](int k, double val) {
+    st(D, wvel, i, j, k, val);
+    if (south) st(D, wvel, i, j - 1, k, val);
+    if (north) st(D, wvel, i, j + 1, k, val);
+  };
+  {
+    const double slope = (z_r(i, j, 1) - zw0) / (z_r(i, j, 2) - z_r(i, j, 1));
+    put(0, cff1 * (vert[1] - slope * (vert[2] - vert[1])) + cff2 * vert[1] - cff3 * vert[2]);
+    put(1, pmn * (W(i, j, 1) + wrk * (z_w(i, j, 1) - zw0)) + cff1 * vert[1] + cff2 * vert[2] - cff3 * vert[3]);
+  }
+  for (int k = 2; k <= N - 2; ++k)
+    put(k, pmn * (W(i, j, k) + wrk * (z_w(i, j, k) - zw0)) + cff4 * (vert[k] + vert[k + 1]) - cff5 * (vert[k - 1] + vert[k + 2]));
+  {
+    const double slope = (zwN - z_r(i, j, N)) / (z_r(i, j, N) - z_r(i, j, N - 1));
+    put(N, pmn * wrk * (zwN - zw0) + cff1 * (vert[N] + slope * (vert[N] - vert[N - 1])) + cff2 * vert[N] - cff3 * vert[N - 1]);
+    put(N - 1, pmn * (W(i, j, N - 1) + wrk * (z_w(i, j, N - 1) - zw0)) + cff1 * vert[N] + cff2 * vert[N - 1] - cff3 * vert[N - 2]);
+  }
+}
+// Interior columns of the tile only (plus E-W periodic images and closed-wall rows): wvel is read by diag on the interior and
+// by the output path; its tile halos are not exchanged (the reference's mp_exchange3d of wvel, wvelocity.F:275-281, serves output).
+int k_wvelocity(roms_b200_ctx* c, int ninp) {
+  const roms_b200_bounds& b = c->D.b;
+  if (b.N < 3) return 1;
+  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(64, 2);
+  wvelocity_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx, ninp); c->launches++;
   return 0;
 }
 
@@ -309,40 +361,117 @@ int k_ana_vmix(roms_b200_ctx* c) {
   return 0;
 }
 
-// ---- diag_tile reductions, Nonlinear/diag.F:225-322 --------------------------
-// One block per j-row strip; deterministic two-stage sum (block partials, then a
-// fixed-order host sum), so results are reproducible run to run.
-__global__ void diag_kernel(const Dev D, int nstp, double* __restrict__ partial) {
-  const roms_b200_bounds& b = D.b; const int N = b.N; const double g = D.p.g;
-  V3 Hz = v3(D, FID(Hz)), z_w = v3(D, FID(z_w)), z_r = v3(D, FID(z_r)), rho = v3(D, FID(rho));
-  V3 u = v3l(D, FID(u), nstp), v = v3l(D, FID(v), nstp); V2 omn = v2(D, FID(omn));
-  const int j = b.Jstr + blockIdx.x;
-  double ke = 0.0, pe = 0.0, vol = 0.0;
-  for (int i = b.Istr + threadIdx.x; i <= b.Iend; i += blockDim.x) {
-    double ke2 = 0.0, pe2 = 0.5 * g * z_w(i, j, N) * z_w(i, j, N);
-    const double cff = g / D.p.rho0;
+// ---- diag_tile, Nonlinear/diag.F:209-411,512-542 -------------------------------------------------------------
+// Stage 1 (one thread per water column, k = N..1 as the reference): ke2d, pe2d of the column into two scratch planes; the
+// column's largest Courant number (strict '>' in descending k keeps the first = the reference's scan order inside a
+// column), speed and density maxima; a block (128 columns of one row) reduces the maxima with a total order, so the result
+// does not depend on the reduction tree.
+// Stage 2: the reference's two-stage horizontal sum (diag.F:296-322): one thread per i collapses j sequentially; the host
+// then adds the per-i sums in i order -- bit-identical to the serial reference.  One extra block reduces stage 1's maxima.
+namespace {
+struct CMax { double C, Cu, Cv, Cw; int i, j, k; };
+// true if a precedes b: larger C, or the same non-zero C met earlier in the reference's scan (j ascending, k descending, i ascending)
+__device__ __forceinline__ bool cmax_before(double aC, int ai, int aj, int ak, double bC, int bi, int bj, int bk) {
+  if (aC > bC) return true;
+  if (!(aC == bC) || !(aC > 0.0)) return false;
+  if (aj != bj) return aj < bj;
+  if (ak != bk) return ak > bk;
+  return ai < bi;
+}
+constexpr int DG_NT = 128;    // threads per block of both stages
+constexpr int DG_NP = 9;      // doubles per partial: C, Cu, Cv, Cw, i, j, k, maxspeed, maxrho
+}  // namespace
+__global__ void __launch_bounds__(DG_NT) diag_cols_kernel(const Dev D, int nstp, V2 ke2d, V2 pe2d, double* __restrict__ partial) {
+  const roms_b200_bounds& b = D.b; const int N = b.N; const double g = D.p.g, dt = D.p.dt;
+  V3 Hz = v3(D, FID(Hz)), z_w = v3(D, FID(z_w)), z_r = v3(D, FID(z_r)), rho = v3(D, FID(rho)), wvel = v3(D, FID(wvel));
+  V3 u = v3l(D, FID(u), nstp), v = v3l(D, FID(v), nstp); V2 pm = v2(D, FID(pm)), pn = v2(D, FID(pn));
+  const int j = b.Jstr + blockIdx.y, i = b.Istr + blockIdx.x * DG_NT + threadIdx.x;
+  double bC = 0.0, bCu = 0.0, bCv = 0.0, bCw = 0.0, spd = 0.0, mrho = -1.0e37; int bk = 0, bi = 0, bj = 0;
+  if (i <= b.Iend) {
+    const double zwN = z_w(i, j, N), zw0 = z_w(i, j, 0), cff = g / D.p.rho0, pmi = pm(i, j), pni = pn(i, j);
+    double ke2 = 0.0, pe2 = 0.5 * g * zwN * zwN;
+    double wup = wvel(i, j, N);
     for (int k = N; k >= 1; --k) {
-      ke2 = ke2 + Hz(i, j, k) * 0.25 * (u(i, j, k) * u(i, j, k) + u(i + 1, j, k) * u(i + 1, j, k) + v(i, j, k) * v(i, j, k) + v(i, j + 1, k) * v(i, j + 1, k));
-      pe2 = pe2 + cff * Hz(i, j, k) * (rho(i, j, k) + 1000.0) * (z_r(i, j, k) - z_w(i, j, 0));
+      const double ua = u(i, j, k), ub = u(i + 1, j, k), va = v(i, j, k), vb = v(i, j + 1, k), hz = Hz(i, j, k), r = rho(i, j, k);
+      const double u2v2 = ua * ua + ub * ub + va * va + vb * vb;
+      ke2 = ke2 + hz * 0.25 * u2v2;
+      pe2 = pe2 + cff * hz * (r + 1000.0) * (z_r(i, j, k) - zw0);
+      const double wlo = wvel(i, j, k - 1);
+      const double Cu = 0.5 * fabs(ua + ub) * dt * pmi, Cv = 0.5 * fabs(va + vb) * dt * pni, Cw = 0.5 * fabs(wlo + wup) * dt / hz;
+      wup = wlo;
+      const double Cc = Cu + Cv + Cw;
+      if (Cc > bC) { bC = Cc; bCu = Cu; bCv = Cv; bCw = Cw; bk = k; bi = i; bj = j; }
+      spd = fmax(spd, sqrt(0.5 * u2v2));
+      mrho = fmax(mrho, r);
     }
-    vol += omn(i, j) * (z_w(i, j, N) - z_w(i, j, 0));
-    ke += omn(i, j) * ke2; pe += omn(i, j) * pe2;
+    ke2d(i, j) = ke2; pe2d(i, j) = pe2;
   }
-  __shared__ double s[3][256];
-  s[0][threadIdx.x] = ke; s[1][threadIdx.x] = pe; s[2][threadIdx.x] = vol;
+  __shared__ double sC[DG_NT], sS[DG_NT], sR[DG_NT]; __shared__ int sK[DG_NT], sI[DG_NT], sJ[DG_NT], sO[DG_NT];
+  const int t = threadIdx.x;
+  sC[t] = bC; sK[t] = bk; sI[t] = bi; sJ[t] = bj; sO[t] = t; sS[t] = spd; sR[t] = mrho;
   __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) for (int q = 0; q < 3; ++q) s[q][threadIdx.x] += s[q][threadIdx.x + o];
+  for (int o = DG_NT / 2; o > 0; o >>= 1) {
+    if (t < o) {
+      if (cmax_before(sC[t + o], sI[t + o], sJ[t + o], sK[t + o], sC[t], sI[t], sJ[t], sK[t])) { sC[t] = sC[t + o]; sI[t] = sI[t + o]; sJ[t] = sJ[t + o]; sK[t] = sK[t + o]; sO[t] = sO[t + o]; }
+      sS[t] = fmax(sS[t], sS[t + o]); sR[t] = fmax(sR[t], sR[t + o]);
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0) for (int q = 0; q < 3; ++q) partial[3 * blockIdx.x + q] = s[q][0];
+  double* out = partial + (size_t)DG_NP * (blockIdx.y * gridDim.x + blockIdx.x);
+  if (t == sO[0]) { out[0] = bC; out[1] = bCu; out[2] = bCv; out[3] = bCw; out[4] = bi; out[5] = bj; out[6] = bk; }
+  if (t == 0) { out[7] = sS[0]; out[8] = sR[0]; }
 }
-// diag in two halves so that a host driver can overlap its own work with the step: begin = reduction kernel + asynchronous
-// D2H of the per-row partial sums into pinned memory; end = wait, final sums in a fixed order, mp_reduce across tiles.
+// red layout: [0,wi) ke sums per i ; [wi,2wi) pe ; [2wi,3wi) volume ; [3wi,3wi+DG_NP) maxima ; then stage 1's partials
+__global__ void __launch_bounds__(DG_NT) diag_sum_kernel(const Dev D, V2 ke2d, V2 pe2d, double* __restrict__ red, int nparts) {
+  const roms_b200_bounds& b = D.b; const int N = b.N, wi = b.Iend - b.Istr + 1, t = threadIdx.x;
+  if (blockIdx.x + 1 < gridDim.x) {
+    const int i = b.Istr + blockIdx.x * DG_NT + t;
+    if (i > b.Iend) return;
+    V3 z_w = v3(D, FID(z_w)); V2 omn = v2(D, FID(omn));
+    double vol = 0.0, pe = 0.0, ke = 0.0;
+    for (int j = b.Jstr; j <= b.Jend; ++j) {
+      const double o = omn(i, j);
+      vol = vol + o * (z_w(i, j, N) - z_w(i, j, 0));
+      pe = pe + o * pe2d(i, j);
+      ke = ke + o * ke2d(i, j);
+    }
+    red[i - b.Istr] = ke; red[wi + i - b.Istr] = pe; red[2 * wi + i - b.Istr] = vol;
+    return;
+  }
+  // last block: maxima over stage 1's partials
+  const double* partial = red + 3 * wi + DG_NP;
+  double bC = 0.0, spd = 0.0, mrho = -1.0e37; int bi = 0, bj = 0, bk = 0, bq = -1;
+  for (int q = t; q < nparts; q += DG_NT) {
+    const double* p = partial + (size_t)DG_NP * q;
+    if (cmax_before(p[0], (int)p[4], (int)p[5], (int)p[6], bC, bi, bj, bk)) { bC = p[0]; bi = (int)p[4]; bj = (int)p[5]; bk = (int)p[6]; bq = q; }
+    spd = fmax(spd, p[7]); mrho = fmax(mrho, p[8]);
+  }
+  __shared__ double sC[DG_NT], sS[DG_NT], sR[DG_NT]; __shared__ int sK[DG_NT], sI[DG_NT], sJ[DG_NT], sQ[DG_NT];
+  sC[t] = bC; sK[t] = bk; sI[t] = bi; sJ[t] = bj; sQ[t] = bq; sS[t] = spd; sR[t] = mrho;
+  __syncthreads();
+  for (int o = DG_NT / 2; o > 0; o >>= 1) {
+    if (t < o) {
+      if (cmax_before(sC[t + o], sI[t + o], sJ[t + o], sK[t + o], sC[t], sI[t], sJ[t], sK[t])) { sC[t] = sC[t + o]; sI[t] = sI[t + o]; sJ[t] = sJ[t + o]; sK[t] = sK[t + o]; sQ[t] = sQ[t + o]; }
+      sS[t] = fmax(sS[t], sS[t + o]); sR[t] = fmax(sR[t], sR[t + o]);
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    double* out = red + 3 * wi;
+    if (sQ[0] >= 0) { const double* p = partial + (size_t)DG_NP * sQ[0]; for (int q = 0; q < 7; ++q) out[q] = p[q]; }
+    else for (int q = 0; q < 7; ++q) out[q] = 0.0;
+    out[7] = sS[0]; out[8] = sR[0];
+  }
+}
+// diag in two halves so that a host driver can overlap its own work with the step: begin = the two kernels + asynchronous
+// D2H of the per-i sums and the maxima into pinned memory; end = wait, final sums in i order, mp_reduce across tiles.
 int k_diag_begin(roms_b200_ctx* c, int nstp) {
-  const roms_b200_bounds& b = c->D.b; const int nb = b.Jend - b.Jstr + 1;
-  diag_kernel<<<nb, 256, 0, c->stream>>>(c->D, nstp, c->D.red); c->launches++;
-  CUDA_OK(cudaMemcpyAsync(c->h_red, c->D.red, sizeof(double) * 3 * nb, cudaMemcpyDeviceToHost, c->stream));
+  const Dev& D = c->D; const roms_b200_bounds& b = D.b; const int wi = b.Iend - b.Istr + 1, wj = b.Jend - b.Jstr + 1;
+  const int nbx = (wi + DG_NT - 1) / DG_NT, nparts = nbx * wj;
+  V2 ke2d{D.scratch2 + 2 * D.nij, b.LBi, D.ni, b.LBj}, pe2d{D.scratch2 + 3 * D.nij, b.LBi, D.ni, b.LBj};
+  diag_cols_kernel<<<dim3(nbx, wj), DG_NT, 0, c->stream>>>(D, nstp, ke2d, pe2d, D.red + 3 * wi + DG_NP); c->launches++;
+  diag_sum_kernel<<<nbx + 1, DG_NT, 0, c->stream>>>(D, ke2d, pe2d, D.red, nparts); c->launches++;
+  CUDA_OK(cudaMemcpyAsync(c->h_red, D.red, sizeof(double) * (3 * wi + DG_NP), cudaMemcpyDeviceToHost, c->stream));
   return 0;
 }
 int k_diag(roms_b200_ctx* c, int nstp, double* out3) {
@@ -350,19 +479,43 @@ int k_diag(roms_b200_ctx* c, int nstp, double* out3) {
   return k_diag_end(c, out3);
 }
 int k_diag_end(roms_b200_ctx* c, double* out3) {
-  const roms_b200_bounds& b = c->D.b; const int nb = b.Jend - b.Jstr + 1;
+  const roms_b200_bounds& b = c->D.b; const int wi = b.Iend - b.Istr + 1;
   CUDA_OK(cudaStreamSynchronize(c->stream));
   double ke = 0, pe = 0, vol = 0;
-  for (int q = 0; q < nb; ++q) { ke += c->h_red[3 * q]; pe += c->h_red[3 * q + 1]; vol += c->h_red[3 * q + 2]; }
-  if (c->comm) {                       // mp_reduce of diag.F:405 across tiles
-    c->h_red[0] = ke; c->h_red[1] = pe; c->h_red[2] = vol;
-    CUDA_OK(cudaMemcpyAsync(c->D.red, c->h_red, 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    if (halo_allreduce_sum(c, c->D.red)) return 1;
-    CUDA_OK(cudaMemcpyAsync(c->h_red, c->D.red, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  for (int q = 0; q < wi; ++q) { vol = vol + c->h_red[2 * wi + q]; pe = pe + c->h_red[wi + q]; ke = ke + c->h_red[q]; }     // diag.F:318-322
+  double mx[DG_NP];
+  for (int q = 0; q < DG_NP; ++q) mx[q] = c->h_red[3 * wi + q];
+  if (c->comm) {
+    // mp_reduce (SUM,SUM,SUM,MAX,MAX) and mp_reduce2 (MAXLOC) of diag.F:385-411 as ONE all-reduce: every tile fills its own
+    // slot of 12 doubles, the sum gathers all slots everywhere, the host combines them in tile order as diag.F:363-384 does
+    double* h = c->h_red; const int nr = c->nranks, n = 12 * nr;
+    if (nr > 64) return 1;
+    for (int q = 0; q < n; ++q) h[q] = 0.0;
+    double* me = h + 12 * c->rank;
+    me[0] = ke; me[1] = pe; me[2] = vol;
+    for (int q = 0; q < DG_NP; ++q) me[3 + q] = mx[q];
+    CUDA_OK(cudaMemcpyAsync(c->D.red, h, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (halo_allreduce_sum(c, c->D.red, n)) return 1;
+    CUDA_OK(cudaMemcpyAsync(h, c->D.red, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
-    ke = c->h_red[0]; pe = c->h_red[1]; vol = c->h_red[2];
+    ke = 0.0; pe = 0.0; vol = 0.0;
+    double C = 0.0, Cu = 0.0, Cv = 0.0, Cw = 0.0, Ci = 0.0, Cj = 0.0, Ck = 0.0, spd = -1.0e35, mr = -1.0e35;
+    for (int r = 0; r < nr; ++r) {
+      const double* t = h + 12 * r;
+      vol = vol + t[2]; ke = ke + t[0]; pe = pe + t[1];
+      spd = std::fmax(spd, t[10]); mr = std::fmax(mr, t[11]);
+      if (t[3] == C) { Ci = std::fmin(Ci, t[7]); Cj = std::fmin(Cj, t[8]); Ck = std::fmin(Ck, t[9]); }
+      else if (t[3] > C) { C = t[3]; Cu = t[4]; Cv = t[5]; Cw = t[6]; Ci = t[7]; Cj = t[8]; Ck = t[9]; }
+    }
+    mx[0] = C; mx[1] = Cu; mx[2] = Cv; mx[3] = Cw; mx[4] = Ci; mx[5] = Cj; mx[6] = Ck; mx[7] = spd; mx[8] = mr;
   }
-  out3[0] = ke / vol; out3[1] = pe / vol; out3[2] = vol;
+  double* d = c->last_diag;
+  d[0] = ke / vol; d[1] = pe / vol; d[2] = vol;
+  for (int q = 0; q < 7; ++q) d[3 + q] = mx[q];
+  d[10] = mx[7]; d[11] = mx[8];
+  // diag.F:512-542: blow-up test (the reference inspects the printed energies for NaN/Inf/overflow characters)
+  d[12] = (!std::isfinite(d[0]) || !std::isfinite(d[1]) || d[10] > 20.0 || d[11] > 200.0) ? 1.0 : 0.0;
+  out3[0] = d[0]; out3[1] = d[1]; out3[2] = d[2];
   return 0;
 }
 

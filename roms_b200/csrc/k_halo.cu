@@ -322,9 +322,11 @@ int halo_exchange(roms_b200_ctx* c, double* const* bases, const int* nplanes, in
   return 0;
 }
 
-// diag's mp_reduce (Utility/distribute.F:6880): sum of 3 doubles over all tiles
-int halo_allreduce_sum(roms_b200_ctx* c, double* dev3) {
+// diag's mp_reduce / mp_reduce2 (Utility/distribute.F): element-wise sum of n doubles over all tiles.  k_grid.cu gives every
+// tile its own slot of the vector (zeros elsewhere), so one all-reduce gathers every tile's partial results on every rank
+// and the host combines them in tile order (deterministic, and MAXLOC needs no second round).
+int halo_allreduce_sum(roms_b200_ctx* c, double* dev, int n) {
   if (!c->comm) return 0;
-  NCCL_OK(g_nccl.AllReduce(dev3, dev3, 3, kNcclFloat64, kNcclSum, (ncclComm_p)c->comm, c->stream));
+  NCCL_OK(g_nccl.AllReduce(dev, dev, (size_t)n, kNcclFloat64, kNcclSum, (ncclComm_p)c->comm, c->stream));
   return 0;
 }

@@ -85,11 +85,12 @@ int roms_b200_create(const roms_b200_bounds* b, const roms_b200_params* p, int d
   D.w1 = v; D.w2 = v + (2 * p->ndtfast + 4);
   if (dev_alloc(&D.P, D.nij * b->N)) return 4;
   if (dev_alloc(&D.scratch2, D.nij * 8)) return 4;
-  c->nred_blocks = D.nj;
-  if (dev_alloc(&D.red, (size_t)3 * D.nj)) return 4;
+  // diag (k_grid.cu): 3 sums per interior column i + 9 maxima + 9 per block of 128 columns of a row
+  const size_t nred = (size_t)3 * D.ni + 16 + 12 * 64 + (size_t)9 * ((D.ni + 127) / 128) * D.nj;   // + one 12-double slot per tile (<= 64)
+  if (dev_alloc(&D.red, nred)) return 4;
   if (dev_alloc(&D.ksbl, D.nij)) return 4;
   if (dev_alloc(&D.err, 1)) return 4;
-  CUDA_OK(cudaMallocHost((void**)&c->h_red, sizeof(double) * 3 * D.nj));
+  CUDA_OK(cudaMallocHost((void**)&c->h_red, sizeof(double) * (3 * D.ni + 16 + 12 * 64)));
   // initialise_mixing (mod_mixing.F:1430-1530) background values are the host's job (upload Akv,Akt,...)
   c->iic = 0; c->ntfirst = 1; c->nstp = 1; c->nnew = 1; c->nrhs = 1; c->indx1 = 1; c->time = 0.0;
   c->use_graph = (getenv("ROMS_B200_NO_GRAPH") == nullptr);
@@ -174,6 +175,7 @@ long roms_b200_launch_count(const roms_b200_ctx* c) { return c->launches; }
 int roms_b200_set_massflux(roms_b200_ctx* c, int nrhs) { ENTER(c); k_set_massflux(c, nrhs); LEAVE(); }
 int roms_b200_rho_eos(roms_b200_ctx* c, int nrhs) { ENTER(c); k_rho_eos(c, nrhs); LEAVE(); }
 int roms_b200_omega(roms_b200_ctx* c) { ENTER(c); k_omega(c); LEAVE(); }
+int roms_b200_wvelocity(roms_b200_ctx* c, int ninp) { ENTER(c); if (k_wvelocity(c, ninp)) return 1; LEAVE(); }
 int roms_b200_set_zeta(roms_b200_ctx* c) { ENTER(c); k_set_zeta(c); LEAVE(); }
 int roms_b200_set_depth(roms_b200_ctx* c) { ENTER(c); k_set_depth(c); LEAVE(); }
 int roms_b200_bulk_flux(roms_b200_ctx* c, int nrhs) { ENTER(c); k_bulk_flux(c, nrhs); LEAVE(); }
@@ -196,6 +198,10 @@ int roms_b200_step2d(roms_b200_ctx* c, int krhs, int kstp, int knew, int nstp, i
 int roms_b200_step3d_uv(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntfirst) { ENTER(c); k_step3d_uv(c, nrhs, nstp, nnew, iic, ntfirst); LEAVE(); }
 int roms_b200_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew) { ENTER(c); k_step3d_t(c, nrhs, nstp, nnew); LEAVE(); }
 int roms_b200_diag(roms_b200_ctx* c, int nstp, double* out3) { ENTER(c); if (k_diag(c, nstp, out3)) return 1; LEAVE(); }
+int roms_b200_diag_full(roms_b200_ctx* c, int nstp, double* out13) {
+  ENTER(c); double d3[3]; if (k_diag(c, nstp, d3)) return 1; memcpy(out13, c->last_diag, sizeof(c->last_diag)); LEAVE();
+}
+int roms_b200_diag_last(const roms_b200_ctx* c, double* out13) { if (!c || !out13) return 1; memcpy(out13, c->last_diag, sizeof(c->last_diag)); return 0; }
 int roms_b200_diag_begin(roms_b200_ctx* c, int nstp) { ENTER(c); if (k_diag_begin(c, nstp)) return 1; LEAVE(); }
 int roms_b200_diag_end(roms_b200_ctx* c, double* out3) { ENTER(c); if (k_diag_end(c, out3)) return 1; LEAVE(); }
 int roms_b200_host_alloc(size_t bytes, void** p) { CUDA_OK(cudaMallocHost(p, bytes)); return 0; }
@@ -317,12 +323,15 @@ int roms_b200_main3d(roms_b200_ctx* c, int nsteps, int analytic_forcing, int wit
     const int nstp = c->nstp, nnew = c->nnew, nrhs = c->nrhs, iic = c->iic, ntf = c->ntfirst;
     if (analytic_forcing) k_set_data(c, c->time / 86400.0);
     k_set_massflux(c, nrhs); k_rho_eos(c, nrhs);
-    if (with_diag) { double d[3]; if (k_diag(c, nstp, d)) return 1; }
+    if (with_diag == 1) { double d[3]; if (k_diag(c, nstp, d)) return 1; }      // main3d.F:300 (diag with NINFO=1), host waits
+    else if (with_diag) { if (k_diag_begin(c, nstp)) return 1; }                 // same place, reductions + D2H stay asynchronous:
+                                                                                 // the caller collects them with roms_b200_diag_end
     if (bench) k_bulk_flux(c, nrhs);
     k_set_vbc(c, nrhs);
     { const XF x[4] = {xf2(FID(sustr)), xf2(FID(svstr)), xf2(FID(bustr)), xf2(FID(bvstr))}; if (xchg(c, x, 4)) return 1; }
     if (bench) { k_lmd_vmix(c, nstp); const XF x[1] = {xf3(c, FID(Akv))}; if (xchg(c, x, 1)) return 1; } else k_ana_vmix(c);
     k_omega(c);
+    if (k_wvelocity(c, nstp)) return 1;                                    // main3d.F:535
     k_set_zeta(c);
     k_pre_step3d(c, nrhs, nstp, nnew, iic, ntf);
     { XF x[HALO_MAXF]; int n = 0; for (int it = 1; it <= c->D.b.NT; ++it) x[n++] = xf3(c, FID(t), 3, it); if (xchg(c, x, n)) return 1; }   // pre_step3d.F:1171

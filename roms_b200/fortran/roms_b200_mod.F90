@@ -206,6 +206,32 @@
           real(c_double), intent(out) :: out3(3)
         END FUNCTION
 !
+!  wvelocity.F:43 -> CALL roms_b200_wvelocity (ctx, Ninp)
+!
+        integer(c_int) FUNCTION roms_b200_wvelocity (ctx, ninp)         &
+     &                          BIND(C, name='roms_b200_wvelocity')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: ninp
+        END FUNCTION
+!
+!  diag.F:209-411,512-542 complete: avgke, avgpe, volume, max_C, max_Cu,
+!  max_Cv, max_Cw, max_Ci, max_Cj, max_Ck, maxspeed, maxrho, exit_flag.
+!
+        integer(c_int) FUNCTION roms_b200_diag_full (ctx, nstp, out13)  &
+     &                          BIND(C, name='roms_b200_diag_full')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nstp
+          real(c_double), intent(out) :: out13(13)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_diag_last (ctx, out13)        &
+     &                          BIND(C, name='roms_b200_diag_last')
+          IMPORT
+          type(c_ptr), value :: ctx
+          real(c_double), intent(out) :: out13(13)
+        END FUNCTION
+!
 !  NCCL communicator (replaces mp_exchange2d/3d/4d): id from rank 0 via
 !  mpi_bcast, then every rank calls comm_init.
 !

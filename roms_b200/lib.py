@@ -75,7 +75,7 @@ class Lib:
         L.roms_b200_launch_count.argtypes = [vp]
         L.roms_b200_launch_count.restype = C.c_long
         sig = {
-            "set_massflux": [ci], "rho_eos": [ci], "omega": [], "set_zeta": [], "set_depth": [], "bulk_flux": [ci],
+            "set_massflux": [ci], "rho_eos": [ci], "omega": [], "wvelocity": [ci], "set_zeta": [], "set_depth": [], "bulk_flux": [ci],
             "set_vbc": [ci], "ana_vmix": [], "lmd_vmix": [ci], "pre_step3d": [ci] * 5, "prsgrd": [ci], "t3dmix2": [ci] * 3,
             "rhs3d_tile": [ci], "uv3dmix2": [ci] * 2, "rhs3d": [ci] * 5, "step2d": [ci] * 9, "step3d_uv": [ci] * 5,
             "step3d_t": [ci] * 3, "set_data": [cd],
@@ -83,6 +83,10 @@ class Lib:
         for name, args in sig.items():
             getattr(L, "roms_b200_" + name).argtypes = [vp] + args
         L.roms_b200_diag.argtypes = [vp, ci, vp]
+        L.roms_b200_diag_full.argtypes = [vp, ci, vp]
+        L.roms_b200_diag_last.argtypes = [vp, vp]
+        L.roms_b200_diag_begin.argtypes = [vp, ci]
+        L.roms_b200_diag_end.argtypes = [vp, vp]
         L.roms_b200_step2d_loop.argtypes = [vp, ci, ci, ci, ci, C.POINTER(ci)]
         L.roms_b200_main3d.argtypes = [vp, ci, ci, ci]
         L.roms_b200_get_stepping.argtypes = [vp, vp, C.POINTER(cd)]
@@ -168,6 +172,17 @@ class Context:
     def diag(self, nstp):
         out = np.zeros(3)
         self._chk(self.L.roms_b200_diag(self.h, nstp, out.ctypes.data), "diag")
+        return out
+
+    def diag_full(self, nstp):
+        """avgke avgpe volume max_C max_Cu max_Cv max_Cw max_Ci max_Cj max_Ck maxspeed maxrho exit_flag (diag.F)."""
+        out = np.zeros(13)
+        self._chk(self.L.roms_b200_diag_full(self.h, nstp, out.ctypes.data), "diag_full")
+        return out
+
+    def diag_last(self):
+        out = np.zeros(13)
+        self._chk(self.L.roms_b200_diag_last(self.h, out.ctypes.data), "diag_last")
         return out
 
     def step2d_loop(self, nstp, nnew, iic, ntfirst, indx1):

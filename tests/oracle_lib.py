@@ -37,13 +37,13 @@ def lib():
         L.orc_field_size.argtypes = [C.c_void_p, C.c_char_p]
         for f in (L.orc_get, L.orc_set, L.orc_get_vec):
             f.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
-        for f in (L.orc_get_dims, L.orc_get_stepping, L.orc_set_stepping, L.orc_get_scalars, L.orc_get_ksbl):
+        for f in (L.orc_get_dims, L.orc_get_stepping, L.orc_set_stepping, L.orc_get_scalars, L.orc_get_ksbl, L.orc_get_diag):
             f.argtypes = [C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
 
 
-PHASES = ["begin", "set_massflux", "rho_eos", "diag", "bulk_flux", "set_vbc", "vmix", "omega", "set_zeta",
+PHASES = ["begin", "set_massflux", "rho_eos", "diag", "bulk_flux", "set_vbc", "vmix", "omega", "wvelocity", "set_zeta",
           "pre_step3d", "prsgrd", "t3dmix2", "rhs3d_tile", "uv3dmix2", "step2d_loop", "set_depth", "step3d_uv",
           "omega2", "step3d_t", "end"]
 
@@ -54,7 +54,7 @@ FIELDS_2D = ["h", "f", "fomn", "pm", "pn", "om_r", "on_r", "om_u", "on_u", "om_v
              "bustr", "bvstr", "srflx", "Uwind", "Vwind", "Tair", "Pair", "Hair", "cloud", "rain", "lrflx", "lhflx",
              "shflx"]
 FIELDS_ND = ["Hz", "z_r", "z_w", "Huon", "Hvom", "diff2", "Akv", "bvf", "Akt", "ghats", "zeta", "ubar", "vbar", "rzeta",
-             "rubar", "rvbar", "rho", "pden", "W", "u", "v", "ru", "rv", "t", "stflx", "btflx", "stflux", "btflux"]
+             "rubar", "rvbar", "rho", "pden", "W", "wvel", "u", "v", "ru", "rv", "t", "stflx", "btflx", "stflux", "btflux"]
 ALL_FIELDS = FIELDS_2D + FIELDS_ND
 
 
@@ -101,6 +101,15 @@ class Oracle:
         self.L.orc_get_scalars(self.h, a)
         k = ["dt", "dtfast", "hc", "time", "tdays", "avgke", "avgpe", "volume"]
         return dict(zip(k, list(a)))
+
+    DIAG_KEYS = ["avgke", "avgpe", "volume", "max_C", "max_Cu", "max_Cv", "max_Cw", "max_Ci", "max_Cj", "max_Ck", "maxspeed",
+                 "maxrho", "exit_flag"]
+
+    def diag_full(self):
+        """Everything diag.F reports after the last `diag` phase, in the order of roms_b200_diag_full."""
+        a = np.zeros(13)
+        self.L.orc_get_diag(self.h, a.ctypes.data)
+        return a
 
     def vec(self, name):
         buf = np.zeros(1024)

@@ -14,6 +14,7 @@ GPU_PHASE = {
     "bulk_flux": ("bulk_flux", lambda s: (s["nrhs"],)),
     "set_vbc": ("set_vbc", lambda s: (s["nrhs"],)),
     "omega": ("omega", lambda s: ()),
+    "wvelocity": ("wvelocity", lambda s: (s["nstp"],)),
     "set_zeta": ("set_zeta", lambda s: ()),
     "pre_step3d": ("pre_step3d", lambda s: (s["nrhs"], s["nstp"], s["nnew"], s["iic"], s["ntfirst"])),
     "prsgrd": ("prsgrd", lambda s: (s["nrhs"],)),

@@ -35,10 +35,21 @@ def run(app, tiles=(1, 1), steps=0, threads=1, **kw):
 def test_oracle_tiling_invariance(app, kw, steps):
     """ROMS/Bin/verify.sh + check_nc.sh:35-43: 1x1, 2x2, 3x3 tilings give bit-identical output."""
     a = run(app, (1, 1), steps, **kw)
+    others = []
     for tiles, th in (((2, 2), 1), ((3, 3), 1), ((4, 2), 4)):
         b = run(app, tiles, steps, threads=th, **kw)
-        for n in PROG + ["Huon", "Hvom", "W", "ru", "rv", "Akv", "Akt", "Zt_avg1", "DU_avg2", "rufrc"]:
+        others.append((tiles, b))
+        for n in PROG + ["Huon", "Hvom", "W", "wvel", "ru", "rv", "Akv", "Akt", "Zt_avg1", "DU_avg2", "rufrc"]:
             assert np.array_equal(a.get(n), b.get(n)), (tiles, n)
+    # diag of the next step: sums differ by round-off between tilings (mp_reduce order); maxima and the MAXLOC location do not
+    for o in [a] + [b for _, b in others]:
+        for ph in ("begin", "set_massflux", "rho_eos", "diag"):
+            o.phase(ph)
+    da = a.diag_full()
+    for tiles, b in others:
+        db = b.diag_full()
+        np.testing.assert_allclose(da[:3], db[:3], rtol=1e-13)
+        assert np.array_equal(da[3:], db[3:]), (tiles, da, db)
 
 
 def test_oracle_fast_time_filter():
@@ -66,6 +77,30 @@ def test_oracle_conservation_benchmark():
     S = o.shaped("t").reshape(2, 3, d["N"], d["UBj"] + 1, -1)[1, :2]
     assert np.max(np.abs(S[:, :, 1:d["Mm"] + 1, 3:3 + d["Lm"]] - 35.0)) < 1e-11
     assert np.all(np.isfinite(o.get("u"))) and np.max(np.abs(o.get("u"))) < 2.0
+
+
+def test_oracle_wvelocity_and_courant():
+    """wvelocity.F: in a resting ocean w = 0; in the spun-up channel the surface value equals the free-surface tendency
+    term (omega(N)=0) and the Courant search of diag.F returns a location inside the grid whose components add up."""
+    o = run(ol.BENCHMARK, Lm=48, Mm=24, N=30)
+    for ph in ol.PHASES[:9]:          # ... omega, wvelocity of the first step: fluid at rest
+        o.phase(ph)
+    assert np.max(np.abs(o.get("wvel"))) == 0.0
+    for ph in ol.PHASES[9:]:
+        o.phase(ph)
+    o.step(5)
+    for ph in ("begin", "set_massflux", "rho_eos", "diag"):
+        o.phase(ph)
+    d = dict(zip(ol.Oracle.DIAG_KEYS, o.diag_full()))
+    dd = o.dims()
+    assert d["max_C"] > 0 and abs(d["max_Cu"] + d["max_Cv"] + d["max_Cw"] - d["max_C"]) <= 1e-15 * d["max_C"] * 4
+    assert 1 <= d["max_Ci"] <= dd["Lm"] and 1 <= d["max_Cj"] <= dd["Mm"] and 1 <= d["max_Ck"] <= dd["N"]
+    assert 0 < d["maxspeed"] < 2.0 and 20.0 < d["maxrho"] < 60.0 and d["exit_flag"] == 0
+    w = o.shaped("wvel")
+    assert np.all(np.isfinite(w)) and 0 < np.max(np.abs(w)) < 1e-2
+    # E-W periodic images and the closed-wall rows of bc_w3d
+    Lm, Mm = dd["Lm"], dd["Mm"]
+    assert np.array_equal(w[:, :, 2 + Lm + 1], w[:, :, 2 + 1]) and np.array_equal(w[:, 0, :], w[:, 1, :]) and np.array_equal(w[:, Mm + 1, :], w[:, Mm, :])
 
 
 def test_oracle_regression_pins():

@@ -41,11 +41,26 @@ def test_roms_initialize_matches_oracle_start_state(app, Lm, Mm, N):
         rel = float(np.max(np.abs(a - g))) / max(float(a.max() - a.min()), 1e-300)
         assert rel <= 1e-10, (n, rel)
     # host-forcing path (per-step H2D of set_data's fields + D2H diag) gives the same answer as device forcing
+    # (diag runs inside the step at the reference's place, after rho_eos: the values returned are those of the last step's
+    # start state, the line the reference prints for that step)
     diag = d.run(2, host_forcing=True)
-    o.step(2)
-    o.phase("begin"); o.phase("set_massflux"); o.phase("rho_eos"); o.phase("diag")
-    sc = o.scalars()
-    np.testing.assert_allclose(diag, [sc["avgke"], sc["avgpe"], sc["volume"]], rtol=1e-9)
+    o.step(1)
+    for ph in ol.PHASES[:4]:
+        o.phase(ph)
+    ref = o.diag_full()
+    np.testing.assert_allclose(diag, ref[:3], rtol=1e-11)
+    full = d.ctx.diag_last()
+    np.testing.assert_allclose(full[3:7], ref[3:7], rtol=1e-8)          # Courant numbers
+    np.testing.assert_array_equal(full[7:10], ref[7:10])                # and where
+    np.testing.assert_allclose(full[10:12], ref[10:12], rtol=1e-9)
+    assert full[12] == 0.0
+    for ph in ol.PHASES[4:]:
+        o.phase(ph)
+    # device-resident run: same diag, launched inside every step, read once at the end
+    diag2 = d.run(1)
+    for ph in ol.PHASES[:4]:
+        o.phase(ph)
+    np.testing.assert_allclose(diag2, o.diag_full()[:3], rtol=1e-11)
     d.finalize()
 
 

@@ -115,15 +115,54 @@ def test_bitwise_loop_with_host_forcing():
     ctx.close()
 
 
-def test_diag_reductions():
-    o, ctx = make_pair(ol.BENCHMARK, 96, 40, 30)
+@pytest.mark.parametrize("Lm,Mm,N", [(96, 40, 30), (200, 9, 8)])
+def test_diag_reductions(Lm, Mm, N):
+    """diag.F in full: energies and volume summed in the reference's two-stage order -> BIT-identical to the oracle; the
+    largest Courant number with its components and location (first point in the reference's scan order), maximum speed and
+    density anomaly, exit_flag."""
+    o, ctx = make_pair(ol.BENCHMARK, Lm, Mm, N)
     o.step(3)
     o.phase("begin"); o.phase("set_massflux"); o.phase("rho_eos")
     push(o, ctx)
     o.phase("diag")
-    d = ctx.diag(o.stepping()["nstp"])
-    sc = o.scalars()
-    np.testing.assert_allclose(d, [sc["avgke"], sc["avgpe"], sc["volume"]], rtol=1e-12)
+    d = ctx.diag_full(o.stepping()["nstp"])
+    ref = o.diag_full()
+    assert ref[3] > 0.0 and ref[9] >= 1, "degenerate Courant search: %s" % ref
+    assert np.array_equal(d, ref), (d, ref)
+    np.testing.assert_array_equal(ctx.diag(o.stepping()["nstp"]), ref[:3])
+    np.testing.assert_array_equal(ctx.diag_last(), ref)
+    # ties: a state at rest has C = 0 everywhere -> location (0,0,0) as the reference's strict '>' leaves it
+    for n in ("u", "v", "wvel"):
+        ctx.upload(n, np.zeros(ctx.size(n))); o.set(n, np.zeros(ctx.size(n)))
+    o.phase("diag")
+    d0, r0 = ctx.diag_full(o.stepping()["nstp"]), o.diag_full()
+    assert np.array_equal(d0, r0) and tuple(r0[3:10]) == (0.0,) * 7, (d0, r0)
+    # equal maxima at several points: the first one in scan order (j ascending, k descending, i ascending) wins
+    u = np.zeros(ctx.size("u")); dd = o.dims(); ni, nj = dd["UBi"] - dd["LBi"] + 1, dd["UBj"] - dd["LBj"] + 1
+    u4 = u.reshape(2, N, nj, ni)
+    u4[:, :, :, :] = 0.25
+    ctx.upload("u", u); o.set("u", u)
+    pm = np.full(ctx.size("pm"), 1.0e-4); ctx.upload("pm", pm); o.set("pm", pm)
+    o.phase("diag")
+    d1, r1 = ctx.diag_full(o.stepping()["nstp"]), o.diag_full()
+    assert np.array_equal(d1, r1), (d1, r1)
+    assert (r1[7], r1[8], r1[9]) == (1.0, 1.0, float(N)), r1
+    ctx.close()
+
+
+def test_diag_detects_blow_up():
+    """diag.F:512-542: non-finite energies or speed / density beyond max_speed, max_rho set exit_flag=1."""
+    o, ctx = make_pair(ol.UPWELLING)
+    o.step(2)
+    o.phase("begin"); o.phase("set_massflux"); o.phase("rho_eos")
+    push(o, ctx)
+    assert ctx.diag_full(o.stepping()["nstp"])[12] == 0.0
+    u = o.get("u"); u[u.size // 3] = 500.0
+    ctx.upload("u", u)
+    assert ctx.diag_full(o.stepping()["nstp"])[12] == 1.0
+    u[u.size // 3] = np.nan
+    ctx.upload("u", u)
+    assert ctx.diag_full(o.stepping()["nstp"])[12] == 1.0
     ctx.close()
 
 

@@ -15,7 +15,7 @@ ctx = d.ctx
 st, _ = ctx.get_stepping()
 iic, ntf, nstp, nnew, nrhs, indx1 = (st[k] for k in ("iic", "ntfirst", "nstp", "nnew", "nrhs", "indx1"))
 phases = [("set_massflux", (nrhs,)), ("rho_eos", (nrhs,)), ("bulk_flux", (nrhs,)), ("set_vbc", (nrhs,)), ("lmd_vmix", (nstp,)),
-          ("omega", ()), ("set_zeta", ()), ("pre_step3d", (nrhs, nstp, nnew, iic, ntf)), ("prsgrd", (nrhs,)),
+          ("omega", ()), ("wvelocity", (nstp,)), ("set_zeta", ()), ("pre_step3d", (nrhs, nstp, nnew, iic, ntf)), ("prsgrd", (nrhs,)),
           ("t3dmix2", (nrhs, nstp, nnew)), ("rhs3d_tile", (nrhs,)), ("uv3dmix2", (nrhs, nnew)),
           ("set_depth", ()), ("step3d_uv", (nrhs, nstp, nnew, iic, ntf)), ("step3d_t", (nrhs, nstp, nnew))]
 tot = 0.0
@@ -28,6 +28,14 @@ for name, args in phases:
     ms = d.timer_stop() / reps
     tot += ms * (2 if name == "omega" else 1)
     print("  %-14s %8.1f us" % (name, 1e3 * ms))
+ctx.diag(nstp)
+d.timer_start()
+for _ in range(reps):
+    ctx.main3d(0)            # no-op; keeps the call pattern
+    ctx.L.roms_b200_diag_begin(ctx.h, nstp)
+ms = d.timer_stop() / reps
+tot += ms
+print("  %-14s %8.1f us  (two kernels + asynchronous D2H)" % ("diag", 1e3 * ms))
 ctx.step2d_loop(nstp, nnew, iic, ntf, indx1); ctx.sync()
 d.timer_start()
 for _ in range(reps):
