@@ -381,31 +381,45 @@ __device__ __forceinline__ bool cmax_before(double aC, int ai, int aj, int ak, d
 constexpr int DG_NT = 128;    // threads per block of both stages
 constexpr int DG_NP = 9;      // doubles per partial: C, Cu, Cv, Cw, i, j, k, maxspeed, maxrho
 }  // namespace
-__global__ void __launch_bounds__(DG_NT) diag_cols_kernel(const Dev D, int nstp, V2 ke2d, V2 pe2d, double* __restrict__ partial) {
+__global__ void __launch_bounds__(DG_NT) diag_cols_kernel(const Dev D, int nstp, V2 ke2d, V2 pe2d, V2 vo2d, double* __restrict__ partial) {
   const roms_b200_bounds& b = D.b; const int N = b.N; const double g = D.p.g, dt = D.p.dt;
   V3 Hz = v3(D, FID(Hz)), z_w = v3(D, FID(z_w)), z_r = v3(D, FID(z_r)), rho = v3(D, FID(rho)), wvel = v3(D, FID(wvel));
-  V3 u = v3l(D, FID(u), nstp), v = v3l(D, FID(v), nstp); V2 pm = v2(D, FID(pm)), pn = v2(D, FID(pn));
+  V3 u = v3l(D, FID(u), nstp), v = v3l(D, FID(v), nstp); V2 pm = v2(D, FID(pm)), pn = v2(D, FID(pn)), omn = v2(D, FID(omn));
   const int j = b.Jstr + blockIdx.y, i = b.Istr + blockIdx.x * DG_NT + threadIdx.x;
-  double bC = 0.0, bCu = 0.0, bCv = 0.0, bCw = 0.0, spd = 0.0, mrho = -1.0e37; int bk = 0, bi = 0, bj = 0;
+  double bC = 0.0, bCu = 0.0, bCv = 0.0, bCw = 0.0, spd2 = 0.0, mrho = -1.0e37; int bk = 0, bi = 0, bj = 0;
   if (i <= b.Iend) {
     const double zwN = z_w(i, j, N), zw0 = z_w(i, j, 0), cff = g / D.p.rho0, pmi = pm(i, j), pni = pn(i, j);
     double ke2 = 0.0, pe2 = 0.5 * g * zwN * zwN;
     double wup = wvel(i, j, N);
-    for (int k = N; k >= 1; --k) {
-      const double ua = u(i, j, k), ub = u(i + 1, j, k), va = v(i, j, k), vb = v(i, j + 1, k), hz = Hz(i, j, k), r = rho(i, j, k);
-      const double u2v2 = ua * ua + ub * ub + va * va + vb * vb;
-      ke2 = ke2 + hz * 0.25 * u2v2;
-      pe2 = pe2 + cff * hz * (r + 1000.0) * (z_r(i, j, k) - zw0);
-      const double wlo = wvel(i, j, k - 1);
-      const double Cu = 0.5 * fabs(ua + ub) * dt * pmi, Cv = 0.5 * fabs(va + vb) * dt * pni, Cw = 0.5 * fabs(wlo + wup) * dt / hz;
-      wup = wlo;
-      const double Cc = Cu + Cv + Cw;
-      if (Cc > bC) { bC = Cc; bCu = Cu; bCv = Cv; bCw = Cw; bk = k; bi = i; bj = j; }
-      spd = fmax(spd, sqrt(0.5 * u2v2));
-      mrho = fmax(mrho, r);
+    constexpr int KB = 5;                       // levels per load batch (the loads of a batch are issued together)
+    for (int k0 = N; k0 >= 1; k0 -= KB) {
+      double ua[KB], ub[KB], va[KB], vb[KB], hz[KB], r[KB], zr[KB], wl[KB];
+#pragma unroll
+      for (int q = 0; q < KB; ++q) {
+        const int k = max(k0 - q, 1);
+        ua[q] = u(i, j, k); ub[q] = u(i + 1, j, k); va[q] = v(i, j, k); vb[q] = v(i, j + 1, k);
+        hz[q] = Hz(i, j, k); r[q] = rho(i, j, k); zr[q] = z_r(i, j, k); wl[q] = wvel(i, j, k - 1);
+      }
+#pragma unroll
+      for (int q = 0; q < KB; ++q) {
+        const int k = k0 - q;
+        if (k >= 1) {
+          const double u2v2 = ua[q] * ua[q] + ub[q] * ub[q] + va[q] * va[q] + vb[q] * vb[q];
+          ke2 = ke2 + hz[q] * 0.25 * u2v2;
+          pe2 = pe2 + cff * hz[q] * (r[q] + 1000.0) * (zr[q] - zw0);
+          const double Cu = 0.5 * fabs(ua[q] + ub[q]) * dt * pmi, Cv = 0.5 * fabs(va[q] + vb[q]) * dt * pni, Cw = 0.5 * fabs(wl[q] + wup) * dt / hz[q];
+          wup = wl[q];
+          const double Cc = Cu + Cv + Cw;
+          if (Cc > bC) { bC = Cc; bCu = Cu; bCv = Cv; bCw = Cw; bk = k; bi = i; bj = j; }
+          spd2 = fmax(spd2, 0.5 * u2v2);        // sqrt is monotonic and correctly rounded: max sqrt(x) == sqrt(max x)
+          mrho = fmax(mrho, r[q]);
+        }
+      }
     }
-    ke2d(i, j) = ke2; pe2d(i, j) = pe2;
+    const double o = omn(i, j);
+    ke2d(i, j) = o * ke2; pe2d(i, j) = o * pe2; vo2d(i, j) = o * (zwN - zw0);     // the products of diag.F:305-313
   }
+  const double spd = sqrt(spd2);
   __shared__ double sC[DG_NT], sS[DG_NT], sR[DG_NT]; __shared__ int sK[DG_NT], sI[DG_NT], sJ[DG_NT], sO[DG_NT];
   const int t = threadIdx.x;
   sC[t] = bC; sK[t] = bk; sI[t] = bi; sJ[t] = bj; sO[t] = t; sS[t] = spd; sR[t] = mrho;
@@ -422,18 +436,19 @@ __global__ void __launch_bounds__(DG_NT) diag_cols_kernel(const Dev D, int nstp,
   if (t == 0) { out[7] = sS[0]; out[8] = sR[0]; }
 }
 // red layout: [0,wi) ke sums per i ; [wi,2wi) pe ; [2wi,3wi) volume ; [3wi,3wi+DG_NP) maxima ; then stage 1's partials
-__global__ void __launch_bounds__(DG_NT) diag_sum_kernel(const Dev D, V2 ke2d, V2 pe2d, double* __restrict__ red, int nparts) {
-  const roms_b200_bounds& b = D.b; const int N = b.N, wi = b.Iend - b.Istr + 1, t = threadIdx.x;
+__global__ void __launch_bounds__(DG_NT) diag_sum_kernel(const Dev D, V2 ke2d, V2 pe2d, V2 vo2d, double* __restrict__ red, int nparts) {
+  const roms_b200_bounds& b = D.b; const int wi = b.Iend - b.Istr + 1, t = threadIdx.x;
   if (blockIdx.x + 1 < gridDim.x) {
     const int i = b.Istr + blockIdx.x * DG_NT + t;
     if (i > b.Iend) return;
-    V3 z_w = v3(D, FID(z_w)); V2 omn = v2(D, FID(omn));
     double vol = 0.0, pe = 0.0, ke = 0.0;
-    for (int j = b.Jstr; j <= b.Jend; ++j) {
-      const double o = omn(i, j);
-      vol = vol + o * (z_w(i, j, N) - z_w(i, j, 0));
-      pe = pe + o * pe2d(i, j);
-      ke = ke + o * ke2d(i, j);
+    constexpr int JB = 8;                       // rows per load batch; the sums stay sequential in j (diag.F:303-316)
+    for (int j0 = b.Jstr; j0 <= b.Jend; j0 += JB) {
+      double a[JB], p[JB], k[JB];
+#pragma unroll
+      for (int q = 0; q < JB; ++q) { const int j = min(j0 + q, b.Jend); a[q] = vo2d(i, j); p[q] = pe2d(i, j); k[q] = ke2d(i, j); }
+#pragma unroll
+      for (int q = 0; q < JB; ++q) if (j0 + q <= b.Jend) { vol = vol + a[q]; pe = pe + p[q]; ke = ke + k[q]; }
     }
     red[i - b.Istr] = ke; red[wi + i - b.Istr] = pe; red[2 * wi + i - b.Istr] = vol;
     return;
@@ -468,9 +483,9 @@ __global__ void __launch_bounds__(DG_NT) diag_sum_kernel(const Dev D, V2 ke2d, V
 int k_diag_begin(roms_b200_ctx* c, int nstp) {
   const Dev& D = c->D; const roms_b200_bounds& b = D.b; const int wi = b.Iend - b.Istr + 1, wj = b.Jend - b.Jstr + 1;
   const int nbx = (wi + DG_NT - 1) / DG_NT, nparts = nbx * wj;
-  V2 ke2d{D.scratch2 + 2 * D.nij, b.LBi, D.ni, b.LBj}, pe2d{D.scratch2 + 3 * D.nij, b.LBi, D.ni, b.LBj};
-  diag_cols_kernel<<<dim3(nbx, wj), DG_NT, 0, c->stream>>>(D, nstp, ke2d, pe2d, D.red + 3 * wi + DG_NP); c->launches++;
-  diag_sum_kernel<<<nbx + 1, DG_NT, 0, c->stream>>>(D, ke2d, pe2d, D.red, nparts); c->launches++;
+  V2 ke2d{D.scratch2 + 2 * D.nij, b.LBi, D.ni, b.LBj}, pe2d{D.scratch2 + 3 * D.nij, b.LBi, D.ni, b.LBj}, vo2d{D.scratch2 + 4 * D.nij, b.LBi, D.ni, b.LBj};
+  diag_cols_kernel<<<dim3(nbx, wj), DG_NT, 0, c->stream>>>(D, nstp, ke2d, pe2d, vo2d, D.red + 3 * wi + DG_NP); c->launches++;
+  diag_sum_kernel<<<nbx + 1, DG_NT, 0, c->stream>>>(D, ke2d, pe2d, vo2d, D.red, nparts); c->launches++;
   CUDA_OK(cudaMemcpyAsync(c->h_red, D.red, sizeof(double) * (3 * wi + DG_NP), cudaMemcpyDeviceToHost, c->stream));
   return 0;
 }

@@ -4,6 +4,7 @@
 // These use exp/log/pow/atan: results agree with the CPU restatement to a few
 // ulp per call (device libm vs glibc), not bit-for-bit.
 #include "common.cuh"
+#include <cmath>
 
 #define VONKAR 0.41              /* mod_scalars.F:469 */
 // mod_scalars.F:1635-1712
@@ -44,40 +45,101 @@ __device__ __forceinline__ void wscale(double Ustar, double Ustar3, double zetah
     else ws = VONKAR * pow(LMD_AS * Ustar3 - LMD_CS * zetahat, r3);
   }
 }
-// spline vertical derivatives used by lmd_vmix.F:189-230 and lmd_skpp.F (same recurrences)
-__device__ __forceinline__ void splines(int N, const V3& Hz, const V3& dens, const V3& u, const V3& v, int i, int j,
-                                        double* FC, double* dR, double* dU, double* dV) {
+// ---- KPP: lmd_vmix_tile (lmd_vmix.F:99-434) + lmd_skpp_tile (lmd_skpp.F) + lmd_finish_tile (lmd_vmix.F:437-660) ----
+// Four kernels; only what is a vertical recurrence or a search runs one thread per water column, the rest runs one thread
+// per (i,j,k).  Every point is evaluated with the operations (and their order) of the reference.
+//   1 kpp_spline  (column)  spline derivatives dR (of pden), dU, dV: forward/backward recurrence (lmd_skpp.F, RI_SPLINES)
+//   2 kpp_levels  (i,j,k)   Bflux, initial ghats, interior Richardson-number mixing, bulk Richardson function FC
+//   3 kpp_sbl     (column)  boundary-layer depth hsbl (first zero crossing of FC from the surface, Ekman / Monin-Obukhov
+//                           limits), ksbl, shape-function constants G1, dG1dS at the base of the layer
+//   4 kpp_finish  (i,j,k)   boundary-layer profiles above ksbl, nonlocal flux ghats, convective adjustment, lateral
+//                           conditions (bc_w3d gradient rows + periodic images)
+// Scratch: D.kpp4 = {dR, dU, dV, FC} (ni,nj,0:N) each, D.swdk = Bflux (ni,nj,0:N), D.scratch2 planes 0..5 = G constants.
+// (The reference also splines rho for lmd_vmix's Rig but then uses bvf, lmd_vmix.F:253: that solve has no effect.)
+namespace {
+struct KppC { double lmd_Cg, Vtc; };      // mod_scalars.F:4592 ; lmd_skpp.F Vtc -- evaluated once on the host
+__device__ __forceinline__ V3 scr3(const Dev& D, double* p) { return V3{p, D.b.LBi, D.ni, D.b.LBj, D.nj, 0}; }
+__device__ __forceinline__ V2 scr2(const Dev& D, int plane) { return V2{D.scratch2 + D.nij * plane, D.b.LBi, D.ni, D.b.LBj}; }
+__device__ __forceinline__ double kpp_ustar(const Dev& D, int i, int j) {
+  V2 sustr = v2(D, FID(sustr)), svstr = v2(D, FID(svstr));
+  const double ta = 0.5 * (sustr(i, j) + sustr(i + 1, j)), tb = 0.5 * (svstr(i, j) + svstr(i, j + 1));
+  return sqrt(sqrt(ta * ta + tb * tb));
+}
+struct KppSurf { double Bo, Bosol, stT, stS, srf; int Jw; };
+__device__ __forceinline__ KppSurf kpp_surf(const Dev& D, int i, int j) {
+  KppSurf q;
+  const double al = v2(D, FID(alpha))(i, j), be = v2(D, FID(beta))(i, j);
+  q.srf = v2(D, FID(srflx))(i, j); q.stT = v2l(D, FID(stflx), 1)(i, j); q.stS = v2l(D, FID(stflx), 2)(i, j);
+  q.Bo = D.p.g * (al * (q.stT - q.srf) - be * q.stS); q.Bosol = D.p.g * al * q.srf;
+  q.Jw = (int)v2(D, FID(Jwtype))(i, j);
+  return q;
+}
+}  // namespace
+
+__global__ void __launch_bounds__(128) kpp_spline_kernel(const Dev D, Box bx, int nstp) {
+  IJ_FROM_BOX(bx);
+  const int N = D.b.N; const size_t vol = D.nij * (size_t)(N + 1);
+  V3 Hz = v3(D, FID(Hz)), pden = v3(D, FID(pden)), u = v3l(D, FID(u), nstp), v = v3l(D, FID(v), nstp);
+  V3 sR = scr3(D, D.kpp4), sU = scr3(D, D.kpp4 + vol), sV = scr3(D, D.kpp4 + 2 * vol);
+  double FC[RB_MAXN + 1], dR[RB_MAXN + 1], dU[RB_MAXN + 1], dV[RB_MAXN + 1];
   FC[0] = 0.0; dR[0] = 0.0; dU[0] = 0.0; dV[0] = 0.0;
-  for (int k = 1; k <= N - 1; ++k) {
-    const double cff = 1.0 / (2.0 * Hz(i, j, k + 1) + Hz(i, j, k) * (2.0 - FC[k - 1]));
-    FC[k] = cff * Hz(i, j, k + 1);
-    dR[k] = cff * (6.0 * (dens(i, j, k + 1) - dens(i, j, k)) - Hz(i, j, k) * dR[k - 1]);
-    dU[k] = cff * (3.0 * (u(i, j, k + 1) - u(i, j, k) + u(i + 1, j, k + 1) - u(i + 1, j, k)) - Hz(i, j, k) * dU[k - 1]);
-    dV[k] = cff * (3.0 * (v(i, j, k + 1) - v(i, j, k) + v(i, j + 1, k + 1) - v(i, j + 1, k)) - Hz(i, j, k) * dV[k - 1]);
+  double hzk = Hz(i, j, 1), dk = pden(i, j, 1), uk = u(i, j, 1), upk = u(i + 1, j, 1), vk = v(i, j, 1), vpk = v(i, j + 1, 1);
+  double fcp = 0.0, drp = 0.0, dup = 0.0, dvp = 0.0;
+  constexpr int KB = 6;                         // levels per load batch
+  for (int k0 = 1; k0 <= N - 1; k0 += KB) {
+    double hzn[KB], dn[KB], un[KB], upn[KB], vn[KB], vpn[KB];
+#pragma unroll
+    for (int q = 0; q < KB; ++q) {
+      const int kk = min(k0 + q + 1, N);
+      hzn[q] = Hz(i, j, kk); dn[q] = pden(i, j, kk); un[q] = u(i, j, kk); upn[q] = u(i + 1, j, kk); vn[q] = v(i, j, kk); vpn[q] = v(i, j + 1, kk);
+    }
+#pragma unroll
+    for (int q = 0; q < KB; ++q) {
+      const int k = k0 + q;
+      if (k <= N - 1) {
+        const double cff = 1.0 / (2.0 * hzn[q] + hzk * (2.0 - fcp));
+        fcp = cff * hzn[q];
+        drp = cff * (6.0 * (dn[q] - dk) - hzk * drp);
+        dup = cff * (3.0 * (un[q] - uk + upn[q] - upk) - hzk * dup);
+        dvp = cff * (3.0 * (vn[q] - vk + vpn[q] - vpk) - hzk * dvp);
+        FC[k] = fcp; dR[k] = drp; dU[k] = dup; dV[k] = dvp;
+        hzk = hzn[q]; dk = dn[q]; uk = un[q]; upk = upn[q]; vk = vn[q]; vpk = vpn[q];
+      }
+    }
   }
-  dR[N] = 0.0; dU[N] = 0.0; dV[N] = 0.0;
+  double rn = 0.0, un_ = 0.0, vn_ = 0.0;         // dR, dU, dV at k+1
+  sR(i, j, N) = 0.0; sU(i, j, N) = 0.0; sV(i, j, N) = 0.0;
   for (int k = N - 1; k >= 1; --k) {
-    dR[k] = dR[k] - FC[k] * dR[k + 1]; dU[k] = dU[k] - FC[k] * dU[k + 1]; dV[k] = dV[k] - FC[k] * dV[k + 1];
+    const double fc = FC[k];
+    rn = dR[k] - fc * rn; un_ = dU[k] - fc * un_; vn_ = dV[k] - fc * vn_;
+    sR(i, j, k) = rn; sU(i, j, k) = un_; sV(i, j, k) = vn_;
   }
+  sR(i, j, 0) = 0.0; sU(i, j, 0) = 0.0; sV(i, j, 0) = 0.0;
 }
 
-// lmd_vmix_tile (lmd_vmix.F:99-434) + lmd_skpp_tile (lmd_skpp.F) + lmd_finish_tile (lmd_vmix.F:437-660)
-__global__ void __launch_bounds__(128) kpp_kernel(const Dev D, Box bx, int nstp) {
+__global__ void __launch_bounds__(256) kpp_levels_kernel(const Dev D, Box bx, int nstp, KppC kc) {
   IJ_FROM_BOX(bx);
-  const roms_b200_bounds& b = D.b; const int N = b.N; const double g = D.p.g, gorho0 = D.p.g / D.p.rho0;
-  const bool south = b.Southern_Edge && !b.NSperiodic && j == b.Jstr, north = b.Northern_Edge && !b.NSperiodic && j == b.Jend;
-  V3 Hz = v3(D, FID(Hz)), z_w = v3(D, FID(z_w)), rho = v3(D, FID(rho)), pden = v3(D, FID(pden)), bvf = v3(D, FID(bvf));
+  const int N = D.b.N, k = blockIdx.z; const size_t vol = D.nij * (size_t)(N + 1);
+  const double gorho0 = D.p.g / D.p.rho0;
+  V3 Hz = v3(D, FID(Hz)), z_w = v3(D, FID(z_w)), pden = v3(D, FID(pden)), bvf = v3(D, FID(bvf));
   V3 u = v3l(D, FID(u), nstp), v = v3l(D, FID(v), nstp);
-  V3 Akv = v3(D, FID(Akv)), Akt1 = v3l(D, FID(Akt), 1), Akt2 = v3l(D, FID(Akt), 2), gh1 = v3l(D, FID(ghats), 1), gh2 = v3l(D, FID(ghats), 2);
-  V2 hsbl = v2(D, FID(hsbl)), sustr = v2(D, FID(sustr)), svstr = v2(D, FID(svstr));
-  double FC[RB_MAXN + 1], dR[RB_MAXN + 1], dU[RB_MAXN + 1], dV[RB_MAXN + 1], Bflux[RB_MAXN + 1];
-  double akv[RB_MAXN + 1], akt1[RB_MAXN + 1], akt2[RB_MAXN + 1], g1[RB_MAXN + 1], g2[RB_MAXN + 1];
-  // ---- interior shear/convective mixing
-  splines(N, Hz, rho, u, v, i, j, FC, dR, dU, dV);
-  akv[0] = Akv(i, j, 0); akv[N] = Akv(i, j, N); akt1[0] = Akt1(i, j, 0); akt1[N] = Akt1(i, j, N); akt2[0] = Akt2(i, j, 0); akt2[N] = Akt2(i, j, N);
-  for (int k = 1; k <= N - 1; ++k) {
-    const double eps = 1.0e-14, bv = bvf(i, j, k);
-    double shear2 = dU[k] * dU[k] + dV[k] * dV[k];
+  V3 Akv = v3(D, FID(Akv)), Akt1 = v3l(D, FID(Akt), 1), gh1 = v3l(D, FID(ghats), 1), gh2 = v3l(D, FID(ghats), 2);
+  V3 sR = scr3(D, D.kpp4), sU = scr3(D, D.kpp4 + vol), sV = scr3(D, D.kpp4 + 2 * vol), sF = scr3(D, D.kpp4 + 3 * vol), sB = scr3(D, D.swdk);
+  const double zwN = z_w(i, j, N), zwk = z_w(i, j, k);
+  const KppSurf q = kpp_surf(D, i, j);
+  // ---- surface buoyancy flux profile and the initial nonlocal-flux factors (lmd_skpp.F)
+  const double swdk = k_swfrac(q.Jw, zwN - zwk);
+  const double Bf = (q.Bo + q.Bosol * (1.0 - swdk));
+  sB(i, j, k) = Bf;
+  {
+    const double cff = 1.0 - (0.5 + copysign(0.5, Bf));
+    gh1(i, j, k) = -cff * (q.stT - q.srf + q.srf * (1.0 - swdk));
+    gh2(i, j, k) = cff * q.stS;
+  }
+  // ---- interior shear / internal-wave mixing (lmd_vmix.F:232-330); Akt(:,:,:,isalt) = Akt(:,:,:,itemp) is set by kpp_finish
+  if (k >= 1 && k <= N - 1) {
+    const double eps = 1.0e-14, bv = bvf(i, j, k), dUk = sU(i, j, k), dVk = sV(i, j, k);
+    double shear2 = dUk * dUk + dVk * dVk;
     const double Rig = bv / (shear2 + eps);
     double cff = fmin(1.0, fmax(0.0, Rig) / LMD_RI0);
     double nu_sx = 1.0 - cff * cff;
@@ -86,55 +148,66 @@ __global__ void __launch_bounds__(128) kpp_kernel(const Dev D, Box bx, int nstp)
     cff = shear2 * shear2 / (shear2 * shear2 + 16.0e-10);
     nu_sx = cff * nu_sx;
     cff = 1.0 / sqrt(fmax(bv, 1.0e-7));
-    akv[k] = 1.0e-6 * cff + LMD_NU0M * nu_sx;
-    akt1[k] = 1.0e-7 * cff + LMD_NU0S * nu_sx;
-    akt2[k] = akt1[k];
+    Akv(i, j, k) = 1.0e-6 * cff + LMD_NU0M * nu_sx;
+    Akt1(i, j, k) = 1.0e-7 * cff + LMD_NU0S * nu_sx;
   }
-  // ---- surface boundary layer
-  const double eps = 1.0e-10, small = 1.0e-20;
-  const double lmd_Cg = LMD_CSTAR * VONKAR * pow(LMD_CS * VONKAR * LMD_EPSILON, 1.0 / 3.0);     // mod_scalars.F:4592
-  const double Vtc = LMD_CV * sqrt(-LMD_BETAT) / (sqrt(LMD_CS * LMD_EPSILON) * LMD_RIC * VONKAR * VONKAR);
-  const double zwN = z_w(i, j, N);
-  double hs = hsbl(i, j);
-  double sl_dpth = LMD_EPSILON * (zwN - hs);
-  const double ta = 0.5 * (sustr(i, j) + sustr(i + 1, j)), tb = 0.5 * (svstr(i, j) + svstr(i, j + 1));
-  const double Ustar = sqrt(sqrt(ta * ta + tb * tb));
-  const double al = v2(D, FID(alpha))(i, j), be = v2(D, FID(beta))(i, j), srf = v2(D, FID(srflx))(i, j);
-  const double stT = v2l(D, FID(stflx), 1)(i, j), stS = v2l(D, FID(stflx), 2)(i, j);
-  const double Bo = g * (al * (stT - srf) - be * stS), Bosol = g * al * srf;
-  const int Jw = (int)v2(D, FID(Jwtype))(i, j);
-  for (int k = 0; k <= N; ++k) {
-    const double swdk = k_swfrac(Jw, zwN - z_w(i, j, k));
-    Bflux[k] = (Bo + Bosol * (1.0 - swdk));
-    const double cff = 1.0 - (0.5 + copysign(0.5, Bflux[k]));
-    g1[k] = -cff * (stT - srf + srf * (1.0 - swdk));
-    g2[k] = cff * stS;
-  }
-  splines(N, Hz, pden, u, v, i, j, FC, dR, dU, dV);
-  const double c13 = 1.0 / 3.0, c16 = 1.0 / 6.0;
-  const double Rref = pden(i, j, N) + Hz(i, j, N) * (c13 * dR[N] + c16 * dR[N - 1]);
-  const double Uref = 0.5 * (u(i, j, N) + u(i + 1, j, N)) + Hz(i, j, N) * (c13 * dU[N] + c16 * dU[N - 1]);
-  const double Vref = 0.5 * (v(i, j, N) + v(i, j + 1, N)) + Hz(i, j, N) * (c13 * dV[N] + c16 * dV[N - 1]);
-  const double Ustar3 = Ustar * Ustar * Ustar;
-  double wm, ws;
-  FC[N] = 0.0;
-  for (int k = N; k >= 1; --k) {
-    const double depth = zwN - z_w(i, j, k - 1);
-    const double sigma = (Bflux[k - 1] < 0.0) ? fmin(sl_dpth, depth) : depth;
-    const double zetahat = VONKAR * sigma * Bflux[k - 1], zetapar = zetahat / (Ustar3 + small);
+  // ---- bulk Richardson function FC(k) = Ritop - Ric*Ribot between the surface reference and level k+1 (lmd_skpp.F)
+  if (k == N) { sF(i, j, N) = 0.0; return; }
+  {
+    const double small = 1.0e-20, c13 = 1.0 / 3.0, c16 = 1.0 / 6.0;
+    const int kk = k + 1;
+    const double sl_dpth = LMD_EPSILON * (zwN - v2(D, FID(hsbl))(i, j));          // hsbl of the previous step
+    const double Ustar = kpp_ustar(D, i, j), Ustar3 = Ustar * Ustar * Ustar;
+    const double hzN = Hz(i, j, N);
+    const double Rref = pden(i, j, N) + hzN * (c13 * sR(i, j, N) + c16 * sR(i, j, N - 1));
+    const double Uref = 0.5 * (u(i, j, N) + u(i + 1, j, N)) + hzN * (c13 * sU(i, j, N) + c16 * sU(i, j, N - 1));
+    const double Vref = 0.5 * (v(i, j, N) + v(i, j + 1, N)) + hzN * (c13 * sV(i, j, N) + c16 * sV(i, j, N - 1));
+    const double depth = zwN - zwk;
+    const double sigma = (Bf < 0.0) ? fmin(sl_dpth, depth) : depth;
+    const double zetahat = VONKAR * sigma * Bf, zetapar = zetahat / (Ustar3 + small);
+    double wm, ws;
     wscale(Ustar, Ustar3, zetahat, zetapar, wm, ws);
-    const double Rk = pden(i, j, k) - Hz(i, j, k) * (c13 * dR[k - 1] + c16 * dR[k]);
-    const double Uk = 0.5 * (u(i, j, k) + u(i + 1, j, k)) - Hz(i, j, k) * (c13 * dU[k - 1] + c16 * dU[k]);
-    const double Vk = 0.5 * (v(i, j, k) + v(i, j + 1, k)) - Hz(i, j, k) * (c13 * dV[k - 1] + c16 * dV[k]);
+    const double hzk = Hz(i, j, kk);
+    const double Rk = pden(i, j, kk) - hzk * (c13 * sR(i, j, kk - 1) + c16 * sR(i, j, kk));
+    const double Uk = 0.5 * (u(i, j, kk) + u(i + 1, j, kk)) - hzk * (c13 * sU(i, j, kk - 1) + c16 * sU(i, j, kk));
+    const double Vk = 0.5 * (v(i, j, kk) + v(i, j + 1, kk)) - hzk * (c13 * sV(i, j, kk - 1) + c16 * sV(i, j, kk));
     const double Ritop = -gorho0 * (Rref - Rk) * depth;
     const double dUr = Uref - Uk, dVr = Vref - Vk;
-    const double Ribot = dUr * dUr + dVr * dVr + Vtc * depth * ws * sqrt(fabs(bvf(i, j, k - 1)));
-    FC[k - 1] = Ritop - LMD_RIC * Ribot;
+    const double Ribot = dUr * dUr + dVr * dVr + kc.Vtc * depth * ws * sqrt(fabs(bvf(i, j, kk - 1)));
+    sF(i, j, k) = Ritop - LMD_RIC * Ribot;
   }
-  int ks = 1; hs = z_w(i, j, 1);
-  for (int k = N; k >= 2; --k)
-    if (ks == 1 && FC[k - 1] > 0.0) { hs = (z_w(i, j, k) * FC[k - 1] - z_w(i, j, k - 1) * FC[k]) / (FC[k - 1] - FC[k]); ks = k; }
-  double Bfsfc = (Bo + Bosol * (1.0 - k_swfrac(Jw, zwN - hs)));
+}
+
+__global__ void __launch_bounds__(128) kpp_sbl_kernel(const Dev D, Box bx) {
+  IJ_FROM_BOX(bx);
+  const roms_b200_bounds& b = D.b; const int N = b.N; const size_t vol = D.nij * (size_t)(N + 1);
+  const bool south = b.Southern_Edge && !b.NSperiodic && j == b.Jstr, north = b.Northern_Edge && !b.NSperiodic && j == b.Jend;
+  V3 z_w = v3(D, FID(z_w)), Akv = v3(D, FID(Akv)), Akt1 = v3l(D, FID(Akt), 1), sF = scr3(D, D.kpp4 + 3 * vol);
+  V2 hsbl = v2(D, FID(hsbl));
+  const double eps = 1.0e-10, small = 1.0e-20;
+  const double zwN = z_w(i, j, N);
+  const double Ustar = kpp_ustar(D, i, j), Ustar3 = Ustar * Ustar * Ustar;
+  const KppSurf q = kpp_surf(D, i, j);
+  // first zero crossing of FC from the surface (k = N..2), linear interpolation between the two w-levels
+  int ks = 1; double hs = z_w(i, j, 1);
+  {
+    constexpr int KB = 6;
+    double fup = sF(i, j, N), zup = zwN;
+    for (int k0 = N; k0 >= 2 && ks == 1; k0 -= KB) {
+      double f[KB], z[KB];
+#pragma unroll
+      for (int r = 0; r < KB; ++r) { const int km = max(k0 - r - 1, 1); f[r] = sF(i, j, km); z[r] = z_w(i, j, km); }
+#pragma unroll
+      for (int r = 0; r < KB; ++r) {
+        const int k = k0 - r;
+        if (k >= 2 && ks == 1) {
+          if (f[r] > 0.0) { hs = (zup * f[r] - z[r] * fup) / (f[r] - fup); ks = k; }
+          fup = f[r]; zup = z[r];
+        }
+      }
+    }
+  }
+  double Bfsfc = (q.Bo + q.Bosol * (1.0 - k_swfrac(q.Jw, zwN - hs)));
   if (Ustar > 0.0 && Bfsfc > 0.0) {
     const double hekman = LMD_CEKMAN * Ustar / fmax(fabs(v2(D, FID(f))(i, j)), eps);
     const double hmonob = LMD_CMONOB * Ustar * Ustar * Ustar / fmax(VONKAR * Bfsfc, eps);
@@ -146,9 +219,18 @@ __global__ void __launch_bounds__(128) kpp_kernel(const Dev D, Box bx, int nstp)
   if (south) st(D, hsbl, i, j - 1, hs);
   if (north) st(D, hsbl, i, j + 1, hs);
   ks = 1;
-  for (int k = N; k >= 2; --k) if (ks == 1 && z_w(i, j, k - 1) < hs) ks = k;
-  Bfsfc = (Bo + Bosol * (1.0 - k_swfrac(Jw, zwN - hs)));
-  sl_dpth = LMD_EPSILON * (zwN - hs);
+  {
+    constexpr int KB = 6;
+    for (int k0 = N; k0 >= 2 && ks == 1; k0 -= KB) {
+      double z[KB];
+#pragma unroll
+      for (int r = 0; r < KB; ++r) z[r] = z_w(i, j, max(k0 - r - 1, 1));
+#pragma unroll
+      for (int r = 0; r < KB; ++r) { const int k = k0 - r; if (k >= 2 && ks == 1 && z[r] < hs) ks = k; }
+    }
+  }
+  Bfsfc = (q.Bo + q.Bosol * (1.0 - k_swfrac(q.Jw, zwN - hs)));
+  double wm, ws;
   {
     const double cff = (Bfsfc > 0.0) ? 1.0 : LMD_EPSILON;
     const double sigma = cff * (zwN - hs);
@@ -160,13 +242,17 @@ __global__ void __launch_bounds__(128) kpp_kernel(const Dev D, Box bx, int nstp)
   const double zbl = zwN - hs;
   if (hs > z_w(i, j, 1)) {
     const int k = ks;
-    const double cff = 1.0 / (z_w(i, j, k) - z_w(i, j, k - 1));
-    const double cff_dn = cff * (hs - z_w(i, j, k - 1)), cff_up = cff * (z_w(i, j, k) - hs);
-    double K_bl = cff_dn * akv[k] + cff_up * akv[k - 1], dK_bl = cff * (akv[k] - akv[k - 1]);
+    const double zk = z_w(i, j, k), zkm = z_w(i, j, k - 1);
+    const double akvk = Akv(i, j, k), akvm = Akv(i, j, k - 1), aktk = Akt1(i, j, k), aktm = Akt1(i, j, k - 1);
+    // salinity: interior values equal the temperature ones; at k = N the (untouched) surface value of Akt(:,:,N,isalt)
+    const double aksk = (k == N) ? v3l(D, FID(Akt), 2)(i, j, N) : aktk, aksm = aktm;
+    const double cff = 1.0 / (zk - zkm);
+    const double cff_dn = cff * (hs - zkm), cff_up = cff * (zk - hs);
+    double K_bl = cff_dn * akvk + cff_up * akvm, dK_bl = cff * (akvk - akvm);
     Gm1 = K_bl / (zbl * wm + eps); dGm1dS = fmin(0.0, -dK_bl / (wm + eps) - K_bl * f1);
-    K_bl = cff_dn * akt1[k] + cff_up * akt1[k - 1]; dK_bl = cff * (akt1[k] - akt1[k - 1]);
+    K_bl = cff_dn * aktk + cff_up * aktm; dK_bl = cff * (aktk - aktm);
     Gt1 = K_bl / (zbl * ws + eps); dGt1dS = fmin(0.0, -dK_bl / (ws + eps) - K_bl * f1);
-    K_bl = cff_dn * akt2[k] + cff_up * akt2[k - 1]; dK_bl = cff * (akt2[k] - akt2[k - 1]);
+    K_bl = cff_dn * aksk + cff_up * aksm; dK_bl = cff * (aksk - aksm);
     Gs1 = K_bl / (zbl * ws + eps); dGs1dS = fmin(0.0, -dK_bl / (ws + eps) - K_bl * f1);
   } else {
     ks = 0;
@@ -179,41 +265,67 @@ __global__ void __launch_bounds__(128) kpp_kernel(const Dev D, Box bx, int nstp)
     Gs1 = Gt1; dGs1dS = dGt1dS;
   }
   D.ksbl[(i - b.LBi) + D.ni * (j - b.LBj)] = ks;
-  for (int k = 1; k <= N - 1; ++k) {
+  scr2(D, 0)(i, j) = Gm1; scr2(D, 1)(i, j) = Gt1; scr2(D, 2)(i, j) = Gs1;
+  scr2(D, 3)(i, j) = dGm1dS; scr2(D, 4)(i, j) = dGt1dS; scr2(D, 5)(i, j) = dGs1dS;
+}
+
+__global__ void __launch_bounds__(256) kpp_finish_kernel(const Dev D, Box bx, KppC kc) {
+  IJ_FROM_BOX(bx);
+  const roms_b200_bounds& b = D.b; const int N = b.N, k = blockIdx.z;
+  const bool south = b.Southern_Edge && !b.NSperiodic && j == b.Jstr, north = b.Northern_Edge && !b.NSperiodic && j == b.Jend;
+  V3 z_w = v3(D, FID(z_w)), bvf = v3(D, FID(bvf)), sB = scr3(D, D.swdk);
+  V3 Akv = v3(D, FID(Akv)), Akt1 = v3l(D, FID(Akt), 1), Akt2 = v3l(D, FID(Akt), 2), gh1 = v3l(D, FID(ghats), 1), gh2 = v3l(D, FID(ghats), 2);
+  double akv, akt1, akt2;
+  if (k >= 1 && k <= N - 1) {
+    const int ks = D.ksbl[(i - b.LBi) + D.ni * (j - b.LBj)];
+    double g1, g2;
     if (k > ks) {
+      const double eps = 1.0e-10, small = 1.0e-20;
+      const double zwN = z_w(i, j, N), hs = v2(D, FID(hsbl))(i, j), zbl = zwN - hs, sl_dpth = LMD_EPSILON * (zwN - hs);
+      const double Ustar = kpp_ustar(D, i, j), Ustar3 = Ustar * Ustar * Ustar;
+      const double Gm1 = scr2(D, 0)(i, j), Gt1 = scr2(D, 1)(i, j), Gs1 = scr2(D, 2)(i, j);
+      const double dGm1dS = scr2(D, 3)(i, j), dGt1dS = scr2(D, 4)(i, j), dGs1dS = scr2(D, 5)(i, j);
+      const double Bf = sB(i, j, k);
       const double depth = zwN - z_w(i, j, k);
-      double sigma = (Bflux[k] < 0.0) ? fmin(sl_dpth, depth) : depth;
-      const double zetahat = VONKAR * sigma * Bflux[k], zetapar = zetahat / (Ustar3 + small);
+      double sigma = (Bf < 0.0) ? fmin(sl_dpth, depth) : depth;
+      const double zetahat = VONKAR * sigma * Bf, zetapar = zetahat / (Ustar3 + small);
+      double wm, ws;
       wscale(Ustar, Ustar3, zetahat, zetapar, wm, ws);
       sigma = depth / (zbl + eps);
       const double a1 = sigma - 2.0, a2 = 3.0 - 2.0 * sigma, a3 = sigma - 1.0;
       const double Gm = a1 + a2 * Gm1 + a3 * dGm1dS, Gt = a1 + a2 * Gt1 + a3 * dGt1dS, Gs = a1 + a2 * Gs1 + a3 * dGs1dS;
-      akv[k] = depth * wm * (1.0 + sigma * Gm);
-      akt1[k] = depth * ws * (1.0 + sigma * Gt);
-      akt2[k] = depth * ws * (1.0 + sigma * Gs);
-      const double cff = lmd_Cg * (1.0 - (0.5 + copysign(0.5, Bflux[k]))) / (zbl * ws + eps);
-      g1[k] = cff * g1[k]; g2[k] = cff * g2[k];
-    } else { g1[k] = 0.0; g2[k] = 0.0; }
-  }
-  for (int k = 0; k <= N; ++k) { gh1(i, j, k) = g1[k]; gh2(i, j, k) = g2[k]; }
-  // ---- lmd_finish: convective adjustment + lateral conditions (bc_w3d: gradient + periodic images)
-  for (int k = 1; k <= N - 1; ++k) {
+      akv = depth * wm * (1.0 + sigma * Gm);
+      akt1 = depth * ws * (1.0 + sigma * Gt);
+      akt2 = depth * ws * (1.0 + sigma * Gs);
+      const double cff = kc.lmd_Cg * (1.0 - (0.5 + copysign(0.5, Bf))) / (zbl * ws + eps);
+      g1 = cff * gh1(i, j, k); g2 = cff * gh2(i, j, k);
+    } else { akv = Akv(i, j, k); akt1 = Akt1(i, j, k); akt2 = akt1; g1 = 0.0; g2 = 0.0; }
+    gh1(i, j, k) = g1; gh2(i, j, k) = g2;
+    // lmd_finish: convective adjustment
     double cff = fmax(bvf(i, j, k), LMD_BVFCON);
     cff = fmin(1.0, (LMD_BVFCON - cff) / LMD_BVFCON);
     double nu_sxc = 1.0 - cff * cff;
     nu_sxc = nu_sxc * nu_sxc * nu_sxc;
-    akv[k] = akv[k] + LMD_NU0C * nu_sxc; akt1[k] = akt1[k] + LMD_NU0C * nu_sxc; akt2[k] = akt2[k] + LMD_NU0C * nu_sxc;
-  }
-  for (int k = 0; k <= N; ++k) {
-    st(D, Akv, i, j, k, akv[k]); st(D, Akt1, i, j, k, akt1[k]); st(D, Akt2, i, j, k, akt2[k]);
-    if (south) { st(D, Akv, i, j - 1, k, akv[k]); st(D, Akt1, i, j - 1, k, akt1[k]); st(D, Akt2, i, j - 1, k, akt2[k]); }
-    if (north) { st(D, Akv, i, j + 1, k, akv[k]); st(D, Akt1, i, j + 1, k, akt1[k]); st(D, Akt2, i, j + 1, k, akt2[k]); }
-  }
+    akv = akv + LMD_NU0C * nu_sxc; akt1 = akt1 + LMD_NU0C * nu_sxc; akt2 = akt2 + LMD_NU0C * nu_sxc;
+  } else { akv = Akv(i, j, k); akt1 = Akt1(i, j, k); akt2 = Akt2(i, j, k); }
+  // lateral conditions (bc_w3d: gradient + periodic images)
+  st(D, Akv, i, j, k, akv); st(D, Akt1, i, j, k, akt1); st(D, Akt2, i, j, k, akt2);
+  if (south) { st(D, Akv, i, j - 1, k, akv); st(D, Akt1, i, j - 1, k, akt1); st(D, Akt2, i, j - 1, k, akt2); }
+  if (north) { st(D, Akv, i, j + 1, k, akv); st(D, Akt1, i, j + 1, k, akt1); st(D, Akt2, i, j + 1, k, akt2); }
 }
 int k_lmd_vmix(roms_b200_ctx* c, int nstp) {
   const roms_b200_bounds& b = c->D.b;
-  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 4);
-  kpp_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx, nstp); c->launches++;
+  if (!c->D.kpp4 || !c->D.swdk) { fprintf(stderr, "roms_b200: lmd_vmix needs the BENCHMARK option set (KPP scratch not allocated)\n"); return 1; }
+  if (b.N < 3) return 1;
+  static const KppC kc = {LMD_CSTAR * VONKAR * pow(LMD_CS * VONKAR * LMD_EPSILON, 1.0 / 3.0),
+                          LMD_CV * sqrt(-LMD_BETAT) / (sqrt(LMD_CS * LMD_EPSILON) * LMD_RIC * VONKAR * VONKAR)};
+  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend};
+  dim3 blkc(32, 4), blkl(64, 4);
+  dim3 gc = grid2(bx, blkc), gl = grid2(bx, blkl); gl.z = b.N + 1;
+  kpp_spline_kernel<<<gc, blkc, 0, c->stream>>>(c->D, bx, nstp); c->launches++;
+  kpp_levels_kernel<<<gl, blkl, 0, c->stream>>>(c->D, bx, nstp, kc); c->launches++;
+  kpp_sbl_kernel<<<gc, blkc, 0, c->stream>>>(c->D, bx); c->launches++;
+  kpp_finish_kernel<<<gl, blkl, 0, c->stream>>>(c->D, bx, kc); c->launches++;
   return 0;
 }
 

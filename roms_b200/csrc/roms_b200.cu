@@ -85,6 +85,10 @@ int roms_b200_create(const roms_b200_bounds* b, const roms_b200_params* p, int d
   D.w1 = v; D.w2 = v + (2 * p->ndtfast + 4);
   if (dev_alloc(&D.P, D.nij * b->N)) return 4;
   if (dev_alloc(&D.scratch2, D.nij * 8)) return 4;
+  if (p->app == ROMS_B200_APP_BENCHMARK) {          // KPP scratch (k_kpp.cu): Bflux and {dR, dU, dV, FC}, (ni,nj,0:N) each
+    if (dev_alloc(&D.swdk, D.nij * (size_t)(b->N + 1))) return 4;
+    if (dev_alloc(&D.kpp4, D.nij * (size_t)(b->N + 1) * 4)) return 4;
+  }
   // diag (k_grid.cu): 3 sums per interior column i + 9 maxima + 9 per block of 128 columns of a row
   const size_t nred = (size_t)3 * D.ni + 16 + 12 * 64 + (size_t)9 * ((D.ni + 127) / 128) * D.nj;   // + one 12-double slot per tile (<= 64)
   if (dev_alloc(&D.red, nred)) return 4;
@@ -104,7 +108,7 @@ int roms_b200_destroy(roms_b200_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (int a = 0; a < 12; ++a) if (c->graph2d[a]) cudaGraphExecDestroy(c->graph2d[a]);
   for (int f = 0; f < ROMS_B200_NFIELDS; ++f) cudaFree(c->D.f[f]);
-  cudaFree((void*)c->D.sc_r); cudaFree((void*)c->D.w1); cudaFree(c->D.P); cudaFree(c->D.scratch2); cudaFree(c->D.red); cudaFree(c->D.ksbl); cudaFree(c->D.err);
+  cudaFree((void*)c->D.sc_r); cudaFree((void*)c->D.w1); cudaFree(c->D.P); cudaFree(c->D.scratch2); cudaFree(c->D.swdk); cudaFree(c->D.kpp4); cudaFree(c->D.red); cudaFree(c->D.ksbl); cudaFree(c->D.err);
   cudaFreeHost(c->h_red);
   roms_b200_comm_destroy(c);
   cudaStreamDestroy(c->stream); cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
@@ -181,7 +185,7 @@ int roms_b200_set_depth(roms_b200_ctx* c) { ENTER(c); k_set_depth(c); LEAVE(); }
 int roms_b200_bulk_flux(roms_b200_ctx* c, int nrhs) { ENTER(c); k_bulk_flux(c, nrhs); LEAVE(); }
 int roms_b200_set_vbc(roms_b200_ctx* c, int nrhs) { ENTER(c); k_set_vbc(c, nrhs); LEAVE(); }
 int roms_b200_ana_vmix(roms_b200_ctx* c) { ENTER(c); k_ana_vmix(c); LEAVE(); }
-int roms_b200_lmd_vmix(roms_b200_ctx* c, int nstp) { ENTER(c); k_lmd_vmix(c, nstp); LEAVE(); }
+int roms_b200_lmd_vmix(roms_b200_ctx* c, int nstp) { ENTER(c); if (k_lmd_vmix(c, nstp)) return 1; LEAVE(); }
 int roms_b200_pre_step3d(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntfirst) { ENTER(c); k_pre_step3d(c, nrhs, nstp, nnew, iic, ntfirst); LEAVE(); }
 int roms_b200_prsgrd(roms_b200_ctx* c, int nrhs) { ENTER(c); k_prsgrd(c, nrhs); LEAVE(); }
 int roms_b200_t3dmix2(roms_b200_ctx* c, int nrhs, int nstp, int nnew) { ENTER(c); k_t3dmix2(c, nrhs, nstp, nnew); LEAVE(); }
@@ -329,7 +333,7 @@ int roms_b200_main3d(roms_b200_ctx* c, int nsteps, int analytic_forcing, int wit
     if (bench) k_bulk_flux(c, nrhs);
     k_set_vbc(c, nrhs);
     { const XF x[4] = {xf2(FID(sustr)), xf2(FID(svstr)), xf2(FID(bustr)), xf2(FID(bvstr))}; if (xchg(c, x, 4)) return 1; }
-    if (bench) { k_lmd_vmix(c, nstp); const XF x[1] = {xf3(c, FID(Akv))}; if (xchg(c, x, 1)) return 1; } else k_ana_vmix(c);
+    if (bench) { if (k_lmd_vmix(c, nstp)) return 1; const XF x[1] = {xf3(c, FID(Akv))}; if (xchg(c, x, 1)) return 1; } else k_ana_vmix(c);
     k_omega(c);
     if (k_wvelocity(c, nstp)) return 1;                                    // main3d.F:535
     k_set_zeta(c);
