@@ -61,13 +61,26 @@ __global__ void omega_kernel(const Dev D, Box bx) {
   const int N = D.b.N; const roms_b200_bounds& b = D.b;
   V3 W = v3(D, FID(W)), Huon = v3(D, FID(Huon)), Hvom = v3(D, FID(Hvom)), z_w = v3(D, FID(z_w));
   const bool south = b.Southern_Edge && j == b.Jstr, north = b.Northern_Edge && j == b.Jend;
-  double w[RB_MAXN + 1];
+  double w[RB_MAXN + 1], zw[RB_MAXN + 1];
   w[0] = 0.0;
-  for (int k = 1; k <= N; ++k)
-    w[k] = w[k - 1] - (Huon(i + 1, j, k) - Huon(i, j, k) + Hvom(i, j + 1, k) - Hvom(i, j, k));
   const double zw0 = z_w(i, j, 0);
-  const double wrk = w[N] / (z_w(i, j, N) - zw0);
-  for (int k = N - 1; k >= 1; --k) w[k] = w[k] - wrk * (z_w(i, j, k) - zw0);
+  constexpr int KB = 6;                          // levels per load batch (the column sum itself stays sequential)
+  double wk = 0.0;
+  for (int k0 = 1; k0 <= N; k0 += KB) {
+    double ue[KB], uw[KB], vn[KB], vs[KB], z[KB];
+#pragma unroll
+    for (int q = 0; q < KB; ++q) {
+      const int k = min(k0 + q, N);
+      ue[q] = Huon(i + 1, j, k); uw[q] = Huon(i, j, k); vn[q] = Hvom(i, j + 1, k); vs[q] = Hvom(i, j, k); z[q] = z_w(i, j, k);
+    }
+#pragma unroll
+    for (int q = 0; q < KB; ++q) {
+      const int k = k0 + q;
+      if (k <= N) { wk = wk - (ue[q] - uw[q] + vn[q] - vs[q]); w[k] = wk; zw[k] = z[q]; }
+    }
+  }
+  const double wrk = w[N] / (zw[N] - zw0);
+  for (int k = N - 1; k >= 1; --k) w[k] = w[k] - wrk * (zw[k] - zw0);
   w[N] = 0.0;
   for (int k = 0; k <= N; ++k) {
     st(D, W, i, j, k, w[k]);
@@ -92,35 +105,50 @@ __global__ void wvelocity_kernel(const Dev D, Box bx, int ninp) {
   V2 pm = v2(D, FID(pm)), pn = v2(D, FID(pn)), DU = v2(D, FID(DU_avg1)), DV = v2(D, FID(DV_avg1));
   const bool south = b.Southern_Edge && j == b.Jstr, north = b.Northern_Edge && j == b.Jend;
   const double pmW = pm(i - 1, j) + pm(i, j), pmE = pm(i, j) + pm(i + 1, j), pnS = pn(i, j - 1) + pn(i, j), pnN = pn(i, j) + pn(i, j + 1);
-  double vert[RB_MAXN + 1];
-  for (int k = 1; k <= N; ++k) {
-    const double zc = z_r(i, j, k);
-    const double wW = u(i, j, k) * (zc - z_r(i - 1, j, k)) * pmW, wE = u(i + 1, j, k) * (z_r(i + 1, j, k) - zc) * pmE;
-    const double wS = v(i, j, k) * (zc - z_r(i, j - 1, k)) * pnS, wN = v(i, j + 1, k) * (z_r(i, j + 1, k) - zc) * pnN;
-    double vt = 0.25 * (wW + wE);
-    vt = vt + 0.25 * (wS + wN);
-    vert[k] = vt;
+  double vert[RB_MAXN + 1], zwv[RB_MAXN + 1], Wv[RB_MAXN + 1];
+  constexpr int KB = 4;                          // levels per load batch
+  for (int k0 = 1; k0 <= N; k0 += KB) {
+    double zc[KB], zW[KB], zE[KB], zS[KB], zN[KB], uW[KB], uE[KB], vS[KB], vN[KB], zz[KB], ww[KB];
+#pragma unroll
+    for (int q = 0; q < KB; ++q) {
+      const int k = min(k0 + q, N);
+      zc[q] = z_r(i, j, k); zW[q] = z_r(i - 1, j, k); zE[q] = z_r(i + 1, j, k); zS[q] = z_r(i, j - 1, k); zN[q] = z_r(i, j + 1, k);
+      uW[q] = u(i, j, k); uE[q] = u(i + 1, j, k); vS[q] = v(i, j, k); vN[q] = v(i, j + 1, k);
+      zz[q] = z_w(i, j, k); ww[q] = W(i, j, k);
+    }
+#pragma unroll
+    for (int q = 0; q < KB; ++q) {
+      const int k = k0 + q;
+      if (k <= N) {
+        const double wW = uW[q] * (zc[q] - zW[q]) * pmW, wE = uE[q] * (zE[q] - zc[q]) * pmE;
+        const double wS = vS[q] * (zc[q] - zS[q]) * pnS, wN = vN[q] * (zN[q] - zc[q]) * pnN;
+        double vt = 0.25 * (wW + wE);
+        vt = vt + 0.25 * (wS + wN);
+        vert[k] = vt; zwv[k] = zz[q]; Wv[k] = ww[q];
+      }
+    }
   }
   const double cff1 = 3.0 / 8.0, cff2 = 3.0 / 4.0, cff3 = 1.0 / 8.0, cff4 = 9.0 / 16.0, cff5 = 1.0 / 16.0;
-  const double zw0 = z_w(i, j, 0), zwN = z_w(i, j, N);
+  const double zw0 = z_w(i, j, 0), zwN = zwv[N];
   const double wrk = (DU(i, j) - DU(i + 1, j) + DV(i, j) - DV(i, j + 1)) / (zwN - zw0);
   const double pmn = pm(i, j) * pn(i, j);
+  const double zr1 = z_r(i, j, 1), zr2 = z_r(i, j, 2), zrN = z_r(i, j, N), zrNm = z_r(i, j, N - 1);
   auto put = [&](int k, double val) {
     st(D, wvel, i, j, k, val);
     if (south) st(D, wvel, i, j - 1, k, val);
     if (north) st(D, wvel, i, j + 1, k, val);
   };
   {
-    const double slope = (z_r(i, j, 1) - zw0) / (z_r(i, j, 2) - z_r(i, j, 1));
+    const double slope = (zr1 - zw0) / (zr2 - zr1);
     put(0, cff1 * (vert[1] - slope * (vert[2] - vert[1])) + cff2 * vert[1] - cff3 * vert[2]);
-    put(1, pmn * (W(i, j, 1) + wrk * (z_w(i, j, 1) - zw0)) + cff1 * vert[1] + cff2 * vert[2] - cff3 * vert[3]);
+    put(1, pmn * (Wv[1] + wrk * (zwv[1] - zw0)) + cff1 * vert[1] + cff2 * vert[2] - cff3 * vert[3]);
   }
   for (int k = 2; k <= N - 2; ++k)
-    put(k, pmn * (W(i, j, k) + wrk * (z_w(i, j, k) - zw0)) + cff4 * (vert[k] + vert[k + 1]) - cff5 * (vert[k - 1] + vert[k + 2]));
+    put(k, pmn * (Wv[k] + wrk * (zwv[k] - zw0)) + cff4 * (vert[k] + vert[k + 1]) - cff5 * (vert[k - 1] + vert[k + 2]));
   {
-    const double slope = (zwN - z_r(i, j, N)) / (z_r(i, j, N) - z_r(i, j, N - 1));
+    const double slope = (zwN - zrN) / (zrN - zrNm);
     put(N, pmn * wrk * (zwN - zw0) + cff1 * (vert[N] + slope * (vert[N] - vert[N - 1])) + cff2 * vert[N] - cff3 * vert[N - 1]);
-    put(N - 1, pmn * (W(i, j, N - 1) + wrk * (z_w(i, j, N - 1) - zw0)) + cff1 * vert[N] + cff2 * vert[N - 1] - cff3 * vert[N - 2]);
+    put(N - 1, pmn * (Wv[N - 1] + wrk * (zwv[N - 1] - zw0)) + cff1 * vert[N] + cff2 * vert[N - 1] - cff3 * vert[N - 2]);
   }
 }
 // Interior columns of the tile only (plus E-W periodic images and closed-wall rows): wvel is read by diag on the interior and
@@ -198,10 +226,11 @@ __global__ void rho_eos_kernel(const Dev D, Box bx, int nrhs) {
   V3 Hz = v3(D, FID(Hz)), z_r = v3(D, FID(z_r)), z_w = v3(D, FID(z_w)), rho = v3(D, FID(rho)), pden = v3(D, FID(pden));
   V3 T = v3l(D, FID(t), nrhs, 1), S = v3l(D, FID(t), nrhs, 2);
   V2 rhoA = v2(D, FID(rhoA)), rhoS = v2(D, FID(rhoS));
-  double den[RB_MAXN + 1];
+  double den[RB_MAXN + 1], hzv[RB_MAXN + 1];
   if (D.p.app == ROMS_B200_APP_UPWELLING) {
     const double R0 = D.p.R0;
     for (int k = 1; k <= N; ++k) {
+      hzv[k] = Hz(i, j, k);
       double r = R0 - R0 * D.p.Tcoef * (T(i, j, k) - D.p.T0);
       r = r + R0 * D.p.Scoef * (S(i, j, k) - D.p.S0);
       r = r - 1000.0;
@@ -210,10 +239,18 @@ __global__ void rho_eos_kernel(const Dev D, Box bx, int nrhs) {
     }
   } else {
     V3 bvf = v3(D, FID(bvf)); V2 alpha = v2(D, FID(alpha)), beta = v2(D, FID(beta));
-    double p_den1 = 0, p_b0 = 0, p_b1 = 0, p_b2 = 0;   // level k-1
-    for (int k = 1; k <= N; ++k) {
-      const double Tt = fmax(-2.0, T(i, j, k)), Ts = fmax(0.0, S(i, j, k));
-      const double sqrtTs = sqrt(Ts), Tp = z_r(i, j, k), Tpr10 = 0.1 * Tp;
+    double p_den1 = 0, p_b0 = 0, p_b1 = 0, p_b2 = 0, p_zr = 0;   // level k-1
+    constexpr int KB = 5;                      // levels per load batch; the polynomial evaluations of a batch are independent
+    for (int k0 = 1; k0 <= N; k0 += KB) {
+    double bT[KB], bS[KB], bZr[KB], bZw[KB];
+#pragma unroll
+    for (int q = 0; q < KB; ++q) { const int k = min(k0 + q, N); bT[q] = T(i, j, k); bS[q] = S(i, j, k); bZr[q] = z_r(i, j, k); bZw[q] = z_w(i, j, k - 1); hzv[k] = Hz(i, j, k); }
+#pragma unroll
+    for (int q = 0; q < KB; ++q) {
+      const int k = k0 + q;
+      if (k > N) break;
+      const double Tt = fmax(-2.0, bT[q]), Ts = fmax(0.0, bS[q]);
+      const double sqrtTs = sqrt(Ts), Tp = bZr[q], Tpr10 = 0.1 * Tp;
       const double C0 = Q00 + Tt * (Q01 + Tt * (Q02 + Tt * (Q03 + Tt * (Q04 + Tt * Q05))));
       const double C1 = U00 + Tt * (U01 + Tt * (U02 + Tt * (U03 + Tt * U04)));
       const double C2 = V00 + Tt * (V01 + Tt * V02);
@@ -235,14 +272,14 @@ __global__ void rho_eos_kernel(const Dev D, Box bx, int nrhs) {
       den[k] = dn;
       st(D, rho, i, j, k, dn); st(D, pden, i, j, k, (den1 - 1000.0));
       if (k > 1) {                     // bvf at interface k-1 (rho_eos.F:402-424)
-        const double zw = z_w(i, j, k - 1);
+        const double zw = bZw[q];
         const double bulk_up = bulk0 - zw * (bulk1 - bulk2 * zw);
         const double bulk_dn = p_b0 - zw * (p_b1 - p_b2 * zw);
         const double cff1 = 1.0 / (bulk_up + 0.1 * zw), cff2 = 1.0 / (bulk_dn + 0.1 * zw);
         const double den_up = cff1 * (den1 * bulk_up), den_dn = cff2 * (p_den1 * bulk_dn);
-        st(D, bvf, i, j, k - 1, -g * (den_up - den_dn) / (0.5 * (den_up + den_dn) * (z_r(i, j, k) - z_r(i, j, k - 1))));
+        st(D, bvf, i, j, k - 1, -g * (den_up - den_dn) / (0.5 * (den_up + den_dn) * (Tp - p_zr)));
       }
-      p_den1 = den1; p_b0 = bulk0; p_b1 = bulk1; p_b2 = bulk2;
+      p_den1 = den1; p_b0 = bulk0; p_b1 = bulk1; p_b2 = bulk2; p_zr = Tp;
       if (k == N) {                    // thermal expansion / saline contraction at the surface (:426-470)
         const double dC0 = Q01 + Tt * (2.0 * Q02 + Tt * (3.0 * Q03 + Tt * (4.0 * Q04 + Tt * 5.0 * Q05)));
         const double dC1 = U01 + Tt * (2.0 * U02 + Tt * (3.0 * U03 + Tt * 4.0 * U04));
@@ -266,13 +303,14 @@ __global__ void rho_eos_kernel(const Dev D, Box bx, int nrhs) {
         st(D, alpha, i, j, ci * Tcof); st(D, beta, i, j, ci * Scof);
       }
     }
+    }
     st(D, bvf, i, j, 0, 0.0); st(D, bvf, i, j, N, 0.0);
   }
   // vertical averages for the barotropic pressure gradient (rho_eos.F:370-387 / :702-718)
-  double cff1 = den[N] * Hz(i, j, N);
-  double rS = 0.5 * cff1 * Hz(i, j, N), rA = cff1;
+  double cff1 = den[N] * hzv[N];
+  double rS = 0.5 * cff1 * hzv[N], rA = cff1;
   for (int k = N - 1; k >= 1; --k) {
-    const double hz = Hz(i, j, k);
+    const double hz = hzv[k];
     cff1 = den[k] * hz;
     rS = rS + hz * (rA + 0.5 * cff1);
     rA = rA + cff1;

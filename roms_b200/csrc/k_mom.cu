@@ -268,63 +268,91 @@ int k_uv3dmix2(roms_b200_ctx* c, int nrhs, int nnew) {
 }
 
 // ---- step3d_uv_tile, step3d_uv.F:330-1824 -------------------------------------------------
+// One thread per (u or v) water column.  The column arrays live in shared memory ([level][thread], conflict-free) instead
+// of thread-local memory (14 warps x 2.6 KB per SM thrashed the L1), global loads are issued in batches of UV_KB levels
+// ahead of the recurrences that consume them, and the per-level reciprocals are the branch-free rcp_ieee (== 1.0/x) so
+// that independent levels overlap.  Per-point operation order is the reference's.  (134 -> 77 us on BENCHMARK1.)
+constexpr int UV_T = 64;      // threads per block (32 x 2)
+constexpr int UV_KB = 6;      // levels per load batch
 // pass 1 (interior u/v points): add ru, implicit spline vertical viscosity, replace the
 // vertical mean by DU_avg1 (:357-715, :859-1182), then the closed-wall u3dbc/v3dbc rows.
-__global__ void __launch_bounds__(128) step3d_uv1_kernel(const Dev D, Box bx, int nrhs, int nnew, double cffab) {
-  IJ_FROM_BOX(bx);
+__global__ void __launch_bounds__(UV_T) step3d_uv1_kernel(const Dev D, Box bx, int nrhs, int nnew, double cffab) {
+  extern __shared__ double uvsm[];
+  const int i = bx.i0 + blockIdx.x * blockDim.x + threadIdx.x, j = bx.j0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > bx.i1 || j > bx.j1) return;
   const roms_b200_bounds& b = D.b; const int N = b.N; const double dt = D.p.dt;
   V3 Hz = v3(D, FID(Hz)), Akv = v3(D, FID(Akv)); V2 pm = v2(D, FID(pm)), pn = v2(D, FID(pn));
   const bool S = b.Southern_Edge && !b.NSperiodic, Nn = b.Northern_Edge && !b.NSperiodic;
-  double q[RB_MAXN + 2], Hzk[RB_MAXN + 2], oHz[RB_MAXN + 2], CF[RB_MAXN + 1], DC[RB_MAXN + 1];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, L = (N + 2) * UV_T;
+  double *q = uvsm + tid, *Hzk = q + L, *oHz = Hzk + L, *CF = oHz + L, *DC = CF + L, *ak = DC + L;   // element k at [k * UV_T]
   const int comp = blockIdx.z;              // u and v columns on separate threads
+  int bad = 0;
   if ((comp == 0 && (i >= b.IstrU && i <= b.Iend && j >= b.Jstr && j <= b.Jend)) ||
       (comp == 1 && (i >= b.Istr && i <= b.Iend && j >= b.JstrV && j <= b.Jend))) {
     const int di = comp == 0 ? 1 : 0, dj = 1 - di;
     V3 qn = v3l(D, comp == 0 ? FID(u) : FID(v), nnew), r = v3l(D, comp == 0 ? FID(ru) : FID(rv), nrhs);
     const double DC0 = cffab * (pm(i, j) + pm(i - di, j - dj)) * (pn(i, j) + pn(i - di, j - dj));
-    for (int k = 1; k <= N; ++k) {
-      Hzk[k] = 0.5 * (Hz(i - di, j - dj, k) + Hz(i, j, k));
-      oHz[k] = 1.0 / Hzk[k];
-      double val = qn(i, j, k) + DC0 * r(i, j, k);
-      q[k] = val * oHz[k];
-    }
-    // spline tridiagonal (step3d_uv.F:392-438)
-    CF[0] = 0.0; DC[0] = 0.0;
-    {
-      double ak_km = 0.5 * (Akv(i - di, j - dj, 0) + Akv(i, j, 0)), ak_k = 0.5 * (Akv(i - di, j - dj, 1) + Akv(i, j, 1));
-      for (int k = 1; k <= N - 1; ++k) {
-        const double ak_kp = 0.5 * (Akv(i - di, j - dj, k + 1) + Akv(i, j, k + 1));
-        const double FC = (1.0 / 6.0) * Hzk[k] - dt * ak_km * oHz[k];
-        const double CFk = (1.0 / 6.0) * Hzk[k + 1] - dt * ak_kp * oHz[k + 1];
-        const double BC = (1.0 / 3.0) * (Hzk[k] + Hzk[k + 1]) + dt * ak_k * (oHz[k] + oHz[k + 1]);
-        const double cf = 1.0 / (BC - FC * CF[k - 1]);
-        CF[k] = cf * CFk;
-        DC[k] = cf * (q[k + 1] - q[k] - FC * DC[k - 1]);
-        ak_km = ak_k; ak_k = ak_kp;
+    ak[0] = 0.5 * (Akv(i - di, j - dj, 0) + Akv(i, j, 0));
+    for (int k0 = 1; k0 <= N; k0 += UV_KB) {
+      double ha[UV_KB], hb[UV_KB], qv[UV_KB], rv[UV_KB], aa[UV_KB], ab[UV_KB];
+#pragma unroll
+      for (int t = 0; t < UV_KB; ++t) {
+        const int k = min(k0 + t, N);
+        ha[t] = Hz(i - di, j - dj, k); hb[t] = Hz(i, j, k); qv[t] = qn(i, j, k); rv[t] = r(i, j, k);
+        aa[t] = Akv(i - di, j - dj, k); ab[t] = Akv(i, j, k);
+      }
+#pragma unroll
+      for (int t = 0; t < UV_KB; ++t) {
+        const int k = k0 + t;
+        if (k <= N) {
+          const double hz = 0.5 * (ha[t] + hb[t]), oh = rcp_ieee(hz, bad);
+          Hzk[k * UV_T] = hz; oHz[k * UV_T] = oh;
+          const double val = qv[t] + DC0 * rv[t];
+          q[k * UV_T] = val * oh;
+          ak[k * UV_T] = 0.5 * (aa[t] + ab[t]);
+        }
       }
     }
-    DC[N] = 0.0;
-    for (int k = N - 1; k >= 1; --k) DC[k] = DC[k] - CF[k] * DC[k + 1];
+    // spline tridiagonal (step3d_uv.F:392-438)
+    {
+      double cfp = 0.0, dcp = 0.0;
+      double hz_k = Hzk[UV_T], oh_k = oHz[UV_T], q_k = q[UV_T], ak_km = ak[0], ak_k = ak[UV_T];
+#pragma unroll 2
+      for (int k = 1; k <= N - 1; ++k) {
+        const double hz_p = Hzk[(k + 1) * UV_T], oh_p = oHz[(k + 1) * UV_T], q_p = q[(k + 1) * UV_T], ak_kp = ak[(k + 1) * UV_T];
+        const double FC = (1.0 / 6.0) * hz_k - dt * ak_km * oh_k;
+        const double CFk = (1.0 / 6.0) * hz_p - dt * ak_kp * oh_p;
+        const double BC = (1.0 / 3.0) * (hz_k + hz_p) + dt * ak_k * (oh_k + oh_p);
+        const double cf = rcp_ieee(BC - FC * cfp, bad);
+        cfp = cf * CFk;
+        dcp = cf * (q_p - q_k - FC * dcp);
+        CF[k * UV_T] = cfp; DC[k * UV_T] = dcp;
+        hz_k = hz_p; oh_k = oh_p; q_k = q_p; ak_km = ak_k; ak_k = ak_kp;
+      }
+    }
+    {
+      double dn = 0.0;                                   // DC(N) = 0
+      DC[N * UV_T] = 0.0;
+      for (int k = N - 1; k >= 1; --k) { dn = DC[k * UV_T] - CF[k * UV_T] * dn; DC[k * UV_T] = dn; }
+    }
     double dcm = 0.0;
     for (int k = 1; k <= N; ++k) {
-      const double ak = 0.5 * (Akv(i - di, j - dj, k) + Akv(i, j, k));
-      const double dck = DC[k] * ak;
-      q[k] = q[k] + dt * oHz[k] * (dck - dcm);
+      const double dck = DC[k * UV_T] * ak[k * UV_T];
+      q[k * UV_T] = q[k * UV_T] + dt * oHz[k * UV_T] * (dck - dcm);
       dcm = dck;
     }
     // vertical mean -> barotropic (step3d_uv.F:597-715)
-    double CF0 = Hzk[1], DCs = q[1] * Hzk[1];
-    for (int k = 2; k <= N; ++k) { CF0 = CF0 + Hzk[k]; DCs = DCs + q[k] * Hzk[k]; }
+    double CF0 = Hzk[UV_T], DCs = q[UV_T] * Hzk[UV_T];
+    for (int k = 2; k <= N; ++k) { const double hz = Hzk[k * UV_T]; CF0 = CF0 + hz; DCs = DCs + q[k * UV_T] * hz; }
     const double met = v2(D, comp == 0 ? FID(on_u) : FID(om_v))(i, j), Davg = v2(D, comp == 0 ? FID(DU_avg1) : FID(DV_avg1))(i, j);
     const double c1 = 1.0 / (CF0 * met);
     const double corr = (DCs * met - Davg) * c1;
+    const bool sw = comp == 0 && S && j == b.Jstr, nw = comp == 0 && Nn && j == b.Jend;
     for (int k = 1; k <= N; ++k) {
-      const double val = q[k] - corr;
+      const double val = q[k * UV_T] - corr;
       qn(i, j, k) = val;
-      if (comp == 0) {                      // u3dbc_im.F:329-343,415-429 (gamma2 slip)
-        if (S && j == b.Jstr) qn(i, j - 1, k) = D.p.gamma2 * val;
-        if (Nn && j == b.Jend) qn(i, j + 1, k) = D.p.gamma2 * val;
-      }
+      if (sw) qn(i, j - 1, k) = D.p.gamma2 * val;         // u3dbc_im.F:329-343,415-429 (gamma2 slip)
+      if (nw) qn(i, j + 1, k) = D.p.gamma2 * val;
     }
   }
   // v3dbc_im.F:171-178,250-257: zero normal flow at the closed walls
@@ -333,13 +361,17 @@ __global__ void __launch_bounds__(128) step3d_uv1_kernel(const Dev D, Box bx, in
     if (S && j == b.Jstr) for (int k = 1; k <= N; ++k) vn(i, b.Jstr, k) = 0.0;
     if (Nn && j == b.Jend) for (int k = 1; k <= N; ++k) vn(i, b.Jend + 1, k) = 0.0;
   }
+  if (bad) atomicOr(D.err, 1);
 }
 // pass 2: 2D/3D coupling on JstrT..JendT rows: ubar,vbar(1:2), time-centred Huon/Hvom (:1312-1756)
-__global__ void __launch_bounds__(128) step3d_uv2_kernel(const Dev D, Box bx, int nnew) {
-  IJ_FROM_BOX(bx);
+__global__ void __launch_bounds__(UV_T) step3d_uv2_kernel(const Dev D, Box bx, int nnew) {
+  extern __shared__ double uvsm[];
+  const int i = bx.i0 + blockIdx.x * blockDim.x + threadIdx.x, j = bx.j0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > bx.i1 || j > bx.j1) return;
   const roms_b200_bounds& b = D.b; const int N = b.N;
   V3 Hz = v3(D, FID(Hz));
-  double DC[RB_MAXN + 1], qk[RB_MAXN + 1], hq[RB_MAXN + 1];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, L = (N + 2) * UV_T;
+  double *DC = uvsm + tid, *qk = DC + L, *hq = qk + L;     // element k at [k * UV_T]
   const int comp = blockIdx.z;
   if ((comp == 0 && (i >= b.IstrP && i <= b.IendT && j >= b.JstrT && j <= b.JendT)) ||
       (comp == 1 && (i >= b.IstrT && i <= b.IendT && j >= b.Jstr && j <= b.JendT))) {
@@ -348,12 +380,24 @@ __global__ void __launch_bounds__(128) step3d_uv2_kernel(const Dev D, Box bx, in
     const double met = v2(D, comp == 0 ? FID(on_u) : FID(om_v))(i, j);
     const double Davg1 = v2(D, comp == 0 ? FID(DU_avg1) : FID(DV_avg1))(i, j), Davg2 = v2(D, comp == 0 ? FID(DU_avg2) : FID(DV_avg2))(i, j);
     double DC0 = 0.0, CF0 = 0.0, FC0 = 0.0;
-    for (int k = 1; k <= N; ++k) {
-      const double cff = 0.5 * met;
-      DC[k] = cff * (Hz(i, j, k) + Hz(i - di, j - dj, k));
-      qk[k] = qn(i, j, k);
-      DC0 = DC0 + DC[k];
-      CF0 = CF0 + DC[k] * qk[k];
+    const double cff = 0.5 * met;
+    for (int k0 = 1; k0 <= N; k0 += UV_KB) {
+      double ha[UV_KB], hb[UV_KB], qv[UV_KB], hv[UV_KB];
+#pragma unroll
+      for (int t = 0; t < UV_KB; ++t) {
+        const int k = min(k0 + t, N);
+        ha[t] = Hz(i, j, k); hb[t] = Hz(i - di, j - dj, k); qv[t] = qn(i, j, k); hv[t] = Hq(i, j, k);
+      }
+#pragma unroll
+      for (int t = 0; t < UV_KB; ++t) {
+        const int k = k0 + t;
+        if (k <= N) {
+          const double dc = cff * (ha[t] + hb[t]);
+          DC[k * UV_T] = dc; qk[k * UV_T] = qv[t]; hq[k * UV_T] = hv[t];     // hq holds Huon/Hvom(k) until the next sweep
+          DC0 = DC0 + dc;
+          CF0 = CF0 + dc * qv[t];
+        }
+      }
     }
     DC0 = 1.0 / DC0;
     CF0 = DC0 * (CF0 - Davg1);
@@ -366,15 +410,16 @@ __global__ void __launch_bounds__(128) step3d_uv2_kernel(const Dev D, Box bx, in
       if (comp == 0 && (j == 0 || j == b.Mm + 1) && i >= b.IstrU && i <= b.Iend) fix = true;
       if (comp == 1 && (j == 1 || j == b.Mm + 1) && i >= b.Istr && i <= b.Iend) fix = true;
     }
-    if (fix) for (int k = 1; k <= N; ++k) qk[k] = qk[k] - CF0;
+    if (fix) for (int k = 1; k <= N; ++k) qk[k * UV_T] = qk[k * UV_T] - CF0;
     for (int k = N; k >= 1; --k) {
-      hq[k] = 0.5 * (Hq(i, j, k) + qk[k] * DC[k]);
-      FC0 = FC0 + hq[k];
+      const double h = 0.5 * (hq[k * UV_T] + qk[k * UV_T] * DC[k * UV_T]);
+      hq[k * UV_T] = h;
+      FC0 = FC0 + h;
     }
     FC0 = DC0 * (FC0 - Davg2);
     for (int k = 1; k <= N; ++k) {
-      st(D, Hq, i, j, k, hq[k] - DC[k] * FC0);
-      st(D, qn, i, j, k, qk[k]);
+      st(D, Hq, i, j, k, hq[k * UV_T] - DC[k * UV_T] * FC0);
+      st(D, qn, i, j, k, qk[k * UV_T]);
     }
   }
 }
@@ -383,11 +428,15 @@ int k_step3d_uv(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntf
   const roms_b200_bounds& b = c->D.b; const double dt = c->D.p.dt;
   double cffab;
   if (iic == ntfirst) cffab = 0.25 * dt; else if (iic == ntfirst + 1) cffab = 0.25 * dt * 3.0 / 2.0; else cffab = 0.25 * dt * 23.0 / 12.0;
-  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 4);
+  const size_t sm1 = (size_t)6 * (b.N + 2) * UV_T * sizeof(double), sm2 = (size_t)3 * (b.N + 2) * UV_T * sizeof(double);
+  static size_t set1 = 0, set2 = 0;
+  if (sm1 > set1) { CUDA_OK(cudaFuncSetAttribute(step3d_uv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)); set1 = sm1; }
+  if (sm2 > set2) { CUDA_OK(cudaFuncSetAttribute(step3d_uv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2)); set2 = sm2; }
+  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, UV_T / 32);
   dim3 g1 = grid2(bx, blk); g1.z = 2;
-  step3d_uv1_kernel<<<g1, blk, 0, c->stream>>>(c->D, bx, nrhs, nnew, cffab); c->launches++;
+  step3d_uv1_kernel<<<g1, blk, sm1, c->stream>>>(c->D, bx, nrhs, nnew, cffab); c->launches++;
   Box b2{b.IstrT, b.IendT, b.JstrT, b.JendT};
   dim3 g2 = grid2(b2, blk); g2.z = 2;
-  step3d_uv2_kernel<<<g2, blk, 0, c->stream>>>(c->D, b2, nnew); c->launches++;
+  step3d_uv2_kernel<<<g2, blk, sm2, c->stream>>>(c->D, b2, nnew); c->launches++;
   return 0;
 }
