@@ -47,12 +47,14 @@ def main():
     d.ctx._bounds = b
     N = cfg.N
     fields = [("zeta", 1, 1, 1), ("zeta", 2, 1, 1), ("u", 1, 1, N), ("u", 2, 1, N), ("v", 1, 1, N), ("v", 2, 1, N),
-              ("t", 1, 1, N), ("t", 2, 1, N), ("t", 1, 2, N), ("t", 2, 2, N), ("ubar", 1, 1, 1), ("vbar", 1, 1, 1)]
+              ("t", 1, 1, N), ("t", 2, 1, N), ("t", 1, 2, N), ("t", 2, 2, N), ("ubar", 1, 1, 1), ("vbar", 1, 1, 1),
+              ("wvel", 1, 1, N + 1), ("Akv", 1, 1, N + 1), ("W", 1, 1, N + 1)]
     mine = {(n, l, m): d.ctx.download_interior(n, l, m, nk) for n, l, m, nk in fields}
     box = (b.Istr, b.Iend, b.Jstr, b.Jend)
     gathered = [None] * world
     dist.all_gather_object(gathered, (box, mine))
     diag = d.run(1, host_forcing=True)
+    dfull = d.ctx.diag_last()
     ok = True
     if rank == 0:
         one = rb.default_config(a.app, *a.grid)
@@ -70,6 +72,11 @@ def main():
                     worst = max(worst, float(np.max(np.abs(got - exp))))
                     print("MISMATCH", n, l, m, "tile box", (i0, i1, j0, j1), "max abs diff", float(np.max(np.abs(got - exp))), flush=True)
         dg = s.run(1, host_forcing=True)
+        sfull = s.ctx.diag_last()
+        # diag across tiles: sums agree to round-off (mp_reduce order), maxima and the MAXLOC location exactly
+        if not (np.allclose(dfull[:3], sfull[:3], rtol=1e-13, atol=0) and np.array_equal(dfull[3:], sfull[3:])):
+            ok = False
+            print("DIAG MISMATCH multi", dfull, "single", sfull, flush=True)
         print("tiling %dx%d vs 1x1 after %d steps: %s ; diag multi %s single %s" % (a.tiles[0], a.tiles[1], a.steps,
               "BIT-IDENTICAL" if ok else "DIFFERENT (max %.3e)" % worst, diag, dg), flush=True)
         s.finalize()
