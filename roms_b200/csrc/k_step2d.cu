@@ -122,8 +122,10 @@ __global__ void __launch_bounds__(S2_TX * S2_TY * 2) step2d_kernel(const Dev D, 
   __shared__ double tDr[S2_TW * S2_TH], tDU[S2_TW * S2_TH], tDV[S2_TW * S2_TH];
   // Programmatic dependent launch (launch_boxes): let the next sub-step's grid be scheduled now, and do not touch any
   // field before the previous sub-step has completed and flushed.  Both are no-ops for an ordinary launch.
+#ifndef ROMS_B200_EMU
   asm volatile("griddepcontrol.launch_dependents;");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
   const Box bx = bxs.b[blockIdx.z];
   if (bx.i0 + (int)blockIdx.x * S2_TX > bx.i1 || bx.j0 + (int)blockIdx.y * S2_TY > bx.j1) return;   // whole block outside this box
   const int i = bx.i0 + blockIdx.x * S2_TX + threadIdx.x, j = bx.j0 + blockIdx.y * S2_TY + threadIdx.y;

@@ -52,8 +52,10 @@ class Lib:
     """Loaded libroms_b200.so with typed prototypes."""
     _inst = None
 
-    def __init__(self):
-        path = library_path()
+    def __init__(self, path=None):
+        # `path` is for tests/emu only (a host build of the kernel sources used to check arithmetic without a GPU);
+        # the product always loads libroms_b200.so and has no CPU path
+        path = path or library_path()
         if not os.path.exists(path):
             raise RuntimeError("roms_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(there is no CPU fallback)" % path)

@@ -1,0 +1,36 @@
+"""CPU tests of the kernel SOURCES: roms_b200/csrc/*.cu built with g++ against a stand-in CUDA runtime (tests/emu/) and
+run through the same per-kernel parity protocol as tests/test_gpu_parity.py -- push the oracle's state, run ONE kernel entry
+point through the C ABI, compare every field of the mirror with the oracle.  This pins loop bounds, stencil indices and
+operation order of a kernel before it ever reaches a GPU (the build container has none).  It says nothing about speed, about
+races between blocks, or about the PTX-level kernels (step3d_t v6/v4, halo transport), which only the `-m gpu` tests cover.
+The emulation library is test infrastructure: the product never loads it."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(HERE, "emu")])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(os.path.dirname(HERE), "oracle")])
+    return os.path.join(HERE, "emu", "libroms_b200_emu.so")
+
+
+# app, Lm, Mm, N, steps: UPWELLING (linear EOS, ana_vmix, t3dmix2_s) on a small channel; BENCHMARK (UNESCO EOS, KPP, bulk
+# fluxes, geopotential mixing, curvilinear terms) on ragged grids: Lm not a multiple of 32, fewer rows than a block, N = 30
+@pytest.mark.parametrize("app,Lm,Mm,N,steps", [(0, 24, 10, 8, 3), (1, 33, 9, 10, 3), (1, 70, 9, 30, 2)])
+def test_kernel_sources_match_oracle_on_cpu(emu_lib, app, Lm, Mm, N, steps):
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py")] + [str(x) for x in (app, Lm, Mm, N, steps)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_emulation_library_is_not_the_product(emu_lib):
+    """The product binding loads roms_b200/libroms_b200.so only; the emulation library lives under tests/."""
+    import roms_b200 as rb
+    assert os.path.basename(rb.library_path()) == "libroms_b200.so" and "tests" not in rb.library_path()
+    assert os.path.dirname(emu_lib).endswith(os.path.join("tests", "emu"))
