@@ -229,11 +229,24 @@ __global__ void t3dmix2_s_kernel(const Dev D, Box bx, int nrhs, int nnew) {
 // Geopotential rotation of the mixing tensor.  The reference rolls two k-levels
 // (k1,k2) of dZdx,dTdx,dZde,dTde,dTdz,FS through scratch planes; here each thread
 // re-evaluates the slopes it needs for level pair (k,k+1) straight from z_r and t.
-struct GeoQ { V3 z_r, tr; V2 pm, pn; int N; };
-__device__ __forceinline__ double g_dTdz(const GeoQ& G, int i, int j, int kw) {   // at w-level kw (0 or N -> 0)
-  if (kw == 0 || kw == G.N) return 0.0;
-  const double c = 1.0 / (G.z_r(i, j, kw + 1) - G.z_r(i, j, kw));
-  return c * (G.tr(i, j, kw + 1) - G.tr(i, j, kw));
+struct GeoQ { V3 z_r, tr; V2 pm, pn; int N; V3 dtz; };
+// dTdz at w-level kw (0 or N -> 0).  Every cell needs it at 17 (point, level) pairs around it, each a division; the reference
+// keeps it in a scratch plane pair (t3dmix2_geo.h:262-285).  Here geo_dTdz_kernel evaluates it once per point into a scratch
+// volume (G.dtz) and the flux kernel loads it; without a scratch volume (G.dtz.p == nullptr) it is re-evaluated in place.
+__device__ __forceinline__ double g_dTdz_eval(const V3& z_r, const V3& tr, int N, int i, int j, int kw) {
+  if (kw == 0 || kw == N) return 0.0;
+  const double c = 1.0 / (z_r(i, j, kw + 1) - z_r(i, j, kw));
+  return c * (tr(i, j, kw + 1) - tr(i, j, kw));
+}
+__device__ __forceinline__ double g_dTdz(const GeoQ& G, int i, int j, int kw) {
+  if (G.dtz.p) return G.dtz(i, j, kw);
+  return g_dTdz_eval(G.z_r, G.tr, G.N, i, j, kw);
+}
+__global__ void __launch_bounds__(256) geo_dTdz_kernel(const Dev D, Box bx, int nrhs, double* scratch) {
+  IJ_FROM_BOX(bx);
+  const int N = D.b.N, kw = blockIdx.z % (N + 1), itrc = 1 + blockIdx.z / (N + 1);
+  V3 S{scratch + D.nij * (size_t)(N + 1) * (itrc - 1), D.b.LBi, D.ni, D.b.LBj, D.nj, 0};
+  S(i, j, kw) = g_dTdz_eval(v3(D, FID(z_r)), v3l(D, FID(t), nrhs, itrc), N, i, j, kw);
 }
 __device__ __forceinline__ void g_dx(const GeoQ& G, int i, int j, int k, double& dZ, double& dT) {   // at u-point, rho-level k
   const double c = 0.5 * (G.pm(i, j) + G.pm(i - 1, j));
@@ -278,12 +291,13 @@ __device__ __forceinline__ double g_FS(const GeoQ& G, const V2& d2, int i, int j
 // run in parallel; FS(k-1) is carried inside a chunk and re-evaluated at its first level (same operations -> same bits).
 // (One level per thread doubles the expensive FS work and was measured slower: 168 vs 129 us on 512x64x30.)
 constexpr int GEO_KCH = 5;
-__global__ void __launch_bounds__(256) t3dmix2_geo_kernel(const Dev D, Box bx, int nrhs, int nnew) {
+__global__ void __launch_bounds__(256) t3dmix2_geo_kernel(const Dev D, Box bx, int nrhs, int nnew, double* scratch) {
   IJ_FROM_BOX(bx);
   const int N = D.b.N, nch = (N + GEO_KCH - 1) / GEO_KCH, k0 = 1 + GEO_KCH * (blockIdx.z % nch), itrc = 1 + blockIdx.z / nch; const double dt = D.p.dt;
   const int k1 = min(k0 + GEO_KCH - 1, N);
   V3 Hz = v3(D, FID(Hz)), tw = v3l(D, FID(t), nnew, itrc);
-  GeoQ G{v3(D, FID(z_r)), v3l(D, FID(t), nrhs, itrc), v2(D, FID(pm)), v2(D, FID(pn)), N};
+  GeoQ G{v3(D, FID(z_r)), v3l(D, FID(t), nrhs, itrc), v2(D, FID(pm)), v2(D, FID(pn)), N,
+         V3{scratch ? scratch + D.nij * (size_t)(N + 1) * (itrc - 1) : nullptr, D.b.LBi, D.ni, D.b.LBj, D.nj, 0}};
   V2 d2 = v2l(D, FID(diff2), itrc), on_u = v2(D, FID(on_u)), om_v = v2(D, FID(om_v));
   const double cff = dt * G.pm(i, j) * G.pn(i, j);
   double FSm = g_FS(G, d2, i, j, k0 - 1);        // FS at w-level k-1
@@ -301,7 +315,16 @@ int k_t3dmix2(roms_b200_ctx* c, int nrhs, int nstp, int nnew) {
   const roms_b200_bounds& b = c->D.b;
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT;
   if (c->D.p.app == ROMS_B200_APP_UPWELLING) t3dmix2_s_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs, nnew);
-  else { g.z = b.NT * ((b.N + GEO_KCH - 1) / GEO_KCH); t3dmix2_geo_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs, nnew); }
+  else {
+    // dTdz once per point into the KPP scratch volumes (free between lmd_vmix calls; 4 volumes of (ni,nj,0:N)), on the points
+    // the fluxes of the interior reach: i-1..i+1, j-1..j+1
+    double* scratch = (c->D.kpp4 && b.NT <= 4) ? c->D.kpp4 : nullptr;
+    if (scratch) {
+      Box bd{b.Istr - 1, b.Iend + 1, b.Jstr - 1, b.Jend + 1}; dim3 gd = grid2(bd, blk); gd.z = b.NT * (b.N + 1);
+      geo_dTdz_kernel<<<gd, blk, 0, c->stream>>>(c->D, bd, nrhs, scratch); c->launches++;
+    }
+    g.z = b.NT * ((b.N + GEO_KCH - 1) / GEO_KCH); t3dmix2_geo_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs, nnew, scratch);
+  }
   c->launches++;
   return 0;
 }
