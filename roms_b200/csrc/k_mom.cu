@@ -228,42 +228,61 @@ __device__ __forceinline__ double m_UFx(const MQ& Q, int i, int j, int k) { retu
 __device__ __forceinline__ double m_VFe(const MQ& Q, int i, int j, int k) { return Q.om_r(i, j) * Q.om_r(i, j) * Q.visc2_r(i, j) * m_cffr(Q, i, j, k); }
 __device__ __forceinline__ double m_UFe(const MQ& Q, int i, int j, int k) { return Q.om_p(i, j) * Q.om_p(i, j) * Q.visc2_p(i, j) * m_cffp(Q, i, j, k); }
 __device__ __forceinline__ double m_VFx(const MQ& Q, int i, int j, int k) { return Q.on_p(i, j) * Q.on_p(i, j) * Q.visc2_p(i, j) * m_cffp(Q, i, j, k); }
-__global__ void __launch_bounds__(256) uv3dmix2_kernel(const Dev D, Box bx, int nrhs, int nnew) {
+// One thread per (i,j,k,component): nothing in the stress divergence is a vertical recurrence.  The two terms every level adds
+// to rufrc/rvfrc (uv3dmix2_s.h:296-297,326-327) are parked in scratch volumes and summed in the reference's order
+// (acc = acc + c1 + c2, k = 1..N) by uv3dmix2_sum_kernel, one thread per column and component.
+__global__ void __launch_bounds__(256) uv3dmix2_kernel(const Dev D, Box bx, int nrhs, int nnew, double* scratch) {
   IJ_FROM_BOX(bx);
-  const roms_b200_bounds& b = D.b; const int N = b.N; const double dt = D.p.dt;
+  const roms_b200_bounds& b = D.b; const int N = b.N, k = 1 + blockIdx.z % N, comp = blockIdx.z / N; const double dt = D.p.dt;
   MQ Q{v3l(D, FID(u), nrhs), v3l(D, FID(v), nrhs), v3(D, FID(Hz)), v2(D, FID(pm)), v2(D, FID(pn)), v2(D, FID(pmon_r)), v2(D, FID(pnom_r)),
        v2(D, FID(pmon_p)), v2(D, FID(pnom_p)), v2(D, FID(om_r)), v2(D, FID(on_r)), v2(D, FID(om_p)), v2(D, FID(on_p)), v2(D, FID(visc2_r)), v2(D, FID(visc2_p))};
-  if (i >= b.IstrU && i <= b.Iend && j >= b.Jstr && j <= b.Jend) {
-    V3 un = v3l(D, FID(u), nnew); V2 rufrc = v2(D, FID(rufrc));
+  const size_t vol = D.nij * (size_t)(N + 1);
+  V3 S1{scratch + (2 * comp) * vol, b.LBi, D.ni, b.LBj, D.nj, 0}, S2{scratch + (2 * comp + 1) * vol, b.LBi, D.ni, b.LBj, D.nj, 0};
+  if (comp == 0) {
+    if (!(i >= b.IstrU && i <= b.Iend && j >= b.Jstr && j <= b.Jend)) return;
+    V3 un = v3l(D, FID(u), nnew);
     const double cff = dt * 0.25 * (Q.pm(i - 1, j) + Q.pm(i, j)) * (Q.pn(i - 1, j) + Q.pn(i, j));
-    double acc = rufrc(i, j);
-    for (int k = 1; k <= N; ++k) {
-      const double c1 = 0.5 * (Q.pn(i - 1, j) + Q.pn(i, j)) * (m_UFx(Q, i, j, k) - m_UFx(Q, i - 1, j, k));
-      const double c2 = 0.5 * (Q.pm(i - 1, j) + Q.pm(i, j)) * (m_UFe(Q, i, j + 1, k) - m_UFe(Q, i, j, k));
-      const double c3 = cff * (c1 + c2);
-      acc = acc + c1 + c2;
-      un(i, j, k) = un(i, j, k) + c3;
-    }
-    rufrc(i, j) = acc;
-  }
-  if (i >= b.Istr && i <= b.Iend && j >= b.JstrV && j <= b.Jend) {
-    V3 vn = v3l(D, FID(v), nnew); V2 rvfrc = v2(D, FID(rvfrc));
+    const double c1 = 0.5 * (Q.pn(i - 1, j) + Q.pn(i, j)) * (m_UFx(Q, i, j, k) - m_UFx(Q, i - 1, j, k));
+    const double c2 = 0.5 * (Q.pm(i - 1, j) + Q.pm(i, j)) * (m_UFe(Q, i, j + 1, k) - m_UFe(Q, i, j, k));
+    const double c3 = cff * (c1 + c2);
+    S1(i, j, k) = c1; S2(i, j, k) = c2;
+    un(i, j, k) = un(i, j, k) + c3;
+  } else {
+    if (!(i >= b.Istr && i <= b.Iend && j >= b.JstrV && j <= b.Jend)) return;
+    V3 vn = v3l(D, FID(v), nnew);
     const double cff = dt * 0.25 * (Q.pm(i, j) + Q.pm(i, j - 1)) * (Q.pn(i, j) + Q.pn(i, j - 1));
-    double acc = rvfrc(i, j);
-    for (int k = 1; k <= N; ++k) {
-      const double c1 = 0.5 * (Q.pn(i, j - 1) + Q.pn(i, j)) * (m_VFx(Q, i + 1, j, k) - m_VFx(Q, i, j, k));
-      const double c2 = 0.5 * (Q.pm(i, j - 1) + Q.pm(i, j)) * (m_VFe(Q, i, j, k) - m_VFe(Q, i, j - 1, k));
-      const double c3 = cff * (c1 - c2);
-      acc = acc + c1 - c2;
-      vn(i, j, k) = vn(i, j, k) + c3;
-    }
-    rvfrc(i, j) = acc;
+    const double c1 = 0.5 * (Q.pn(i, j - 1) + Q.pn(i, j)) * (m_VFx(Q, i + 1, j, k) - m_VFx(Q, i, j, k));
+    const double c2 = 0.5 * (Q.pm(i, j - 1) + Q.pm(i, j)) * (m_VFe(Q, i, j, k) - m_VFe(Q, i, j - 1, k));
+    const double c3 = cff * (c1 - c2);
+    S1(i, j, k) = c1; S2(i, j, k) = c2;
+    vn(i, j, k) = vn(i, j, k) + c3;
   }
+}
+__global__ void __launch_bounds__(128) uv3dmix2_sum_kernel(const Dev D, Box bx, const double* scratch) {
+  IJ_FROM_BOX(bx);
+  const roms_b200_bounds& b = D.b; const int N = b.N, comp = blockIdx.z;
+  if (comp == 0 ? !(i >= b.IstrU && i <= b.Iend && j >= b.Jstr && j <= b.Jend) : !(i >= b.Istr && i <= b.Iend && j >= b.JstrV && j <= b.Jend)) return;
+  const size_t vol = D.nij * (size_t)(N + 1), o = (i - b.LBi) + (size_t)D.ni * (j - b.LBj);
+  const double* p1 = scratch + (2 * comp) * vol + o; const double* p2 = p1 + vol;
+  V2 frc = v2(D, comp == 0 ? FID(rufrc) : FID(rvfrc));
+  double acc = frc(i, j);
+  constexpr int KB = 6;
+  for (int k0 = 1; k0 <= N; k0 += KB) {
+    double a[KB], c[KB];
+#pragma unroll
+    for (int q = 0; q < KB; ++q) { const int k = min(k0 + q, N); a[q] = p1[D.nij * k]; c[q] = p2[D.nij * k]; }
+#pragma unroll
+    for (int q = 0; q < KB; ++q) if (k0 + q <= N) { if (comp == 0) acc = acc + a[q] + c[q]; else acc = acc + a[q] - c[q]; }
+  }
+  frc(i, j) = acc;
 }
 int k_uv3dmix2(roms_b200_ctx* c, int nrhs, int nnew) {
   const roms_b200_bounds& b = c->D.b;
-  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8);
-  uv3dmix2_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx, nrhs, nnew); c->launches++;
+  if (!c->D.kpp4) return 1;
+  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = 2 * b.N;
+  uv3dmix2_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs, nnew, c->D.kpp4); c->launches++;
+  dim3 blk2(32, 4); dim3 g2 = grid2(bx, blk2); g2.z = 2;
+  uv3dmix2_sum_kernel<<<g2, blk2, 0, c->stream>>>(c->D, bx, c->D.kpp4); c->launches++;
   return 0;
 }
 

@@ -16,9 +16,16 @@
 // halo the 4th-order fluxes reach (3 west/south, 2 east/north) into shared memory; everything downstream reads them there
 // (the first layout re-evaluated them per use: ~100 DUon/DVom per thread).  Same operations on the same operands -> same bits.
 constexpr int S2_TX = 32, S2_TY = 4, S2_TW = S2_TX + 5, S2_TH = S2_TY + 5;
+// ubar/vbar(:,:,krhs) and pm, pn of the tile + halo live in shared memory too: every flux reads them at up to 5 x 5 neighbours
+// (about half of the ~90 global loads of the main phase), and filling them together with Drhs makes it ONE round of L2 loads
+// before the main phase instead of two (ncu: the sub-step is bound by dependent load rounds, long-scoreboard 7.8 warps per issue).
+struct T2 {
+  const double* t; int ti0, tj0;
+  __device__ __forceinline__ double operator()(int i, int j) const { return t[(i - ti0) + S2_TW * (j - tj0)]; }
+};
 struct S2 {
-  V2 zk, zs, ub, vb;                      // zeta(:,:,krhs), zeta(:,:,kstp), ubar/vbar(:,:,krhs)
-  V2 h, pm, pn, on_u, om_v, rhoA, rhoS, rzs, rzp;   // rzeta(:,:,kstp), rzeta(:,:,ptsk)
+  V2 zk, zs; T2 ub, vb;                   // zeta(:,:,krhs), zeta(:,:,kstp) ; ubar/vbar(:,:,krhs) tiles
+  V2 h; T2 pm, pn; V2 on_u, om_v, rhoA, rhoS, rzs, rzp;   // pm, pn tiles ; rzeta(:,:,kstp), rzeta(:,:,ptsk)
   double fac, dtfast; int mode;           // mode: 0 iif==1, 1 predictor, 2 corrector
   int S, N, Jstr, Jend;
   const double *tDr, *tDU, *tDV;          // shared-memory tiles, element (i,j) at (i-ti0) + S2_TW*(j-tj0)
@@ -119,7 +126,7 @@ struct Step2dArgs { int krhs, kstp, knew, nstp, nnew, iif, pred, stepmode; };  /
 // z=1 advances vbar (both evaluate the free-surface state they need from the shared tiles).
 struct Boxes { Box b[4]; };               // blockIdx.z selects the box (the frame of a tile is up to four strips)
 __global__ void __launch_bounds__(S2_TX * S2_TY * 2) step2d_kernel(const Dev D, const Boxes bxs, Step2dArgs a) {
-  __shared__ double tDr[S2_TW * S2_TH], tDU[S2_TW * S2_TH], tDV[S2_TW * S2_TH];
+  __shared__ double tDr[S2_TW * S2_TH], tDU[S2_TW * S2_TH], tDV[S2_TW * S2_TH], tU[S2_TW * S2_TH], tV[S2_TW * S2_TH], tPm[S2_TW * S2_TH], tPn[S2_TW * S2_TH];
   // Programmatic dependent launch (launch_boxes): let the next sub-step's grid be scheduled now, and do not touch any
   // field before the previous sub-step has completed and flushed.  Both are no-ops for an ordinary launch.
 #ifndef ROMS_B200_EMU
@@ -132,34 +139,53 @@ __global__ void __launch_bounds__(S2_TX * S2_TY * 2) step2d_kernel(const Dev D, 
   const roms_b200_bounds& b = D.b;
   const int krhs = a.krhs, kstp = a.kstp, knew = a.knew, iif = a.iif, ptsk = 3 - kstp;
   const bool PRED = a.pred != 0;
-  S2 s{v2l(D, FID(zeta), krhs), v2l(D, FID(zeta), kstp), v2l(D, FID(ubar), krhs), v2l(D, FID(vbar), krhs),
-       v2(D, FID(h)), v2(D, FID(pm)), v2(D, FID(pn)), v2(D, FID(on_u)), v2(D, FID(om_v)), v2(D, FID(rhoA)), v2(D, FID(rhoS)),
+  const int ti0 = bx.i0 + (int)blockIdx.x * S2_TX - 3, tj0 = bx.j0 + (int)blockIdx.y * S2_TY - 3;
+  S2 s{v2l(D, FID(zeta), krhs), v2l(D, FID(zeta), kstp), T2{tU, ti0, tj0}, T2{tV, ti0, tj0},
+       v2(D, FID(h)), T2{tPm, ti0, tj0}, T2{tPn, ti0, tj0}, v2(D, FID(on_u)), v2(D, FID(om_v)), v2(D, FID(rhoA)), v2(D, FID(rhoS)),
        v2l(D, FID(rzeta), kstp > 2 ? 1 : kstp), v2l(D, FID(rzeta), ptsk < 1 ? 1 : ptsk),
        1000.0 / D.p.rho0, D.p.dtfast, (iif == 1) ? 0 : (PRED ? 1 : 2),
        b.Southern_Edge && !b.NSperiodic, b.Northern_Edge && !b.NSperiodic, b.Jstr, b.Jend,
-       tDr, tDU, tDV, bx.i0 + (int)blockIdx.x * S2_TX - 3, bx.j0 + (int)blockIdx.y * S2_TY - 3};
+       tDr, tDU, tDV, ti0, tj0};
   {
-    // ---- shared tiles: Drhs on [I0-3,I1+2]x[J0-3,J1+2], then DUon/DVom where Drhs(i-1)/(j-1) exist (:664-702)
+    // ---- shared tiles on [I0-3,I1+2]x[J0-3,J1+2]: Drhs, ubar, vbar (one round of loads; on_u, om_v of the cell ride along in
+    // registers), then DUon/DVom where Drhs(i-1)/(j-1) exist (:664-702).  A thread owns at most S2_NQ cells of the tile.
+    constexpr int S2_NT = S2_TX * S2_TY * 2, S2_NQ = (S2_TW * S2_TH + S2_NT - 1) / S2_NT;
     const int tid = (threadIdx.z * S2_TY + threadIdx.y) * S2_TX + threadIdx.x;
-    for (int q = tid; q < S2_TW * S2_TH; q += S2_TX * S2_TY * 2) {
-      const int ii = s.ti0 + q % S2_TW, jj = s.tj0 + q / S2_TW;
-      const bool in = (ii >= b.LBi && ii <= b.UBi && jj >= b.LBj && jj <= b.UBj);
-      tDr[q] = in ? (s.zk(ii, jj) + s.h(ii, jj)) : 0.0;
+    V2 ubg = v2l(D, FID(ubar), krhs), vbg = v2l(D, FID(vbar), krhs), pmg = v2(D, FID(pm)), png = v2(D, FID(pn));
+    double r_ou[S2_NQ], r_ov[S2_NQ], r_ub[S2_NQ], r_vb[S2_NQ];
+#pragma unroll
+    for (int n = 0; n < S2_NQ; ++n) {
+      const int q = tid + n * S2_NT;
+      r_ou[n] = 0.0; r_ov[n] = 0.0; r_ub[n] = 0.0; r_vb[n] = 0.0;
+      if (q < S2_TW * S2_TH) {
+        const int ii = s.ti0 + q % S2_TW, jj = s.tj0 + q / S2_TW;
+        const bool in = (ii >= b.LBi && ii <= b.UBi && jj >= b.LBj && jj <= b.UBj);
+        double dr = 0.0, pmv = 0.0, pnv = 0.0;
+        if (in) {
+          dr = s.zk(ii, jj) + s.h(ii, jj); r_ub[n] = ubg(ii, jj); r_vb[n] = vbg(ii, jj); r_ou[n] = s.on_u(ii, jj); r_ov[n] = s.om_v(ii, jj);
+          pmv = pmg(ii, jj); pnv = png(ii, jj);
+        }
+        tDr[q] = dr; tU[q] = r_ub[n]; tV[q] = r_vb[n]; tPm[q] = pmv; tPn[q] = pnv;
+      }
     }
     __syncthreads();
-    for (int q = tid; q < S2_TW * S2_TH; q += S2_TX * S2_TY * 2) {
-      const int qi = q % S2_TW, qj = q / S2_TW, ii = s.ti0 + qi, jj = s.tj0 + qj;
-      const bool in = (ii >= b.LBi && ii <= b.UBi && jj >= b.LBj && jj <= b.UBj);
-      double du = 0.0, dv = 0.0;
-      if (in && qi >= 1 && ii - 1 >= b.LBi) {
-        const double cff = 0.5 * s.on_u(ii, jj); const double cff1 = cff * (tDr[q] + tDr[q - 1]);
-        du = s.ub(ii, jj) * cff1;
+#pragma unroll
+    for (int n = 0; n < S2_NQ; ++n) {
+      const int q = tid + n * S2_NT;
+      if (q < S2_TW * S2_TH) {
+        const int qi = q % S2_TW, qj = q / S2_TW, ii = s.ti0 + qi, jj = s.tj0 + qj;
+        const bool in = (ii >= b.LBi && ii <= b.UBi && jj >= b.LBj && jj <= b.UBj);
+        double du = 0.0, dv = 0.0;
+        if (in && qi >= 1 && ii - 1 >= b.LBi) {
+          const double cff = 0.5 * r_ou[n]; const double cff1 = cff * (tDr[q] + tDr[q - 1]);
+          du = r_ub[n] * cff1;
+        }
+        if (in && qj >= 1 && jj - 1 >= b.LBj) {
+          const double cff = 0.5 * r_ov[n]; const double cff1 = cff * (tDr[q] + tDr[q - S2_TW]);
+          dv = r_vb[n] * cff1;
+        }
+        tDU[q] = du; tDV[q] = dv;
       }
-      if (in && qj >= 1 && jj - 1 >= b.LBj) {
-        const double cff = 0.5 * s.om_v(ii, jj); const double cff1 = cff * (tDr[q] + tDr[q - S2_TW]);
-        dv = s.vb(ii, jj) * cff1;
-      }
-      tDU[q] = du; tDV[q] = dv;
     }
     __syncthreads();
   }

@@ -85,9 +85,10 @@ int roms_b200_create(const roms_b200_bounds* b, const roms_b200_params* p, int d
   D.w1 = v; D.w2 = v + (2 * p->ndtfast + 4);
   if (dev_alloc(&D.P, D.nij * b->N)) return 4;
   if (dev_alloc(&D.scratch2, D.nij * 8)) return 4;
-  if (p->app == ROMS_B200_APP_BENCHMARK) {          // KPP scratch (k_kpp.cu): Bflux and {dR, dU, dV, FC}, (ni,nj,0:N) each
+  // four 3-D scratch volumes (ni,nj,0:N): KPP {dR, dU, dV, FC}, t3dmix2_geo dTdz per tracer, uv3dmix2's rufrc/rvfrc terms
+  if (dev_alloc(&D.kpp4, D.nij * (size_t)(b->N + 1) * 4)) return 4;
+  if (p->app == ROMS_B200_APP_BENCHMARK) {          // KPP surface buoyancy flux profile Bflux
     if (dev_alloc(&D.swdk, D.nij * (size_t)(b->N + 1))) return 4;
-    if (dev_alloc(&D.kpp4, D.nij * (size_t)(b->N + 1) * 4)) return 4;
   }
   // diag (k_grid.cu): 3 sums per interior column i + 9 maxima + 9 per block of 128 columns of a row
   const size_t nred = (size_t)3 * D.ni + 16 + 12 * 64 + (size_t)9 * ((D.ni + 127) / 128) * D.nj;   // + one 12-double slot per tile (<= 64)
@@ -190,7 +191,7 @@ int roms_b200_pre_step3d(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic
 int roms_b200_prsgrd(roms_b200_ctx* c, int nrhs) { ENTER(c); k_prsgrd(c, nrhs); LEAVE(); }
 int roms_b200_t3dmix2(roms_b200_ctx* c, int nrhs, int nstp, int nnew) { ENTER(c); k_t3dmix2(c, nrhs, nstp, nnew); LEAVE(); }
 int roms_b200_rhs3d_tile(roms_b200_ctx* c, int nrhs) { ENTER(c); k_rhs3d_tile(c, nrhs); LEAVE(); }
-int roms_b200_uv3dmix2(roms_b200_ctx* c, int nrhs, int nnew) { ENTER(c); k_uv3dmix2(c, nrhs, nnew); LEAVE(); }
+int roms_b200_uv3dmix2(roms_b200_ctx* c, int nrhs, int nnew) { ENTER(c); if (k_uv3dmix2(c, nrhs, nnew)) return 1; LEAVE(); }
 int roms_b200_rhs3d(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntfirst) {
   ENTER(c);
   k_pre_step3d(c, nrhs, nstp, nnew, iic, ntfirst); k_prsgrd(c, nrhs); k_t3dmix2(c, nrhs, nstp, nnew); k_rhs3d_tile(c, nrhs); k_uv3dmix2(c, nrhs, nnew);
