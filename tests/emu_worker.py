@@ -17,7 +17,7 @@ import numpy as np  # noqa: E402
 import oracle_lib as ol  # noqa: E402
 import roms_b200 as rb  # noqa: E402
 
-rb.lib.Lib._inst = rb.lib.Lib(path=os.path.join(HERE, "emu", "libroms_b200_emu.so"))
+rb.lib.Lib._inst = rb.lib.Lib(path=os.path.join(HERE, "emu", os.environ.get("EMU_WORKER_LIB", "libroms_b200_emu.so")))
 from parity_common import GPU_PHASE, TRANSCENDENTAL, make_pair, push, diff_fields, run_phase_gpu  # noqa: E402
 
 

@@ -29,6 +29,19 @@ def test_kernel_sources_match_oracle_on_cpu(emu_lib, app, Lm, Mm, N, steps):
     assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+def test_kernel_sources_memory_safe_under_asan(emu_lib):
+    """Same protocol with the emulation built under AddressSanitizer: every mirror field is its own heap block and every
+    shared-memory tile its own static array, so a stencil index outside a field or a tile aborts the worker."""
+    asan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(HERE, "emu"), "ASAN=1"])
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0", EMU_WORKER_LIB="libroms_b200_emu_asan.so")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "1", "33", "9", "10", "2"], capture_output=True, text=True,
+                       timeout=900, env=env)
+    assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout and "AddressSanitizer" not in r.stderr, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_emulation_library_is_not_the_product(emu_lib):
     """The product binding loads roms_b200/libroms_b200.so only; the emulation library lives under tests/."""
     import roms_b200 as rb
