@@ -4,31 +4,51 @@
 #include "common.cuh"
 
 // ---- prsgrd32_tile, prsgrd32.h:238-433 -----------------------------------------
-// pass 1: column pressure P(i,j,k) with harmonic-mean spline slopes dR,dZ
-__global__ void __launch_bounds__(256) prsgrd_P_kernel(const Dev D, Box bx) {
+// pass 1: column pressure P(i,j,k) with harmonic-mean spline slopes dR,dZ.  Only the running sum over k is a recurrence:
+// prsgrd_T_kernel (one thread per (i,j,k)) evaluates the increment of level k -- the harmonic means of levels k and k+1 from
+// the raw differences k-1..k+1, exactly as the in-place descending sweep of prsgrd32.h:258-271 sees them -- and parks it in
+// P(i,j,k); prsgrd_P_kernel (one thread per column) then adds the increments from the surface down (:279-305).
+// (One column kernel doing both took 43 us on BENCHMARK1: 32 k threads, two dependent sweeps of L2 loads.)
+__device__ __forceinline__ double prs_raw(const V3& a, int i, int j, int m, int N) {     // a(m+1)-a(m), with dX(N)=dX(N-1), dX(0)=dX(1)
+  const int mm = (m >= N) ? N - 1 : (m <= 0 ? 1 : m);
+  return a(i, j, mm + 1) - a(i, j, mm);
+}
+__global__ void __launch_bounds__(256) prsgrd_T_kernel(const Dev D, Box bx) {
   IJ_FROM_BOX(bx);
-  const int N = D.b.N; const double g = D.p.g, GRho = g / D.p.rho0, HalfGRho = 0.5 * GRho;
+  const int N = D.b.N, k = 1 + blockIdx.z; const double g = D.p.g, GRho = g / D.p.rho0, HalfGRho = 0.5 * GRho;
   const double OneFifth = 0.2, OneTwelfth = 1.0 / 12.0, eps = 1.0e-10;
   V3 rho = v3(D, FID(rho)), z_r = v3(D, FID(z_r)), z_w = v3(D, FID(z_w));
   V3 P{D.P, D.b.LBi, D.ni, D.b.LBj, D.nj, 1};
-  double dR[RB_MAXN + 1], dZ[RB_MAXN + 1];
-  for (int k = 1; k <= N - 1; ++k) { dR[k] = rho(i, j, k + 1) - rho(i, j, k); dZ[k] = z_r(i, j, k + 1) - z_r(i, j, k); }
-  dR[N] = dR[N - 1]; dZ[N] = dZ[N - 1]; dR[0] = dR[1]; dZ[0] = dZ[1];
-  for (int k = N; k >= 1; --k) {
-    const double cff = 2.0 * dR[k] * dR[k - 1];
-    dR[k] = (cff > eps) ? cff / (dR[k] + dR[k - 1]) : 0.0;
-    dZ[k] = 2.0 * dZ[k] * dZ[k - 1] / (dZ[k] + dZ[k - 1]);
+  if (k == N) {
+    const double zwN = z_w(i, j, N), zrN = z_r(i, j, N), rN = rho(i, j, N);
+    const double cff1 = 1.0 / (zrN - z_r(i, j, N - 1));
+    const double cff2 = 0.5 * (rN - rho(i, j, N - 1)) * (zwN - zrN) * cff1;
+    P(i, j, N) = g * zwN + GRho * (rN + cff2) * (zwN - zrN);
+    return;
   }
-  const double cff1 = 1.0 / (z_r(i, j, N) - z_r(i, j, N - 1));
-  const double cff2 = 0.5 * (rho(i, j, N) - rho(i, j, N - 1)) * (z_w(i, j, N) - z_r(i, j, N)) * cff1;
-  double Pk = g * z_w(i, j, N) + GRho * (rho(i, j, N) + cff2) * (z_w(i, j, N) - z_r(i, j, N));
-  P(i, j, N) = Pk;
-  for (int k = N - 1; k >= 1; --k) {
-    const double rk1 = rho(i, j, k + 1), rk = rho(i, j, k), zk1 = z_r(i, j, k + 1), zk = z_r(i, j, k);
-    Pk = Pk + HalfGRho * ((rk1 + rk) * (zk1 - zk) -
-                          OneFifth * ((dR[k + 1] - dR[k]) * (zk1 - zk - OneTwelfth * (dZ[k + 1] + dZ[k])) -
-                                      (dZ[k + 1] - dZ[k]) * (rk1 - rk - OneTwelfth * (dR[k + 1] + dR[k]))));
-    P(i, j, k) = Pk;
+  // raw differences at k-1, k, k+1 and the harmonic means at k, k+1
+  const double rm = prs_raw(rho, i, j, k - 1, N), r0 = prs_raw(rho, i, j, k, N), rp = prs_raw(rho, i, j, k + 1, N);
+  const double zm = prs_raw(z_r, i, j, k - 1, N), z0 = prs_raw(z_r, i, j, k, N), zp = prs_raw(z_r, i, j, k + 1, N);
+  const double cK = 2.0 * r0 * rm, cP = 2.0 * rp * r0;
+  const double dRk = (cK > eps) ? cK / (r0 + rm) : 0.0, dRp = (cP > eps) ? cP / (rp + r0) : 0.0;
+  const double dZk = 2.0 * z0 * zm / (z0 + zm), dZp = 2.0 * zp * z0 / (zp + z0);
+  const double rk1 = rho(i, j, k + 1), rk = rho(i, j, k), zk1 = z_r(i, j, k + 1), zk = z_r(i, j, k);
+  P(i, j, k) = HalfGRho * ((rk1 + rk) * (zk1 - zk) -
+                           OneFifth * ((dRp - dRk) * (zk1 - zk - OneTwelfth * (dZp + dZk)) -
+                                       (dZp - dZk) * (rk1 - rk - OneTwelfth * (dRp + dRk))));
+}
+__global__ void __launch_bounds__(256) prsgrd_P_kernel(const Dev D, Box bx) {
+  IJ_FROM_BOX(bx);
+  const int N = D.b.N;
+  V3 P{D.P, D.b.LBi, D.ni, D.b.LBj, D.nj, 1};
+  double Pk = P(i, j, N);
+  constexpr int KB = 8;
+  for (int k0 = N - 1; k0 >= 1; k0 -= KB) {
+    double t[KB];
+#pragma unroll
+    for (int q = 0; q < KB; ++q) t[q] = P(i, j, max(k0 - q, 1));
+#pragma unroll
+    for (int q = 0; q < KB; ++q) { const int k = k0 - q; if (k >= 1) { Pk = Pk + t[q]; P(i, j, k) = Pk; } }
   }
 }
 // harmonic-mean horizontal slopes (prsgrd32.h:319-336, 383-400)
@@ -76,6 +96,8 @@ __global__ void __launch_bounds__(256) prsgrd_ruv_kernel(const Dev D, Box bx, in
 int k_prsgrd(roms_b200_ctx* c, int nrhs) {
   const roms_b200_bounds& b = c->D.b;
   Box bp{b.IstrU - 1, b.Iend, b.JstrV - 1, b.Jend}; dim3 blk(32, 8);
+  if (b.N < 2) return 1;
+  { dim3 blkT(128, 2); dim3 gT = grid2(bp, blkT); gT.z = b.N; prsgrd_T_kernel<<<gT, blkT, 0, c->stream>>>(c->D, bp); c->launches++; }
   prsgrd_P_kernel<<<grid2(bp, blk), blk, 0, c->stream>>>(c->D, bp); c->launches++;
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk2(128, 2); dim3 g = grid2(bx, blk2); g.z = b.N;
   prsgrd_ruv_kernel<<<g, blk2, 0, c->stream>>>(c->D, bx, nrhs); c->launches++;
