@@ -54,5 +54,50 @@ def main():
     print("EMU-PARITY-OK app=%d %dx%dx%d steps=%d ; within tolerance but not bit-identical: %s" % (app, Lm, Mm, N, nsteps, sorted(not_bitwise)))
 
 
+def driver():
+    """ROMS_initialize / ROMS_run of the C++ host driver on the emulated kernels vs the oracle: with glibc on both sides the
+    whole loop is bit-identical, including KPP, bulk fluxes and the analytical initial state."""
+    app, Lm, Mm, N, nsteps = (int(x) for x in sys.argv[2:7])
+    o = ol.Oracle(app, Lm, Mm, N)
+    o.initial()
+    o.phase("begin")
+    d = rb.Driver(rb.default_config(app, Lm, Mm, N))
+    assert d.nfast == o.dims()["nfast"]
+    skip = {"xr", "yr", "lonr", "latr"}        # set only on Istr-1..Iend+1 by the reference; the product fills the whole row
+    bad = [n for n in rb.FIELD_NAMES if n not in skip and not np.array_equal(o.get(n), d.ctx.download(n))]
+    assert not bad, ("start state", bad)
+    for ph in ol.PHASES[1:]:
+        o.phase(ph)
+    o.step(nsteps - 1)
+    d.run(nsteps)                              # device-resident: forcing evaluated by set_data_kernel, diag launched in every step
+    bad = [n for n in rb.FIELD_NAMES if n not in skip and not np.array_equal(o.get(n), d.ctx.download(n))]
+    assert not bad, ("after %d steps" % nsteps, bad)
+    # host forcing (set_data on the host, upload, diag read back every step): the diag returned is that of the last step's start
+    diag = d.run(2, host_forcing=True)
+    o.step(1)
+    for ph in ol.PHASES[:4]:
+        o.phase(ph)
+    ref = o.diag_full()
+    assert np.array_equal(diag, ref[:3]) and np.array_equal(d.ctx.diag_last(), ref), (diag, d.ctx.diag_last(), ref)
+    for ph in ol.PHASES[4:]:
+        o.phase(ph)
+    bad = [n for n in ("zeta", "ubar", "vbar", "u", "v", "t") if not np.array_equal(o.get(n), d.ctx.download(n))]
+    assert not bad, ("host forcing", bad)
+    # blow-up: diag.F:512-542 sets exit_flag=1 and the driver stops (main3d.F:362)
+    u = d.ctx.download("u")
+    u[u.size // 3] = 1.0e3
+    d.ctx.upload("u", u)
+    try:
+        d.run(1, host_forcing=True)
+        raise AssertionError("blow-up not detected")
+    except RuntimeError:
+        pass
+    d.finalize()
+    print("EMU-DRIVER-OK app=%d %dx%dx%d steps=%d" % (app, Lm, Mm, N, nsteps))
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1] == "driver":
+        driver()
+    else:
+        main()

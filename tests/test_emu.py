@@ -29,6 +29,15 @@ def test_kernel_sources_match_oracle_on_cpu(emu_lib, app, Lm, Mm, N, steps):
     assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+def test_host_driver_on_emulated_kernels(emu_lib):
+    """ROMS_initialize / ROMS_run (C++ host driver, roms_b200/csrc/host_driver.cpp) over the emulated kernels: start state, the
+    device-resident loop, the host-forcing loop with diag read back every step and the blow-up stop -- all bit-identical to
+    the oracle (glibc on both sides)."""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "driver", "1", "33", "9", "10", "3"], capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0 and "EMU-DRIVER-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_kernel_sources_memory_safe_under_asan(emu_lib):
     """Same protocol with the emulation built under AddressSanitizer: every mirror field is its own heap block and every
     shared-memory tile its own static array, so a stencil index outside a field or a tile aborts the worker."""
