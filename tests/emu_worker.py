@@ -85,7 +85,8 @@ def driver():
     assert not bad, ("host forcing", bad)
     # blow-up: diag.F:512-542 sets exit_flag=1 and the driver stops (main3d.F:362)
     u = d.ctx.download("u")
-    u[u.size // 3] = 1.0e3
+    u[u.size // 3] = 1.0e3                      # an interior point of time level 1 ...
+    u[u.size // 2 + u.size // 3] = 1.0e3        # ... and of level 2 (diag reads level nstp)
     d.ctx.upload("u", u)
     try:
         d.run(1, host_forcing=True)
