@@ -204,6 +204,15 @@ int roms_b200_p2p_connect(roms_b200_ctx* ctx, const char* handles, int nranks);
  * storage plane `plane0`, into a dense host buffer (nplanes, Jend-Jstr+1, Iend-Istr+1) */
 int roms_b200_download_interior(roms_b200_ctx* ctx, int field, int plane0, int nplanes, double* host);
 
+/* ---- output path without stalling the time loop (what `output` needs before wrt_his / wrt_rst / wrt_avg, output.F:217,703).
+ * roms_b200_snapshot_begin copies the listed fields device-to-device into a staging area ON THE LAUNCH STREAM (it orders after
+ * every kernel launched so far and costs microseconds), then device-to-host into the caller's PINNED buffers
+ * (roms_b200_host_alloc; buffer q holds roms_b200_field_size(fields[q]) doubles) on a separate copy stream, and returns at
+ * once: the following steps run while the snapshot drains over PCIe.  roms_b200_snapshot_end waits for the host copies; one
+ * snapshot may be in flight at a time (a second begin before end returns 1). */
+int roms_b200_snapshot_begin(roms_b200_ctx* ctx, int nfields, const int* fields, double* const* pinned_host);
+int roms_b200_snapshot_end(roms_b200_ctx* ctx);
+
 /* CUDA-event stopwatch on the context's launch stream, and an L2 flush (writes `mbytes` MiB) */
 int roms_b200_timer_start(roms_b200_ctx* ctx);
 int roms_b200_timer_stop(roms_b200_ctx* ctx, float* ms);

@@ -111,6 +111,8 @@ int roms_b200_destroy(roms_b200_ctx* c) {
   for (int f = 0; f < ROMS_B200_NFIELDS; ++f) cudaFree(c->D.f[f]);
   cudaFree((void*)c->D.sc_r); cudaFree((void*)c->D.w1); cudaFree(c->D.P); cudaFree(c->D.scratch2); cudaFree(c->D.swdk); cudaFree(c->D.kpp4); cudaFree(c->D.red); cudaFree(c->D.ksbl); cudaFree(c->D.err);
   cudaFreeHost(c->h_red);
+  if (c->snap_stream) { cudaStreamSynchronize(c->snap_stream); cudaStreamDestroy(c->snap_stream); cudaEventDestroy(c->snap_ready); cudaEventDestroy(c->snap_done); }
+  cudaFree(c->snap_buf);
   roms_b200_comm_destroy(c);
   cudaStreamDestroy(c->stream); cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
   delete c;
@@ -352,6 +354,49 @@ int roms_b200_main3d(roms_b200_ctx* c, int nsteps, int analytic_forcing, int wit
     { XF x[HALO_MAXF]; int n = 0; for (int it = 1; it <= c->D.b.NT; ++it) x[n++] = xf3(c, FID(t), nnew, it); if (xchg(c, x, n)) return 1; }   // step3d_t.F:1920
     c->iic += 1; c->time += c->D.p.dt;
   }
+  LEAVE();
+}
+
+// Output snapshots: mirror -> staging (launch stream, device-to-device) -> pinned host buffers (copy stream), see roms_b200.h
+int roms_b200_snapshot_begin(roms_b200_ctx* c, int nfields, const int* fields, double* const* host) {
+  ENTER(c);
+  if (nfields <= 0 || !fields || !host || c->snap_pending) return 1;
+  size_t total = 0;
+  for (int q = 0; q < nfields; ++q) { if (fields[q] < 0 || fields[q] >= ROMS_B200_NFIELDS || !host[q]) return 1; total += c->fsize[fields[q]]; }
+  if (!c->snap_stream) {
+    CUDA_OK(cudaStreamCreateWithFlags(&c->snap_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&c->snap_ready, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&c->snap_done, cudaEventDisableTiming));
+  }
+  if (total > c->snap_cap) {
+    if (c->snap_buf) CUDA_OK(cudaFree(c->snap_buf));
+    c->snap_buf = nullptr; c->snap_cap = 0;
+    CUDA_OK(cudaMalloc((void**)&c->snap_buf, total * sizeof(double)));
+    c->snap_cap = total;
+  }
+  size_t off = 0;
+  for (int q = 0; q < nfields; ++q) {                 // the state as of this point of the launch stream
+    const size_t n = c->fsize[fields[q]];
+    CUDA_OK(cudaMemcpyAsync(c->snap_buf + off, c->D.f[fields[q]], n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    off += n;
+  }
+  CUDA_OK(cudaEventRecord(c->snap_ready, c->stream));
+  CUDA_OK(cudaStreamWaitEvent(c->snap_stream, c->snap_ready, 0));
+  off = 0;
+  for (int q = 0; q < nfields; ++q) {
+    const size_t n = c->fsize[fields[q]];
+    CUDA_OK(cudaMemcpyAsync(host[q], c->snap_buf + off, n * sizeof(double), cudaMemcpyDeviceToHost, c->snap_stream));
+    off += n;
+  }
+  CUDA_OK(cudaEventRecord(c->snap_done, c->snap_stream));
+  c->snap_pending = 1;
+  LEAVE();
+}
+int roms_b200_snapshot_end(roms_b200_ctx* c) {
+  ENTER(c);
+  if (!c->snap_pending) return 0;
+  CUDA_OK(cudaEventSynchronize(c->snap_done));
+  c->snap_pending = 0;
   LEAVE();
 }
 

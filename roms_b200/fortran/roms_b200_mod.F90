@@ -232,6 +232,25 @@
           real(c_double), intent(out) :: out13(13)
         END FUNCTION
 !
+!  Output path (output.F:217,703): asynchronous snapshot of nfields mirror
+!  fields into pinned host buffers (roms_b200_host_alloc); the time loop
+!  continues, roms_b200_snapshot_end waits before wrt_his / wrt_rst read them.
+!
+        integer(c_int) FUNCTION roms_b200_snapshot_begin (ctx, nfields, &
+     &                                   fields, pinned_host)           &
+     &                          BIND(C, name='roms_b200_snapshot_begin')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nfields
+          integer(c_int), intent(in) :: fields(*)
+          type(c_ptr), intent(in) :: pinned_host(*)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_snapshot_end (ctx)            &
+     &                          BIND(C, name='roms_b200_snapshot_end')
+          IMPORT
+          type(c_ptr), value :: ctx
+        END FUNCTION
+!
 !  NCCL communicator (replaces mp_exchange2d/3d/4d): id from rank 0 via
 !  mpi_bcast, then every rank calls comm_init.
 !

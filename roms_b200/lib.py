@@ -208,6 +208,29 @@ class Context:
     def launches(self):
         return self.L.roms_b200_launch_count(self.h)
 
+    def snapshot_begin(self, names):
+        """Start an asynchronous snapshot of the named fields into pinned host buffers; returns {name: numpy view}.  The views
+        are valid after snapshot_end()."""
+        self.L.roms_b200_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+        self.L.roms_b200_snapshot_begin.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+        self.L.roms_b200_snapshot_end.argtypes = [C.c_void_p]
+        pool = self.__dict__.setdefault("_snap_pinned", {})
+        ids = (C.c_int * len(names))(*[self.fid(n) for n in names])
+        ptrs = (C.c_void_p * len(names))()
+        views = {}
+        for q, n in enumerate(names):
+            if n not in pool:
+                p = C.c_void_p()
+                self._chk(self.L.roms_b200_host_alloc(self.size(n) * 8, C.byref(p)), "host_alloc")
+                pool[n] = p
+            ptrs[q] = pool[n]
+            views[n] = np.ctypeslib.as_array(C.cast(pool[n], C.POINTER(C.c_double)), shape=(self.size(n),))
+        self._chk(self.L.roms_b200_snapshot_begin(self.h, len(names), ids, ptrs), "snapshot_begin")
+        return views
+
+    def snapshot_end(self):
+        self._chk(self.L.roms_b200_snapshot_end(self.h), "snapshot_end")
+
     def time_step3d_t(self, nrhs, nstp, nnew, reps):
         ms = C.c_float()
         self._chk(self.L.roms_b200_time_step3d_t(self.h, nrhs, nstp, nnew, reps, C.byref(ms)), "time_step3d_t")

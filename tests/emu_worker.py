@@ -83,6 +83,18 @@ def driver():
         o.phase(ph)
     bad = [n for n in ("zeta", "ubar", "vbar", "u", "v", "t") if not np.array_equal(o.get(n), d.ctx.download(n))]
     assert not bad, ("host forcing", bad)
+    # output snapshot (data path only: the emulation is synchronous)
+    names = ["zeta", "u", "t"]
+    ref_s = {n: d.ctx.download(n) for n in names}
+    views = d.ctx.snapshot_begin(names)
+    try:
+        d.ctx.snapshot_begin(names)
+        raise AssertionError("second snapshot_begin accepted while one is pending")
+    except RuntimeError:
+        pass
+    d.run(1)
+    d.ctx.snapshot_end()
+    assert all(np.array_equal(views[n], ref_s[n]) for n in names)
     # blow-up: diag.F:512-542 sets exit_flag=1 and the driver stops (main3d.F:362)
     u = d.ctx.download("u")
     u[u.size // 3] = 1.0e3                      # an interior point of time level 1 ...

@@ -64,6 +64,32 @@ def test_roms_initialize_matches_oracle_start_state(app, Lm, Mm, N):
     d.finalize()
 
 
+def test_output_snapshot_does_not_disturb_the_time_loop():
+    """roms_b200_snapshot_begin/end (the output path): the snapshot holds the state of the instant it was requested although the
+    loop keeps stepping while it drains, and the loop's results are those of a run without snapshots."""
+    cfg = rb.default_config(ol.BENCHMARK, 96, 40, 30)
+    names = ["zeta", "ubar", "vbar", "u", "v", "t"]
+    d = rb.Driver(cfg)
+    d.run(3)
+    ref = {n: d.ctx.download(n) for n in names}
+    views = d.ctx.snapshot_begin(names)
+    with pytest.raises(RuntimeError):
+        d.ctx.snapshot_begin(names)            # one snapshot in flight at a time
+    d.run(2)
+    d.ctx.snapshot_end()
+    for n in names:
+        assert np.array_equal(views[n], ref[n]), n
+    d2 = rb.Driver(cfg)
+    d2.run(3)
+    d2.run(2)
+    for n in names:
+        assert np.array_equal(d.ctx.download(n), d2.ctx.download(n)), n
+    views = d.ctx.snapshot_begin(["zeta"])     # buffers are reused, a smaller request works after a larger one
+    d.ctx.snapshot_end()
+    assert np.array_equal(views["zeta"], d.ctx.download("zeta"))
+    d.finalize(); d2.finalize()
+
+
 def test_negative_control_detects_missing_kernel():
     """If a kernel is NOT run the comparison must fail: guards against a vacuous harness."""
     o, ctx = make_pair(ol.UPWELLING)
