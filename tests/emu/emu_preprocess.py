@@ -23,10 +23,33 @@ def split_top(s):
 
 def rewrite_launches(line):
     while True:
-        m = re.search(r"([A-Za-z_]\w*)\s*<<<", line)
-        if not m:
+        pos = line.find("<<<")
+        if pos < 0:
             return line
-        a = m.end()
+        # kernel expression before <<<: an identifier, optionally with template arguments
+        e = pos
+        while e > 0 and line[e - 1] == " ":
+            e -= 1
+        st = e
+        if line[st - 1] == ">":
+            depth = 0
+            while True:
+                st -= 1
+                if line[st] == ">":
+                    depth += 1
+                elif line[st] == "<":
+                    depth -= 1
+                    if depth == 0:
+                        break
+        while st > 0 and (line[st - 1].isalnum() or line[st - 1] == "_"):
+            st -= 1
+        kern = line[st:e]
+
+        class M:                                   # same interface as the former regex match
+            def start(self): return st
+            def group(self, n): return "(" + kern + ")" if "<" in kern else kern
+        m = M()
+        a = pos + 3
         b = line.index(">>>", a)
         cfg = split_top(line[a:b])
         assert len(cfg) in (2, 3, 4), line
@@ -51,6 +74,6 @@ out = []
 for line in open(src):
     if "<<<" in line and not line.lstrip().startswith("//"):
         line = rewrite_launches(line)
-    line = re.sub(r"extern\s+__shared__\s+double\s+(\w+)\s*\[\s*\]\s*;", r"double* \1 = (double*)emu::dyn_smem();", line)
+    line = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?double\s+(\w+)\s*\[\s*\]\s*;", r"double* \1 = (double*)emu::dyn_smem();", line)
     out.append(line)
 open(dst, "w").write('#line 1 "%s"\n' % src + "".join(out))

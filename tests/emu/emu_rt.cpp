@@ -16,8 +16,8 @@ double emu_now_ms() { return std::chrono::duration<double, std::milli>(std::chro
 namespace emu {
 namespace {
 // kernels that call __syncthreads(): their blocks run as teams of real threads; every other kernel runs its threads in a loop
-const char* kTeamKernels[] = {"step2d_kernel", "diag_cols_kernel", "diag_sum_kernel"};
-bool needs_team(const char* k) { for (const char* t : kTeamKernels) if (!strcmp(k, t)) return true; return false; }
+const char* kTeamKernels[] = {"step2d_kernel", "diag_cols_kernel", "diag_sum_kernel", "step3d_t_v6_kernel"};
+bool needs_team(const char* k) { for (const char* t : kTeamKernels) if (strstr(k, t)) return true; return false; }
 std::vector<double> g_smem(64 * 1024, 0.0);          // dynamic shared memory of the running block
 thread_local bool in_team = false;
 
@@ -26,6 +26,9 @@ struct Team {
   std::vector<std::thread> th; std::mutex mu; std::condition_variable cv_go, cv_done, cv_bar;
   const std::function<void()>* body = nullptr; dim3 bdim; long gen = 0; int nthr = 0, pending = 0; bool stop = false;
   int bar_count = 0, bar_live = 0; long bar_gen = 0;
+  struct Named { int count = 0; long gen = 0; } named[16];           // PTX named barriers 0..15
+  struct Vote { int count = 0; bool acc = false, result = false; long gen = 0; } vote[64];   // one per warp of the block
+  std::condition_variable cv_named;
   void worker(int w) {
     long seen = 0;
     for (;;) {
@@ -53,8 +56,26 @@ struct Team {
     ensure(n);
     std::unique_lock<std::mutex> lk(mu);
     body = &f; bdim = b; nthr = n; pending = n; bar_live = n; bar_count = 0; ++gen;
+    for (auto& q : named) q.count = 0;
+    for (auto& q : vote) { q.count = 0; q.acc = false; }
     cv_go.notify_all();
     cv_done.wait(lk, [&] { return pending == 0; });
+  }
+  void named_barrier(int id, int n, bool wait) {
+    std::unique_lock<std::mutex> lk(mu);
+    Named& b = named[id & 15];
+    const long g = b.gen;
+    if (++b.count == n) { b.count = 0; ++b.gen; cv_named.notify_all(); return; }
+    if (wait) cv_named.wait(lk, [&] { return b.gen != g; });
+  }
+  bool warp_any(int warp, bool pred) {
+    std::unique_lock<std::mutex> lk(mu);
+    Vote& v = vote[warp & 63];
+    const long g = v.gen;
+    v.acc = v.acc || pred;
+    if (++v.count == 32) { v.result = v.acc; v.acc = false; v.count = 0; ++v.gen; cv_named.notify_all(); return v.result; }
+    cv_named.wait(lk, [&] { return v.gen != g; });
+    return v.result;
   }
   void barrier() {
     std::unique_lock<std::mutex> lk(mu);
@@ -72,6 +93,15 @@ void barrier() {
   if (!in_team) { fprintf(stderr, "emu: __syncthreads() in a kernel that is not listed in kTeamKernels (tests/emu/emu_rt.cpp)\n"); abort(); }
   team().barrier();
 }
+void named_barrier(int id, int nthreads, bool wait) {
+  if (!in_team) { fprintf(stderr, "emu: named barrier outside a team kernel\n"); abort(); }
+  team().named_barrier(id, nthreads, wait);
+}
+bool warp_any(bool pred) {
+  if (!in_team) { fprintf(stderr, "emu: warp vote outside a team kernel\n"); abort(); }
+  const unsigned lin = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  return team().warp_any((int)(lin / 32), pred);
+}
 void run_grid(dim3 g, dim3 b, size_t smem, const char* kernel, const std::function<void()>& body) {
   if (smem > g_smem.size() * sizeof(double)) { fprintf(stderr, "emu: %zu bytes of dynamic shared memory requested by %s\n", smem, kernel); abort(); }
   gridDim = g; blockDim = b;
@@ -87,10 +117,9 @@ void run_grid(dim3 g, dim3 b, size_t smem, const char* kernel, const std::functi
 }
 }  // namespace emu
 
-// ---- not built for emulation: the warp-specialised step3d_t (named barriers, PTX loads) and its shuffle-based predecessor
-// decline, so k_step3d_t() runs the plain column kernel of k_tracer.cu (tests set ROMS_B200_STEP3D_T_V1=1); no transport.
-int k_step3d_t_v6(roms_b200_ctx*, int) { return 2; }
-int k_step3d_t_v4(roms_b200_ctx*, int) { fprintf(stderr, "emu: set ROMS_B200_STEP3D_T_V1=1 (k_step3d_t4.cu is not built for emulation)\n"); return 1; }
+// ---- not built for emulation: the shuffle-based column step3d_t (k_step3d_t4.cu, the fallback of the production kernel for
+// closed W/E walls and N < 4) and the halo transport.
+int k_step3d_t_v4(roms_b200_ctx*, int) { fprintf(stderr, "emu: k_step3d_t4.cu is not built for emulation (N < 4 or closed W/E walls)\n"); return 1; }
 int halo_exchange(roms_b200_ctx*, double* const*, const int*, int) { return 0; }
 int halo_allreduce_sum(roms_b200_ctx*, double*, int) { return 0; }
 extern "C" {

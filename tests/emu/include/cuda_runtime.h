@@ -4,7 +4,7 @@
 // with g++ and run on the host: the container this repository is developed in has no GPU, and a B200 box costs minutes per
 // call, so the per-point arithmetic of a kernel (loop bounds, stencil indices, operation order) is checked here bit-for-bit
 // against the oracle before it goes to the GPU.  What this does NOT check: anything about performance, races between
-// threads of different blocks (blocks run one after the other), PTX paths (k_step3d_t6.cu, k_halo.cu are not built).
+// threads of different blocks (blocks run one after the other), and the files that are not built (k_step3d_t4.cu, k_halo.cu).
 // The product library libroms_b200.so never includes this header; `roms_b200` never loads the emulation library.
 #pragma once
 #include <math.h>
@@ -23,6 +23,8 @@
 #define __launch_bounds__(...)
 #define __constant__
 #define __shared__ static
+#define __grid_constant__
+#define __align__(n)
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 { unsigned x, y, z; dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {} };
@@ -34,9 +36,14 @@ namespace emu {
 void run_grid(dim3 g, dim3 b, size_t smem, const char* kernel, const std::function<void()>& body);
 void barrier();
 void* dyn_smem();
+void named_barrier(int id, int nthreads, bool wait);     // PTX bar.sync / bar.arrive id, nthreads
+bool warp_any(bool pred);                                // __any_sync over the 32 lanes of the calling thread's warp
 }
 #define EMU_LAUNCH(kernel, g, b, smem, ...) emu::run_grid((g), (b), (smem), #kernel, [&]() { kernel(__VA_ARGS__); })
 inline void __syncthreads() { emu::barrier(); }
+inline void __syncwarp() {}
+inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline bool __any_sync(unsigned, bool pred) { return emu::warp_any(pred); }
 inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline int min(int a, int b) { return a < b ? a : b; }
@@ -54,6 +61,13 @@ inline const char* cudaGetErrorString(cudaError_t) { return "emulation"; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+enum cudaDeviceAttr { cudaDevAttrMaxSharedMemoryPerBlockOptin = 97, cudaDevAttrMultiProcessorCount = 16 };
+inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) {     // a B200; EMU_SM_COUNT changes the CTA count of persistent-style launches
+  if (a == cudaDevAttrMaxSharedMemoryPerBlockOptin) *v = 232448;
+  else { const char* e = getenv("EMU_SM_COUNT"); *v = e ? atoi(e) : 148; }
+  return cudaSuccess;
+}
 inline cudaError_t cudaMalloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? cudaSuccess : 2; }
 inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
 inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }

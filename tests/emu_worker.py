@@ -2,13 +2,14 @@
 Loads tests/emu/libroms_b200_emu.so (the kernel SOURCES of roms_b200/csrc built with g++, see tests/emu/include/cuda_runtime.h)
 in place of the CUDA library and runs the per-kernel parity protocol of tests/test_gpu_parity.py against the oracle.
 Runs in its own process because the switches it needs (no CUDA graph, no programmatic launch, column step3d_t) are read once
-per process by the library.   usage: emu_worker.py APP Lm Mm N NSTEPS"""
+per process by the library.   usage: emu_worker.py [driver] APP Lm Mm N NSTEPS [v6]"""
 import os
 import sys
 
 os.environ["ROMS_B200_NO_GRAPH"] = "1"
 os.environ["ROMS_B200_NO_PDL"] = "1"
-os.environ["ROMS_B200_STEP3D_T_V1"] = "1"
+if "v6" not in sys.argv:                      # "v6": step3d_t through the production kernel k_step3d_t6.cu (named barriers and
+    os.environ["ROMS_B200_STEP3D_T_V1"] = "1"  # the warp vote emulated by thread teams: slow), else the plain column kernel
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(HERE))

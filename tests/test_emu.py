@@ -2,7 +2,8 @@
 run through the same per-kernel parity protocol as tests/test_gpu_parity.py -- push the oracle's state, run ONE kernel entry
 point through the C ABI, compare every field of the mirror with the oracle.  This pins loop bounds, stencil indices and
 operation order of a kernel before it ever reaches a GPU (the build container has none).  It says nothing about speed, about
-races between blocks, or about the PTX-level kernels (step3d_t v6/v4, halo transport), which only the `-m gpu` tests cover.
+races between blocks, or about the kernels that are not built here (k_step3d_t4.cu, the halo transport), which only the
+`-m gpu` tests cover.  The production step3d_t (k_step3d_t6.cu) IS built: its PTX helpers have host alternates.
 The emulation library is test infrastructure: the product never loads it."""
 import os
 import subprocess
@@ -20,12 +21,18 @@ def emu_lib():
     return os.path.join(HERE, "emu", "libroms_b200_emu.so")
 
 
-# app, Lm, Mm, N, steps: UPWELLING (linear EOS, ana_vmix, t3dmix2_s) on a small channel; BENCHMARK (UNESCO EOS, KPP, bulk
-# fluxes, geopotential mixing, curvilinear terms) on ragged grids: Lm not a multiple of 32, fewer rows than a block, N = 30
-@pytest.mark.parametrize("app,Lm,Mm,N,steps", [(0, 24, 10, 8, 3), (1, 33, 9, 10, 3), (1, 70, 9, 30, 2)])
-def test_kernel_sources_match_oracle_on_cpu(emu_lib, app, Lm, Mm, N, steps):
-    r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py")] + [str(x) for x in (app, Lm, Mm, N, steps)],
-                       capture_output=True, text=True, timeout=600)
+# app, Lm, Mm, N, steps, step3d_t kernel, emulated SM count: UPWELLING (linear EOS, ana_vmix, t3dmix2_s) on a small channel;
+# BENCHMARK (UNESCO EOS, KPP, bulk fluxes, geopotential mixing, curvilinear terms) on ragged grids: Lm not a multiple of 32,
+# fewer rows than a block, N = 30.  "v6" = the production warp-specialised step3d_t (k_step3d_t6.cu: 10-18 warps per CTA as a
+# team of real threads, named barriers and the warp vote emulated); with 2-3 "SMs" a CTA marches many rows (ring reuse,
+# EMPTY barriers), with 148 every CTA gets one or two rows (start-up path).  "v1" = the plain column kernel.
+CASES = [(0, 24, 10, 8, 3, "v6", 3), (1, 33, 9, 10, 3, "v6", 2), (1, 70, 9, 30, 2, "v6", 148), (1, 33, 9, 10, 2, "v1", 148)]
+
+
+@pytest.mark.parametrize("app,Lm,Mm,N,steps,s3t,nsm", CASES)
+def test_kernel_sources_match_oracle_on_cpu(emu_lib, app, Lm, Mm, N, steps, s3t, nsm):
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py")] + [str(x) for x in (app, Lm, Mm, N, steps)] + [s3t],
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, EMU_SM_COUNT=str(nsm)))
     assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
@@ -45,8 +52,8 @@ def test_kernel_sources_memory_safe_under_asan(emu_lib):
     if not os.path.isabs(asan) or not os.path.exists(asan):
         pytest.skip("libasan not available")
     subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(HERE, "emu"), "ASAN=1"])
-    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0", EMU_WORKER_LIB="libroms_b200_emu_asan.so")
-    r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "1", "33", "9", "10", "2"], capture_output=True, text=True,
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0", EMU_WORKER_LIB="libroms_b200_emu_asan.so", EMU_SM_COUNT="2")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "1", "33", "9", "10", "2", "v6"], capture_output=True, text=True,
                        timeout=900, env=env)
     assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout and "AddressSanitizer" not in r.stderr, r.stdout[-2000:] + r.stderr[-4000:]
 
