@@ -198,7 +198,8 @@ int k_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew) {
   // (the shared-memory column variants v2/v3 and the TMA-tensor variant v5 of the first session were slower or broken and are gone).
   static const bool use_v1 = (getenv("ROMS_B200_STEP3D_T_V1") != nullptr);   // first (local-memory) version
   static const bool use_v4 = (getenv("ROMS_B200_STEP3D_T_V4") != nullptr);   // one-thread-per-column checkpointed Thomas
-  if (!use_v1 && !use_v4) { const int rc = k_step3d_t_v6(c, nnew); if (rc != 2) return rc; }
+  static const bool use_v7 = (getenv("ROMS_B200_STEP3D_T_V7") != nullptr);   // experimental variant of v6 (k_step3d_t7.cu)
+  if (!use_v1 && !use_v4) { const int rc = use_v7 ? k_step3d_t_v7(c, nnew) : k_step3d_t_v6(c, nnew); if (rc != 2) return rc; }
   if (!use_v1) return k_step3d_t_v4(c, nnew);
   const roms_b200_bounds& b = c->D.b;
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT;

@@ -75,5 +75,6 @@ for line in open(src):
     if "<<<" in line and not line.lstrip().startswith("//"):
         line = rewrite_launches(line)
     line = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?double\s+(\w+)\s*\[\s*\]\s*;", r"double* \1 = (double*)emu::dyn_smem();", line)
+    line = re.sub(r'#include\s+"(\w+)\.cu"', r'#include "\1.cpp"', line)      # a .cu that includes another .cu: use its rewritten copy
     out.append(line)
 open(dst, "w").write('#line 1 "%s"\n' % src + "".join(out))

@@ -16,7 +16,7 @@ double emu_now_ms() { return std::chrono::duration<double, std::milli>(std::chro
 namespace emu {
 namespace {
 // kernels that call __syncthreads(): their blocks run as teams of real threads; every other kernel runs its threads in a loop
-const char* kTeamKernels[] = {"step2d_kernel", "diag_cols_kernel", "diag_sum_kernel", "step3d_t_v6_kernel"};
+const char* kTeamKernels[] = {"step2d_kernel", "diag_cols_kernel", "diag_sum_kernel", "step3d_t_v6_kernel", "step3d_t_v7_kernel"};
 bool needs_team(const char* k) { for (const char* t : kTeamKernels) if (strstr(k, t)) return true; return false; }
 std::vector<double> g_smem(64 * 1024, 0.0);          // dynamic shared memory of the running block
 thread_local bool in_team = false;
@@ -68,6 +68,15 @@ struct Team {
     if (++b.count == n) { b.count = 0; ++b.gen; cv_named.notify_all(); return; }
     if (wait) cv_named.wait(lk, [&] { return b.gen != g; });
   }
+  double shbuf[64][32];
+  double warp_shfl(int warp, int lane, double v, int src) {          // two rendezvous: all lanes have written / all lanes have read
+    { std::unique_lock<std::mutex> lk(mu); shbuf[warp & 63][lane] = v; }
+    (void)warp_any(warp, false);
+    double r;
+    { std::unique_lock<std::mutex> lk(mu); r = shbuf[warp & 63][src & 31]; }
+    (void)warp_any(warp, false);
+    return r;
+  }
   bool warp_any(int warp, bool pred) {
     std::unique_lock<std::mutex> lk(mu);
     Vote& v = vote[warp & 63];
@@ -102,6 +111,14 @@ bool warp_any(bool pred) {
   const unsigned lin = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
   return team().warp_any((int)(lin / 32), pred);
 }
+void sync_warp() { if (in_team) (void)warp_any(false); }
+int lane_id() { return (int)((threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)) & 31); }
+double warp_shfl(double v, int src) {
+  if (!in_team) { fprintf(stderr, "emu: warp shuffle outside a team kernel\n"); abort(); }
+  const unsigned lin = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  return team().warp_shfl((int)(lin / 32), (int)(lin & 31), v, src);
+}
+void yield() { std::this_thread::yield(); }
 void run_grid(dim3 g, dim3 b, size_t smem, const char* kernel, const std::function<void()>& body) {
   if (smem > g_smem.size() * sizeof(double)) { fprintf(stderr, "emu: %zu bytes of dynamic shared memory requested by %s\n", smem, kernel); abort(); }
   gridDim = g; blockDim = b;

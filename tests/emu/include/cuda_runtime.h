@@ -38,12 +38,18 @@ void barrier();
 void* dyn_smem();
 void named_barrier(int id, int nthreads, bool wait);     // PTX bar.sync / bar.arrive id, nthreads
 bool warp_any(bool pred);                                // __any_sync over the 32 lanes of the calling thread's warp
+void yield();
 }
 #define EMU_LAUNCH(kernel, g, b, smem, ...) emu::run_grid((g), (b), (smem), #kernel, [&]() { kernel(__VA_ARGS__); })
 inline void __syncthreads() { emu::barrier(); }
-inline void __syncwarp() {}
+namespace emu { void sync_warp(); double warp_shfl(double v, int src_lane); int lane_id(); }
+inline double __shfl_sync(unsigned, double v, int src) { return emu::warp_shfl(v, src); }
+inline double __shfl_up_sync(unsigned, double v, unsigned d) { const int l = emu::lane_id(); return emu::warp_shfl(v, l - (int)d >= 0 ? l - (int)d : l); }
+inline double __shfl_down_sync(unsigned, double v, unsigned d) { const int l = emu::lane_id(); return emu::warp_shfl(v, l + (int)d <= 31 ? l + (int)d : l); }
+inline void __syncwarp() { emu::sync_warp(); }              // rendezvous of the 32 lanes (team kernels), no-op in loop mode
 inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline bool __any_sync(unsigned, bool pred) { return emu::warp_any(pred); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline int min(int a, int b) { return a < b ? a : b; }

@@ -26,7 +26,10 @@ def emu_lib():
 # fewer rows than a block, N = 30.  "v6" = the production warp-specialised step3d_t (k_step3d_t6.cu: 10-18 warps per CTA as a
 # team of real threads, named barriers and the warp vote emulated); with 2-3 "SMs" a CTA marches many rows (ring reuse,
 # EMPTY barriers), with 148 every CTA gets one or two rows (start-up path).  "v1" = the plain column kernel.
-CASES = [(0, 24, 10, 8, 3, "v6", 3), (1, 33, 9, 10, 3, "v6", 2), (1, 70, 9, 30, 2, "v6", 148), (1, 33, 9, 10, 2, "v1", 148)]
+# "v7" = the experimental build of the same source (k_step3d_t7.cu: producers decoupled through a per-slot counter, x-neighbours
+# by warp shuffle on full stripes, loads on the ragged last stripe), opt-in on the GPU with ROMS_B200_STEP3D_T_V7=1.
+CASES = [(0, 24, 10, 8, 3, "v6", 3), (1, 33, 9, 10, 3, "v6", 2), (1, 70, 9, 30, 2, "v6", 148), (1, 33, 9, 10, 2, "v1", 148),
+         (1, 70, 9, 30, 1, "v7", 2)]
 
 
 @pytest.mark.parametrize("app,Lm,Mm,N,steps,s3t,nsm", CASES)

@@ -194,6 +194,32 @@ def test_tile_kernels_on_ragged_shapes(Lm, Mm, N):
     ctx.close()
 
 
+def test_experimental_step3d_t_variant_matches_production():
+    """k_step3d_t7.cu (same source as the production kernel, S3T_EXP=1: decoupled staggered producers, x-neighbours by warp
+    shuffle) must give the bits of the production kernel; it is selected per process, so it runs in a child process."""
+    import os
+    import subprocess
+    import sys
+    if not os.environ.get("ROMS_B200_TEST_V7"):
+        pytest.skip("experimental kernel, never run on hardware yet (spin-waits): set ROMS_B200_TEST_V7=1 to include it")
+    code = ("import sys, os; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np, oracle_lib as ol\n"
+            "from parity_common import make_pair, push\n"
+            "for (Lm, Mm, N) in ((70, 9, 30), (96, 40, 30), (45, 7, 50), (20, 6, 8)):\n"
+            "    o, ctx = make_pair(ol.BENCHMARK, Lm, Mm, N)\n"
+            "    o.step(2)\n"
+            "    for ph in ol.PHASES[:ol.PHASES.index('step3d_t')]: o.phase(ph)\n"
+            "    push(o, ctx); s = o.stepping()\n"
+            "    ctx.call('step3d_t', s['nrhs'], s['nstp'], s['nnew']); ctx.sync()\n"
+            "    o.phase('step3d_t')\n"
+            "    assert np.array_equal(o.get('t'), ctx.download('t')), (Lm, Mm, N)\n"
+            "    ctx.close()\n"
+            "print('V7-OK')\n") % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, ROMS_B200_STEP3D_T_V7="1"))
+    assert r.returncode == 0 and "V7-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
 def test_blown_up_state_raises_error_word():
     """Error behaviour of the boundary: a state the reference's diag would reject (Hz = 0 -> 1/Hz not finite) must not be
     silently 'fixed' by the branch-free reciprocal of step3d_t: the device error word is raised and roms_b200_sync returns
