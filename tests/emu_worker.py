@@ -112,8 +112,63 @@ def driver():
     print("EMU-DRIVER-OK app=%d %dx%dx%d steps=%d" % (app, Lm, Mm, N, nsteps))
 
 
+def tiles():
+    """Tiling invariance on the emulated kernels (the reference's acceptance criterion, ROMS/Bin/verify.sh): NtileI x NtileJ ranks,
+    one host thread and one mirror each, halo swaps as in-process copies (tests/emu/emu_rt.cpp), against ONE tile."""
+    import threading
+    app, Lm, Mm, N, nsteps, nti, ntj = (int(x) for x in sys.argv[2:9])
+    one = rb.Driver(rb.default_config(app, Lm, Mm, N))
+    one.run(nsteps)
+    one.ctx._bounds = one.bounds()
+    cfg = rb.default_config(app, Lm, Mm, N)
+    cfg.NtileI, cfg.NtileJ = nti, ntj
+    world = nti * ntj
+    ds = [rb.Driver(cfg, tile=r) for r in range(world)]
+    for r, d in enumerate(ds):
+        d.comm_init(r, world, bytes(128))
+        d.ctx._bounds = d.bounds()
+    errs, diags = [], [None] * world
+
+    def work(r, fn):
+        try:
+            fn(r)
+        except Exception as e:      # noqa: BLE001
+            errs.append((r, repr(e)))
+
+    def par(fn):
+        th = [threading.Thread(target=work, args=(r, fn)) for r in range(world)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errs, errs
+
+    par(lambda r: ds[r].run(nsteps))
+    fields = [("zeta", 1, 1, 1), ("zeta", 2, 1, 1), ("ubar", 1, 1, 1), ("vbar", 2, 1, 1), ("u", 1, 1, N), ("u", 2, 1, N), ("v", 1, 1, N),
+              ("v", 2, 1, N), ("t", 1, 1, N), ("t", 2, 1, N), ("t", 1, 2, N), ("t", 2, 2, N), ("wvel", 1, 1, N + 1), ("Akv", 1, 1, N + 1),
+              ("W", 1, 1, N + 1), ("Huon", 1, 1, N), ("rho", 1, 1, N)]
+    bad = []
+    for n, l, m, nk in fields:
+        ref = one.ctx.download_interior(n, l, m, nk)
+        for d in ds:
+            b = d.ctx._bounds
+            if not np.array_equal(d.ctx.download_interior(n, l, m, nk), ref[:, b.Jstr - 1:b.Jend, b.Istr - 1:b.Iend]):
+                bad.append((n, l, m, (b.Itile, b.Jtile)))
+    assert not bad, bad
+
+    def last(r):
+        ds[r].run(1, host_forcing=True)
+        diags[r] = ds[r].ctx.diag_last()
+    par(last)
+    one.run(1, host_forcing=True)
+    ref = one.ctx.diag_last()
+    for dg in diags:
+        assert np.allclose(dg[:3], ref[:3], rtol=1e-13, atol=0.0) and np.array_equal(dg[3:], ref[3:]), (dg, ref)
+    print("EMU-TILES-OK app=%d %dx%dx%d steps=%d tiles=%dx%d" % (app, Lm, Mm, N, nsteps, nti, ntj))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "driver":
+    if sys.argv[1] == "tiles":
+        tiles()
+    elif sys.argv[1] == "driver":
         driver()
     else:
         main()

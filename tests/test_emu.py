@@ -39,6 +39,19 @@ def test_kernel_sources_match_oracle_on_cpu(emu_lib, app, Lm, Mm, N, steps, s3t,
     assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+# app, Lm, Mm, N, steps, NtileI, NtileJ: the tilings of the scaling run (2x1, 2x2, 4x2) and an N-S split, against ONE tile
+@pytest.mark.parametrize("app,Lm,Mm,N,steps,nti,ntj", [(1, 48, 24, 10, 2, 2, 1), (1, 48, 24, 10, 2, 2, 2), (1, 64, 32, 8, 2, 4, 2),
+                                                       (1, 48, 36, 10, 2, 1, 2), (0, 40, 24, 8, 3, 2, 2)])
+def test_tiling_invariance_on_emulated_kernels(emu_lib, app, Lm, Mm, N, steps, nti, ntj):
+    """ROMS/Bin/verify.sh: results must not depend on the tiling.  Every rank is a host thread with its own mirror, the halo
+    swaps of k_halo.cu are in-process copies along roms_b200_halo_plan (tests/emu/emu_rt.cpp): checks the distributed LOGIC
+    (tile bounds, redundant evaluation on halos, deep-halo predictor, what is swapped when, diag's gather) bit for bit,
+    including wvel, Akv, W, Huon, rho and the 13 diag outputs."""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "tiles"] + [str(x) for x in (app, Lm, Mm, N, steps, nti, ntj)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "EMU-TILES-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_host_driver_on_emulated_kernels(emu_lib):
     """ROMS_initialize / ROMS_run (C++ host driver, roms_b200/csrc/host_driver.cpp) over the emulated kernels: start state, the
     device-resident loop, the host-forcing loop with diag read back every step and the blow-up stop -- all bit-identical to
@@ -55,7 +68,8 @@ def test_kernel_sources_memory_safe_under_asan(emu_lib):
     if not os.path.isabs(asan) or not os.path.exists(asan):
         pytest.skip("libasan not available")
     subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(HERE, "emu"), "ASAN=1"])
-    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0", EMU_WORKER_LIB="libroms_b200_emu_asan.so", EMU_SM_COUNT="2")
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0", EMU_WORKER_LIB="libroms_b200_emu_asan.so", EMU_SM_COUNT="2",
+               EMU_TEAM="threads")          # AddressSanitizer does not follow swapcontext: OS-thread teams
     r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "1", "33", "9", "10", "2", "v6"], capture_output=True, text=True,
                        timeout=900, env=env)
     assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout and "AddressSanitizer" not in r.stderr, r.stdout[-2000:] + r.stderr[-4000:]
