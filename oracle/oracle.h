@@ -6,12 +6,16 @@
 // statement (same loop bounds, same operation order); the file:line of the
 // Fortran it follows is cited at each function.
 //
-// PARITY UNPINNED: the reference ships no golden vectors, no test data and no
+// PARITY UNPINNED, with one exception: the reference ships no test data and no
 // expected logs for this path, and no Fortran compiler
 // exists in this image, so this restatement cannot be checked against reference
-// output.  Pins we do have: tiling invariance (1x1 == 2x2 == 4x2 bit-for-bit,
-// the reference's own verify.sh criterion), volume/tracer conservation and
-// self-consistency tests under tests/.
+// output.  The exception is the only known-answer vector in the reference
+// sources for this path, the "Check Values" of the equation of state in the
+// header of ROMS/Nonlinear/rho_eos.F:21-29 (T=3, S=35.5, Z=-5000 m): rho_eos()
+// reproduces den, den1, alpha and beta to the 14 digits printed there
+// (tests/test_cpu.py).  Other pins: tiling invariance (1x1 == 2x2 == 4x2
+// bit-for-bit, the reference's own verify.sh criterion), volume/tracer
+// conservation and self-consistency tests under tests/.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference
 // legs may load this library.  The product (roms_b200/) never links it.

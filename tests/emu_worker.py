@@ -165,8 +165,21 @@ def tiles():
     print("EMU-TILES-OK app=%d %dx%dx%d steps=%d tiles=%dx%d" % (app, Lm, Mm, N, nsteps, nti, ntj))
 
 
+def eos():
+    """rho_eos_kernel (emulated) against the reference's own check values, rho_eos.F:21-29."""
+    from parity_common import eos_check_state, eos_check_compare, push
+    o, ctx = make_pair(ol.BENCHMARK, 32, 16, 10)
+    o.phase("begin")
+    N, nj, ni, nrhs = eos_check_state(o)
+    push(o, ctx)
+    ctx.call("rho_eos", nrhs); ctx.sync()
+    print("EMU-EOS-OK", eos_check_compare(ctx.download, N, nj, ni))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "tiles":
+    if sys.argv[1] == "eos":
+        eos()
+    elif sys.argv[1] == "tiles":
         tiles()
     elif sys.argv[1] == "driver":
         driver()

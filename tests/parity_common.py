@@ -93,3 +93,34 @@ def run_phase_gpu(o, ctx, ph):
         ctx.call(name, *argf(s))
     ctx.sync()
     return None
+
+
+# The one known-answer vector the reference holds for this path: the header of ROMS/Nonlinear/rho_eos.F:21-29,
+# "Check Values: (T=3 C, S=35.5 PSU, Z=-5000 m)" of the Jackett & McDougall (1995) equation of state.
+EOS_CHECK = {"den": 1050.3639165364, "den1": 1028.2845117925, "alpha": 2.1014611551470e-04, "beta": 7.2575037309946e-04}
+
+
+def eos_check_state(o):
+    """Put T=3, S=35.5, z_r=-5000 into the surface level of the oracle's state (alpha, beta are evaluated there,
+    rho_eos.F:426-470) and return the indices of an interior point plus the array shapes."""
+    d = o.dims()
+    N, ni, nj = d["N"], d["UBi"] - d["LBi"] + 1, d["UBj"] - d["LBj"] + 1
+    nrhs = o.stepping()["nrhs"]
+    t = o.get("t").reshape(2, 3, N, nj, ni)
+    t[0, nrhs - 1, N - 1] = 3.0
+    t[1, nrhs - 1, N - 1] = 35.5
+    o.set("t", t)
+    zr = o.get("z_r").reshape(N, nj, ni)
+    zr[N - 1] = -5000.0
+    o.set("z_r", zr)
+    return N, nj, ni, nrhs
+
+
+def eos_check_compare(get, N, nj, ni):
+    """`get(name)` returns a field after rho_eos ran on the state above; compare with the reference's printed digits."""
+    j, i = nj // 2, ni // 2
+    got = {"den": get("rho").reshape(N, nj, ni)[N - 1, j, i] + 1000.0, "den1": get("pden").reshape(N, nj, ni)[N - 1, j, i] + 1000.0,
+           "alpha": get("alpha").reshape(nj, ni)[j, i], "beta": get("beta").reshape(nj, ni)[j, i]}
+    for k, ref in EOS_CHECK.items():
+        assert abs(got[k] / ref - 1.0) < 5e-14, (k, got[k], ref)      # the header prints 14 significant digits
+    return got

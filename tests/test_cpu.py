@@ -103,6 +103,17 @@ def test_oracle_wvelocity_and_courant():
     assert np.array_equal(w[:, :, 2 + Lm + 1], w[:, :, 2 + 1]) and np.array_equal(w[:, 0, :], w[:, 1, :]) and np.array_equal(w[:, Mm + 1, :], w[:, Mm, :])
 
 
+def test_oracle_eos_matches_the_reference_check_values():
+    """The only known-answer vector the reference ships for this path (rho_eos.F:21-29): T=3, S=35.5, Z=-5000 m ->
+    den, den1, alpha, beta to the 14 digits printed there.  Pins the nonlinear equation of state of the oracle."""
+    from parity_common import eos_check_state, eos_check_compare
+    o = run(ol.BENCHMARK, Lm=32, Mm=16, N=10)
+    o.phase("begin")
+    N, nj, ni, nrhs = eos_check_state(o)
+    o.phase("rho_eos")
+    eos_check_compare(o.get, N, nj, ni)
+
+
 def test_oracle_regression_pins():
     """Self-generated regression values (NOT reference output): tests/golden/make_golden.py."""
     with open(os.path.join(ROOT, "tests", "golden", "oracle_pins.json")) as f:

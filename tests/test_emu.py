@@ -52,6 +52,11 @@ def test_tiling_invariance_on_emulated_kernels(emu_lib, app, Lm, Mm, N, steps, n
     assert r.returncode == 0 and "EMU-TILES-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+def test_emulated_rho_eos_matches_the_reference_check_values(emu_lib):
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "eos"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "EMU-EOS-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_host_driver_on_emulated_kernels(emu_lib):
     """ROMS_initialize / ROMS_run (C++ host driver, roms_b200/csrc/host_driver.cpp) over the emulated kernels: start state, the
     device-resident loop, the host-forcing loop with diag read back every step and the blow-up stop -- all bit-identical to

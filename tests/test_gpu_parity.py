@@ -194,6 +194,18 @@ def test_tile_kernels_on_ragged_shapes(Lm, Mm, N):
     ctx.close()
 
 
+def test_rho_eos_matches_the_reference_check_values():
+    """rho_eos_kernel through the C ABI against the reference's own check values (rho_eos.F:21-29), not against the oracle."""
+    from parity_common import eos_check_state, eos_check_compare
+    o, ctx = make_pair(ol.BENCHMARK, 32, 16, 10)
+    o.phase("begin")
+    N, nj, ni, nrhs = eos_check_state(o)
+    push(o, ctx)
+    ctx.call("rho_eos", nrhs); ctx.sync()
+    eos_check_compare(ctx.download, N, nj, ni)
+    ctx.close()
+
+
 def test_experimental_step3d_t_variant_matches_production():
     """k_step3d_t7.cu (same source as the production kernel, S3T_EXP=1: decoupled staggered producers, x-neighbours by warp
     shuffle) must give the bits of the production kernel; it is selected per process, so it runs in a child process."""
