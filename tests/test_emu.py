@@ -28,8 +28,10 @@ def emu_lib():
 # EMPTY barriers), with 148 every CTA gets one or two rows (start-up path).  "v1" = the plain column kernel.
 # "v7" = the experimental build of the same source (k_step3d_t7.cu: producers decoupled through a per-slot counter, x-neighbours
 # by warp shuffle on full stripes, loads on the ragged last stripe), opt-in on the GPU with ROMS_B200_STEP3D_T_V7=1.
-CASES = [(0, 24, 10, 8, 3, "v6", 3), (1, 33, 9, 10, 3, "v6", 2), (1, 70, 9, 30, 2, "v6", 148), (1, 33, 9, 10, 2, "v1", 148),
-         (1, 70, 9, 30, 1, "v7", 2)]
+CASES = [(0, 24, 10, 8, 3, "v6", 3), (0, 0, 0, 0, 2, "v6", 148),                       # UPWELLING small and as shipped (41x80x16)
+         (1, 20, 6, 8, 3, "v6", 2), (1, 33, 5, 9, 3, "v6", 2), (1, 70, 9, 30, 3, "v6", 148), (1, 45, 7, 50, 2, "v6", 2),
+         (1, 40, 6, 64, 2, "v6", 148),                                                      # the ragged shapes of the GPU tests
+         (1, 33, 9, 10, 2, "v1", 148), (1, 70, 9, 30, 2, "v7", 2), (1, 45, 7, 50, 1, "v7", 2)]
 
 
 @pytest.mark.parametrize("app,Lm,Mm,N,steps,s3t,nsm", CASES)
