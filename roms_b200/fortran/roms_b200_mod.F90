@@ -232,6 +232,90 @@
           real(c_double), intent(out) :: out13(13)
         END FUNCTION
 !
+!  Synchronisation + device error word (non-zero -> exit_flag=8), pieces of
+!  rhs3d, the whole fast loop (main3d.F:810-918, indx1 updated as the
+!  reference does) and the whole step on the mirror.
+!
+        integer(c_int) FUNCTION roms_b200_sync (ctx)                    &
+     &                          BIND(C, name='roms_b200_sync')
+          IMPORT
+          type(c_ptr), value :: ctx
+        END FUNCTION
+        integer(c_long) FUNCTION roms_b200_field_size (ctx, field)      &
+     &                          BIND(C, name='roms_b200_field_size')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: field
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_rhs3d_tile (ctx, nrhs)        &
+     &                          BIND(C, name='roms_b200_rhs3d_tile')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nrhs
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_t3dmix2 (ctx, nrhs, nstp,     &
+     &                                            nnew)                 &
+     &                          BIND(C, name='roms_b200_t3dmix2')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nrhs, nstp, nnew
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_uv3dmix2 (ctx, nrhs, nnew)    &
+     &                          BIND(C, name='roms_b200_uv3dmix2')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nrhs, nnew
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_step2d_loop (ctx, nstp, nnew, &
+     &                                   iic, ntfirst, indx1)           &
+     &                          BIND(C, name='roms_b200_step2d_loop')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nstp, nnew, iic, ntfirst
+          integer(c_int), intent(inout) :: indx1
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_main3d (ctx, nsteps,          &
+     &                                   analytic_forcing, with_diag)   &
+     &                          BIND(C, name='roms_b200_main3d')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: nsteps, analytic_forcing, with_diag
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_get_stepping (ctx, out6,      &
+     &                                                 time)            &
+     &                          BIND(C, name='roms_b200_get_stepping')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), intent(out) :: out6(6)   ! iic ntfirst nstp nnew nrhs indx1
+          real(c_double), intent(out) :: time
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_set_stepping (ctx, in6, time) &
+     &                          BIND(C, name='roms_b200_set_stepping')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), intent(in) :: in6(6)
+          real(c_double), value :: time
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_set_data (ctx, tdays)         &
+     &                          BIND(C, name='roms_b200_set_data')
+          IMPORT
+          type(c_ptr), value :: ctx
+          real(c_double), value :: tdays
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_download_interior (ctx,       &
+     &                             field, plane0, nplanes, host)        &
+     &                    BIND(C, name='roms_b200_download_interior')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: field, plane0, nplanes
+          type(c_ptr), value :: host
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_comm_destroy (ctx)            &
+     &                          BIND(C, name='roms_b200_comm_destroy')
+          IMPORT
+          type(c_ptr), value :: ctx
+        END FUNCTION
+!
 !  Output path (output.F:217,703): asynchronous snapshot of nfields mirror
 !  fields into pinned host buffers (roms_b200_host_alloc); the time loop
 !  continues, roms_b200_snapshot_end waits before wrt_his / wrt_rst read them.
