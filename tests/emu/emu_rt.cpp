@@ -134,8 +134,17 @@ struct Fibers {
       f[w].ctx.uc_stack.ss_sp = stacks[w]; f[w].ctx.uc_stack.ss_size = kStack; f[w].ctx.uc_link = &sched;
       makecontext(&f[w].ctx, (void (*)())entry, 2, (unsigned)(me & 0xffffffffu), (unsigned)(me >> 32));
     }
-    while (live > 0)
-      for (int w = 0; w < n; ++w) if (!f[w].done) { cur = w; set_tid(w); swapcontext(&sched, &f[w].ctx); }
+    // EMU_SCHED_SEED=s: the threads of a block are resumed in a pseudo-random order that changes at every pass (whole warps
+    // stay together or not depending on the draw), to shake out orderings a round-robin schedule never produces
+    static const char* seed_env = getenv("EMU_SCHED_SEED");
+    static unsigned long long rng = seed_env ? (unsigned long long)atoll(seed_env) * 2654435761ull + 88172645463325252ull : 0;
+    std::vector<int> order(n);
+    for (int w = 0; w < n; ++w) order[w] = w;
+    while (live > 0) {
+      if (seed_env)
+        for (int w = n - 1; w > 0; --w) { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; std::swap(order[w], order[(int)(rng % (unsigned)(w + 1))]); }
+      for (int q = 0; q < n; ++q) { const int w = order[q]; if (!f[w].done) { cur = w; set_tid(w); swapcontext(&sched, &f[w].ctx); } }
+    }
     in_team = false;
   }
   void yield() { const int w = cur; swapcontext(&f[w].ctx, &sched); }         // the scheduler restores cur/threadIdx before resuming

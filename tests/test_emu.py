@@ -54,6 +54,15 @@ def test_tiling_invariance_on_emulated_kernels(emu_lib, app, Lm, Mm, N, steps, n
     assert r.returncode == 0 and "EMU-TILES-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("seed,s3t", [(1, "v6"), (2, "v7")])
+def test_step3d_t_synchronisation_under_random_schedules(emu_lib, seed, s3t):
+    """The warp-specialised step3d_t (ring slots, named barriers, per-slot counters in the experimental variant) with the threads
+    of a block resumed in a pseudo-random order at every scheduling pass: results must not depend on the schedule."""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "1", "70", "9", "30", "2", s3t], capture_output=True, text=True,
+                       timeout=900, env=dict(os.environ, EMU_SM_COUNT="2", EMU_SCHED_SEED=str(seed)))
+    assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_emulated_rho_eos_matches_the_reference_check_values(emu_lib):
     r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "eos"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "EMU-EOS-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
