@@ -376,9 +376,10 @@ __global__ void set_vbc_kernel(const Dev D, Box bx, int nrhs) {
   }
 }
 int k_set_vbc(roms_b200_ctx* c, int nrhs) {
-  const roms_b200_bounds& b = c->D.b;
+  // with neighbour tiles: also on two halo points (see k_bulk_flux), so stflx, btflx, bustr, bvstr need no halo swap
+  const Dev De = widened(c, 2); const roms_b200_bounds& b = De.b;
   Box bx{b.IstrR, b.IendR, b.JstrR, b.JendR}; dim3 blk(128, 2);
-  set_vbc_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(c->D, bx, nrhs); c->launches++;
+  set_vbc_kernel<<<grid2(bx, blk), blk, 0, c->stream>>>(De, bx, nrhs); c->launches++;
   return 0;
 }
 

@@ -319,13 +319,17 @@ int k_lmd_vmix(roms_b200_ctx* c, int nstp) {
   if (b.N < 3) return 1;
   static const KppC kc = {LMD_CSTAR * VONKAR * pow(LMD_CS * VONKAR * LMD_EPSILON, 1.0 / 3.0),
                           LMD_CV * sqrt(-LMD_BETAT) / (sqrt(LMD_CS * LMD_EPSILON) * LMD_RIC * VONKAR * VONKAR)};
-  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend};
+  // With neighbour tiles the column physics is also evaluated on the first ring of halo points (same inputs, same bits as the
+  // neighbour's interior): step3d_uv and pre_step3d read Akv at (i-1,j), (i,j-1), so the mp_exchange3d of Akv
+  // (lmd_vmix.F:640-650) needs no message.  Inputs reach one point further (u(i+1), sustr(i+1), ...): see k_bulk_flux / k_set_vbc.
+  const Dev De = widened(c, 1); const roms_b200_bounds& e = De.b;
+  Box bx{e.Istr, e.Iend, e.Jstr, e.Jend};
   dim3 blkc(32, 4), blkl(64, 4);
   dim3 gc = grid2(bx, blkc), gl = grid2(bx, blkl); gl.z = b.N + 1;
-  kpp_spline_kernel<<<gc, blkc, 0, c->stream>>>(c->D, bx, nstp); c->launches++;
-  kpp_levels_kernel<<<gl, blkl, 0, c->stream>>>(c->D, bx, nstp, kc); c->launches++;
-  kpp_sbl_kernel<<<gc, blkc, 0, c->stream>>>(c->D, bx); c->launches++;
-  kpp_finish_kernel<<<gl, blkl, 0, c->stream>>>(c->D, bx, kc); c->launches++;
+  kpp_spline_kernel<<<gc, blkc, 0, c->stream>>>(De, bx, nstp); c->launches++;
+  kpp_levels_kernel<<<gl, blkl, 0, c->stream>>>(De, bx, nstp, kc); c->launches++;
+  kpp_sbl_kernel<<<gc, blkc, 0, c->stream>>>(De, bx); c->launches++;
+  kpp_finish_kernel<<<gl, blkl, 0, c->stream>>>(De, bx, kc); c->launches++;
   return 0;
 }
 
@@ -455,11 +459,14 @@ __global__ void bulk_flux2_kernel(const Dev D, Box bx) {
   if (i >= b.IstrR && i <= b.IendR && j >= b.Jstr && j <= b.JendR) st(D, v2(D, FID(svstr)), i, j, cff * (Tauy(i, j - 1) + Tauy(i, j)));
 }
 int k_bulk_flux(roms_b200_ctx* c, int nrhs) {
-  const roms_b200_bounds& b = c->D.b;
+  // With neighbour tiles the fluxes are evaluated two points into the halo (point-wise in the surface state and the forcing,
+  // which are valid on the whole halo), so sustr, svstr, stflux need no halo swap: KPP on the first halo ring reads them one
+  // point further out.
+  const Dev De = widened(c, 2); const roms_b200_bounds& b = De.b;
   Box b1{b.Istr - 1, b.IendR, b.Jstr - 1, b.JendR}; dim3 blk(32, 4);
-  bulk_flux1_kernel<<<grid2(b1, blk), blk, 0, c->stream>>>(c->D, b1, nrhs); c->launches++;
+  bulk_flux1_kernel<<<grid2(b1, blk), blk, 0, c->stream>>>(De, b1, nrhs); c->launches++;
   Box b2{b.IstrR, b.IendR, b.JstrR, b.JendR};
-  bulk_flux2_kernel<<<grid2(b2, blk), blk, 0, c->stream>>>(c->D, b2); c->launches++;
+  bulk_flux2_kernel<<<grid2(b2, blk), blk, 0, c->stream>>>(De, b2); c->launches++;
   return 0;
 }
 

@@ -335,8 +335,11 @@ int roms_b200_main3d(roms_b200_ctx* c, int nsteps, int analytic_forcing, int wit
                                                                                  // the caller collects them with roms_b200_diag_end
     if (bench) k_bulk_flux(c, nrhs);
     k_set_vbc(c, nrhs);
-    { const XF x[4] = {xf2(FID(sustr)), xf2(FID(svstr)), xf2(FID(bustr)), xf2(FID(bvstr))}; if (xchg(c, x, 4)) return 1; }
-    if (bench) { if (k_lmd_vmix(c, nstp)) return 1; const XF x[1] = {xf3(c, FID(Akv))}; if (xchg(c, x, 1)) return 1; } else k_ana_vmix(c);
+    // no halo swap of the stresses (bulk_flux, set_vbc evaluated two points into the halo) nor of Akv (KPP evaluated on the
+    // first halo ring; ana_vmix on the whole mirror): ROMS_B200_SWAP_VBC=1 restores the two messages of the reference
+    static const bool swap_vbc = (getenv("ROMS_B200_SWAP_VBC") != nullptr);
+    if (swap_vbc) { const XF x[4] = {xf2(FID(sustr)), xf2(FID(svstr)), xf2(FID(bustr)), xf2(FID(bvstr))}; if (xchg(c, x, 4)) return 1; }
+    if (bench) { if (k_lmd_vmix(c, nstp)) return 1; if (swap_vbc) { const XF x[1] = {xf3(c, FID(Akv))}; if (xchg(c, x, 1)) return 1; } } else k_ana_vmix(c);
     k_omega(c);
     if (k_wvelocity(c, nstp)) return 1;                                    // main3d.F:535
     k_set_zeta(c);
