@@ -17,7 +17,7 @@ double emu_now_ms() { return std::chrono::duration<double, std::milli>(std::chro
 namespace emu {
 namespace {
 // kernels that call __syncthreads(): their blocks run as teams of real threads; every other kernel runs its threads in a loop
-const char* kTeamKernels[] = {"step2d_kernel", "diag_cols_kernel", "diag_sum_kernel", "step3d_t_v6_kernel", "step3d_t_v7_kernel"};
+const char* kTeamKernels[] = {"step2d_kernel", "diag_cols_kernel", "diag_sum_kernel", "step3d_t_v6_kernel", "step3d_t_v7_kernel", "step3d_t_v4_kernel"};
 bool needs_team(const char* k) { for (const char* t : kTeamKernels) if (strstr(k, t)) return true; return false; }
 std::vector<double> g_smem(64 * 1024, 0.0);          // dynamic shared memory of the running block
 thread_local bool in_team = false;
@@ -212,9 +212,7 @@ void run_grid(dim3 g, dim3 b, size_t smem, const char* kernel, const std::functi
 }
 }  // namespace emu
 
-// ---- not built for emulation: the shuffle-based column step3d_t (k_step3d_t4.cu, the fallback of the production kernel for
-// closed W/E walls and N < 4) and the halo transport.
-int k_step3d_t_v4(roms_b200_ctx*, int) { fprintf(stderr, "emu: k_step3d_t4.cu is not built for emulation (N < 4 or closed W/E walls)\n"); return 1; }
+// ---- not built for emulation: the halo transport (k_halo.cu); see the multi-tile emulation below.
 // ---- multi-tile emulation: every rank is a host thread of this process with its own context (mirror); the halo exchange of
 // k_halo.cu becomes a copy between the mirrors (each rank PULLS the blocks its eight neighbours would send, rectangles from
 // roms_b200_halo_plan, between two rendezvous of all ranks) and diag's all-reduce a sum over the ranks' buffers in rank order.

@@ -4,7 +4,8 @@
 // with g++ and run on the host: the container this repository is developed in has no GPU, and a B200 box costs minutes per
 // call, so the per-point arithmetic of a kernel (loop bounds, stencil indices, operation order) is checked here bit-for-bit
 // against the oracle before it goes to the GPU.  What this does NOT check: anything about performance, races between
-// threads of different blocks (blocks run one after the other), and the files that are not built (k_step3d_t4.cu, k_halo.cu).
+// threads of different blocks (blocks run one after the other), and the halo transport (k_halo.cu is not built; emu_rt.cpp
+replaces it by copies between the mirrors of the ranks of one process).
 // The product library libroms_b200.so never includes this header; `roms_b200` never loads the emulation library.
 #pragma once
 #include <math.h>

@@ -8,7 +8,9 @@ import sys
 
 os.environ["ROMS_B200_NO_GRAPH"] = "1"
 os.environ["ROMS_B200_NO_PDL"] = "1"
-if "v7" in sys.argv:                          # experimental variant of v6 (k_step3d_t7.cu)
+if "v4" in sys.argv:                          # the column-march fallback (closed W/E walls, N < 4): k_step3d_t4.cu
+    os.environ["ROMS_B200_STEP3D_T_V4"] = "1"
+elif "v7" in sys.argv:                        # experimental variant of v6 (k_step3d_t7.cu)
     os.environ["ROMS_B200_STEP3D_T_V7"] = "1"
 elif "v6" not in sys.argv:                      # "v6": step3d_t through the production kernel k_step3d_t6.cu (named barriers and
     os.environ["ROMS_B200_STEP3D_T_V1"] = "1"  # the warp vote emulated by thread teams: slow), else the plain column kernel

@@ -2,8 +2,8 @@
 run through the same per-kernel parity protocol as tests/test_gpu_parity.py -- push the oracle's state, run ONE kernel entry
 point through the C ABI, compare every field of the mirror with the oracle.  This pins loop bounds, stencil indices and
 operation order of a kernel before it ever reaches a GPU (the build container has none).  It says nothing about speed, about
-races between blocks, or about the kernels that are not built here (k_step3d_t4.cu, the halo transport), which only the
-`-m gpu` tests cover.  The production step3d_t (k_step3d_t6.cu) IS built: its PTX helpers have host alternates.
+races between blocks, or about the halo transport (k_halo.cu is not built; the multi-tile test replaces it by in-process
+copies), which only the GPU runs cover.  The production step3d_t (k_step3d_t6.cu) IS built: its PTX helpers have host alternates.
 The emulation library is test infrastructure: the product never loads it."""
 import os
 import subprocess
@@ -25,13 +25,14 @@ def emu_lib():
 # BENCHMARK (UNESCO EOS, KPP, bulk fluxes, geopotential mixing, curvilinear terms) on ragged grids: Lm not a multiple of 32,
 # fewer rows than a block, N = 30.  "v6" = the production warp-specialised step3d_t (k_step3d_t6.cu: 10-18 warps per CTA as a
 # team of real threads, named barriers and the warp vote emulated); with 2-3 "SMs" a CTA marches many rows (ring reuse,
-# EMPTY barriers), with 148 every CTA gets one or two rows (start-up path).  "v1" = the plain column kernel.
+# EMPTY barriers), with 148 every CTA gets one or two rows (start-up path).  "v1" = the plain column kernel, "v4" = the
+# shuffle-based column march (the production kernel's fallback for closed W/E walls and N < 4).
 # "v7" = the experimental build of the same source (k_step3d_t7.cu: producers decoupled through a per-slot counter, x-neighbours
 # by warp shuffle on full stripes, loads on the ragged last stripe), opt-in on the GPU with ROMS_B200_STEP3D_T_V7=1.
 CASES = [(0, 24, 10, 8, 3, "v6", 3), (0, 0, 0, 0, 2, "v6", 148),                       # UPWELLING small and as shipped (41x80x16)
          (1, 20, 6, 8, 3, "v6", 2), (1, 33, 5, 9, 3, "v6", 2), (1, 70, 9, 30, 3, "v6", 148), (1, 45, 7, 50, 2, "v6", 2),
          (1, 40, 6, 64, 2, "v6", 148),                                                      # the ragged shapes of the GPU tests
-         (1, 33, 9, 10, 2, "v1", 148), (1, 70, 9, 30, 2, "v7", 2), (1, 45, 7, 50, 1, "v7", 2)]
+         (1, 33, 9, 10, 2, "v1", 148), (1, 33, 9, 10, 2, "v4", 148), (1, 70, 9, 30, 2, "v7", 2), (1, 45, 7, 50, 1, "v7", 2)]
 
 
 @pytest.mark.parametrize("app,Lm,Mm,N,steps,s3t,nsm", CASES)
