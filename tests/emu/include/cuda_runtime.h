@@ -5,7 +5,7 @@
 // call, so the per-point arithmetic of a kernel (loop bounds, stencil indices, operation order) is checked here bit-for-bit
 // against the oracle before it goes to the GPU.  What this does NOT check: anything about performance, races between
 // threads of different blocks (blocks run one after the other), and the halo transport (k_halo.cu is not built; emu_rt.cpp
-replaces it by copies between the mirrors of the ranks of one process).
+// replaces it by copies between the mirrors of the ranks of one process).
 // The product library libroms_b200.so never includes this header; `roms_b200` never loads the emulation library.
 #pragma once
 #include <math.h>
