@@ -1,0 +1,558 @@
+// roms_b200/csrc/k_step3d_t8.cu -- step3d_t_tile as a TMA-fed, mbarrier-pipelined 2.5-D blocked sweep (production layout, sm_100a).
+//
+// Reference: Nonlinear/step3d_t.F:393-399 (1/Hz), :641-916 (U3 horizontal advection of t(3)), :1150-1365 (C4 vertical advection),
+// :1672-1721 (spline implicit vertical diffusion), t3dbc_im.F:334-341,415-422 + exchange_3d.F (wall rows, E-W periodic images).
+//
+// A persistent CTA (one per SM) takes work items = (i-stripe of 16 water columns) x (chunk of JCH rows) and marches along j.
+// NO thread of the compute warps ever loads from global memory: every operand is staged into shared memory by TMA
+// (cp.async.bulk.tensor.3d, j x k tiles of the 3-D volumes: box = {columns, 1 row, all N levels}) issued by one elected
+// thread a full row or more ahead, completion is signalled on mbarriers (expect_tx / complete_tx):
+//   * t(3) rows land in a 4-deep ring (rows j, j+1, j+2 in use, row j+3 in flight): the 5-point x/eta stencil and the 4-point
+//     vertical stencil read it with LDS; the eta-direction is rolled through registers (the north-face flux of row j is the
+//     south-face flux of row j+1), so each t(3) row is fetched once per stripe;
+//   * the read-once operands of a row (t(nnew) x2, Akt x2, Hz, Hvom(j+1), Huon, W) land in one of S "slots"; the slot is then
+//     worked on IN PLACE: producer warps (level-parallel, a warp = 16 columns x 2 levels, both tracers per thread) overwrite
+//     t(nnew) by q = (t(nnew) - dt*pm*pn*div F)/Hz and Hvom by 1/Hz; a consumer warp (lane = column x tracer) then runs the
+//     spline tridiagonal (Thomas, software-pipelined, operation order of the reference) out of the slot, parks CF/DC in the
+//     slot's dead Huon/W areas and writes t(nnew) with its periodic images and wall rows.
+// Slots and ring rows are recycled through full/ready/empty mbarriers; roles never meet at a CTA-wide barrier.
+// Per-point arithmetic (operation order, no FMA contraction, rcp_ieee == 1.0/x) is that of k_step3d_t6.cu, which is
+// bit-identical to the oracle; tests/emu runs this file on the CPU (mbarriers and TMA boxes emulated) before it goes to a GPU.
+#include "common.cuh"
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#ifndef ROMS_B200_EMU
+#include <cuda.h>       // CUtensorMap and its enums (types only: the encoder is fetched with cudaGetDriverEntryPoint)
+#endif
+
+namespace {
+constexpr int BI = 16;            // water columns per stripe (a half-warp)
+constexpr int TW = BI + 4;        // t(3) ring row: columns i0-2 .. i0+17
+constexpr int HUW = BI + 2;       // Huon row: columns i0 .. i0+17 (i0+16 is used; 18 keeps the box rows 16-byte multiples)
+constexpr int RING = 4;           // t(3) rows resident per stripe
+constexpr int MAXS = 8;           // most slots
+constexpr int LS = BI;            // doubles per level of a slot array
+__host__ __device__ constexpr int pad16(int n) { return (n + 15) & ~15; }
+
+#ifdef ROMS_B200_EMU
+struct TMap { const double* base; long dim[3]; long stride[3]; int box[3]; };   // strides in elements
+#else
+typedef CUtensorMap TMap;
+#endif
+
+struct alignas(64) A8 {
+  TMap t3[2], tw[2], ak[2], hz, hv, hu, w;      // tensor maps (3-D: i, j, k) of the volumes this launch reads
+  double* out[2];                               // t(:,:,:,nnew,itrc) volumes (stores)
+  const double *pm, *pn;
+  int* err;
+  double dt;
+  int N, ni, sk, LBi, LBj, Lm;
+  int i0, i1, ib, j0, j1, Jstr, Jend, wallS, wallN, wrapEW;   // ib: first column of stripe 0 (<= i0, see k_step3d_t_v8)
+  int nstripes, JCH, nitems, S, NC, NP;
+};
+
+// shared-memory layout of one slot (offsets in doubles; every TMA destination is a multiple of 16 doubles = 128 bytes)
+template <int NTR> struct Lay {
+  int N;
+  __host__ __device__ int q(int c) const { return c * N * LS; }                               // t(nnew) -> q           [N][16]
+  __host__ __device__ int ak(int c) const { return NTR * N * LS + c * (N + 1) * LS; }         // Akt, levels 0..N       [N+1][16]
+  __host__ __device__ int hz() const { return NTR * N * LS + NTR * (N + 1) * LS; }            // Hz                     [N][16]
+  __host__ __device__ int hv() const { return hz() + N * LS; }                                // Hvom(j+1) -> 1/Hz      [N][16]
+  __host__ __device__ int hu() const { return hv() + N * LS; }                                // Huon -> CF of tracer 0 [N][18]
+  __host__ __device__ int w() const { return hu() + pad16(N * HUW); }                         // W 0..N -> CF of tracer 1 [N+1][16]
+  __host__ __device__ int dc(int c) const { return w() + (N + 1) * LS + c * N * LS; }         // DC                     [N][16]
+  __host__ __device__ int slot() const { return dc(0) + NTR * N * LS; }
+  __host__ __device__ int cf(int c) const { return c == 0 ? hu() : w(); }
+  __host__ __device__ int ring_tr() const { return pad16(N * TW); }                           // one tracer of a ring row [N][20]
+  __host__ __device__ int ring_row() const { return NTR * ring_tr(); }
+  __host__ __device__ size_t bytes(int S) const { return 256 + 128 + sizeof(double) * ((size_t)RING * ring_row() + (size_t)S * slot()); }
+  __host__ __device__ unsigned slot_tx() const {                                              // bytes TMA delivers into a full slot
+    return 8u * (unsigned)(NTR * N * LS + NTR * (N + 1) * LS + N * LS + N * LS + N * HUW + (N + 1) * LS);
+  }
+};
+
+#ifdef ROMS_B200_EMU
+// ---- host emulation of mbarriers and TMA box loads (tests/emu): the threads of a block are cooperative fibers, a wait yields.
+// word: bit 63 phase, bits 48..62 arrival count per phase, bits 32..47 pending arrivals, bits 0..31 pending transaction bytes (signed)
+struct EmuBar { int32_t tx; uint16_t pending; uint16_t init_phase; };
+__device__ __forceinline__ EmuBar* eb(uint64_t* b) { return (EmuBar*)b; }
+__device__ __forceinline__ void eb_check(EmuBar* e) { if (e->pending == 0 && e->tx == 0) { e->pending = e->init_phase & 0x7fff; e->init_phase ^= 0x8000; } }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) { EmuBar* e = eb(b); e->tx = 0; e->pending = (uint16_t)count; e->init_phase = (uint16_t)count; }
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) { EmuBar* e = eb(b); if (e->pending == 0) abort(); --e->pending; eb_check(e); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) { EmuBar* e = eb(b); e->tx += (int32_t)bytes; if (e->pending == 0) abort(); --e->pending; eb_check(e); }
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int*) { while (((eb(b)->init_phase >> 15) & 1u) == parity) emu::yield(); }
+__device__ __forceinline__ void tma3d(double* dst, const TMap* m, int c0, int c1, int c2, uint64_t* bar) {
+  if ((c0 & 1) || ((uintptr_t)dst & 127)) { fprintf(stderr, "emu: TMA box start not 16-byte aligned in global memory (column %d) or destination not 128-byte aligned\n", c0); abort(); }
+  for (int z = 0; z < m->box[2]; ++z) for (int y = 0; y < m->box[1]; ++y) for (int x = 0; x < m->box[0]; ++x) {
+    const long X = c0 + x, Y = c1 + y, Z = c2 + z;
+    const bool in = X >= 0 && X < m->dim[0] && Y >= 0 && Y < m->dim[1] && Z >= 0 && Z < m->dim[2];
+    dst[((size_t)z * m->box[1] + y) * m->box[0] + x] = in ? m->base[X + m->stride[1] * Y + m->stride[2] * Z] : 0.0;
+  }
+  EmuBar* e = eb(bar); e->tx -= 8 * m->box[0] * m->box[1] * m->box[2]; eb_check(e);
+}
+__device__ __forceinline__ void fence_barrier_init() {}
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ double* align128(double* p) { return (double*)(((uintptr_t)p + 127) & ~(uintptr_t)127); }
+#else
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory"); }
+// try_wait suspends the warp in hardware until the phase completes or a time limit passes; a wait that lasts longer than
+// ~4 s (a lost arrival: a bug) raises the device error word and traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int* err) {
+  uint32_t ok; unsigned spins = 0; unsigned long long t0 = 0;
+  for (;;) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(s32(b)), "r"(parity) : "memory");
+    if (ok) return;
+    if ((++spins & 1023u) == 0) {
+      unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (!t0) t0 = t; else if (t - t0 > 4000000000ull) { atomicOr(err, 4); __threadfence(); asm volatile("trap;"); }
+    }
+  }
+}
+__device__ __forceinline__ void tma3d(double* dst, const TMap* m, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(s32(dst)), "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ double* align128(double* p) { return (double*)(((uintptr_t)p + 127) & ~(uintptr_t)127); }
+#endif
+
+// C4 vertical flux at w-level k from t(k-1),t(k),t(k+1),t(k+2) (step3d_t.F:1150-1185)
+__device__ __forceinline__ double vflux8(int k, int N, double tm1, double t0, double tp1, double tp2, double w) {
+  if (k <= 0 || k >= N) return 0.0;
+  if (k == 1) return w * (0.5 * t0 + (7.0 / 12.0) * tp1 - (1.0 / 12.0) * tp2);
+  if (k == N - 1) return w * (0.5 * tp1 + (7.0 / 12.0) * t0 - (1.0 / 12.0) * tm1);
+  return w * ((7.0 / 12.0) * (t0 + tp1) - (1.0 / 12.0) * (tm1 + tp2));
+}
+}  // namespace
+
+// KP: level-pair batches per producer warp (NP * KP >= ceil(N/2))
+template <int NTR, int KP>
+__global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_constant__ A8 a) {
+  extern __shared__ __align__(128) double sm_raw[];
+  double* sm = align128(sm_raw);
+  const int N = a.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int S = a.S, NC = a.NC, NP = a.NP;
+  uint64_t* ring_full = (uint64_t*)sm;          // [RING]  TMA has filled ring row
+  uint64_t* ring_empty = ring_full + RING;      // [RING]  every producer warp is done with the row
+  uint64_t* slot_full = ring_empty + RING;      // [MAXS]  TMA has filled the slot
+  uint64_t* slot_ready = slot_full + MAXS;      // [MAXS]  every producer warp has written q, 1/Hz
+  uint64_t* slot_empty = slot_ready + MAXS;     // [MAXS]  the consumer warp is done with the slot
+  const Lay<NTR> L{N};
+  const int trD = L.ring_tr(), rowD = L.ring_row(), slotD = L.slot();
+  double* ring = sm + 32;                       // 32 x 8 bytes of barriers
+  double* slots = ring + RING * rowD;
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < RING; ++q) { mbar_init(&ring_full[q], 1); mbar_init(&ring_empty[q], NP); }
+    for (int q = 0; q < MAXS; ++q) { mbar_init(&slot_full[q], 1); mbar_init(&slot_ready[q], NP); mbar_init(&slot_empty[q], 1); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const double dt = a.dt, c16 = 1.0 / 6.0;
+  int bad = 0;
+
+  if (warp == 0) {
+    // ======================= loader: one thread issues every TMA copy of the CTA =======================
+    if (lane == 0) {
+      unsigned g = 0, q = 0;                    // ring rows / slots issued so far
+      for (int it = blockIdx.x; it < a.nitems; it += gridDim.x) {
+        const int stripe = it % a.nstripes, chunk = it / a.nstripes;
+        const int i0s = a.ib + stripe * BI, ja = a.j0 + chunk * a.JCH, jb = min(ja + a.JCH - 1, a.j1);
+        const int nrows = jb - ja + 1, ci = i0s - a.LBi;
+        for (int r = 0; r < nrows + 4; ++r) {
+          const int n = ja - 2 + r;             // t(3) row that arrives at this step
+          {
+            const int buf = g % RING;
+            mbar_wait(&ring_empty[buf], ((g / RING) & 1u) ^ 1u, a.err);
+            mbar_arrive_expect_tx(&ring_full[buf], 8u * (unsigned)(NTR * N * TW));
+#pragma unroll
+            for (int c = 0; c < NTR; ++c) tma3d(ring + buf * rowD + c * trD, &a.t3[c], ci - 2, n - a.LBj, 0, &ring_full[buf]);
+            ++g;
+          }
+          if (r >= 3) {                         // operands of row j = n-2 (r == 3: the row below the chunk, only its Hvom(j+1) is needed)
+            const int cj = n - 2 - a.LBj, sl = q % S;
+            mbar_wait(&slot_empty[sl], ((q / S) & 1u) ^ 1u, a.err);
+            double* sp = slots + (size_t)sl * slotD;
+            if (r == 3) {
+              mbar_arrive_expect_tx(&slot_full[sl], 8u * (unsigned)(N * LS));
+              tma3d(sp + L.hv(), &a.hv, ci, cj + 1, 0, &slot_full[sl]);
+            } else {
+              mbar_arrive_expect_tx(&slot_full[sl], L.slot_tx());
+#pragma unroll
+              for (int c = 0; c < NTR; ++c) {
+                tma3d(sp + L.q(c), &a.tw[c], ci, cj, 0, &slot_full[sl]);
+                tma3d(sp + L.ak(c), &a.ak[c], ci, cj, 0, &slot_full[sl]);
+              }
+              tma3d(sp + L.hz(), &a.hz, ci, cj, 0, &slot_full[sl]);
+              tma3d(sp + L.hv(), &a.hv, ci, cj + 1, 0, &slot_full[sl]);
+              tma3d(sp + L.hu(), &a.hu, ci, cj, 0, &slot_full[sl]);
+              tma3d(sp + L.w(), &a.w, ci, cj, 0, &slot_full[sl]);
+            }
+            ++q;
+          }
+        }
+      }
+    }
+  } else if (warp > NC) {
+    // ======================= producers: advection, level-parallel =======================
+    const int p = warp - 1 - NC, h = lane >> 4, col = lane & 15;
+    double Cj[KP][NTR], FEs[KP][NTR];           // eta-direction carry per (batch, tracer): curv(j), FE(j) (south face of the next row)
+    unsigned g = 0, q = 0;
+    for (int it = blockIdx.x; it < a.nitems; it += gridDim.x) {
+      const int stripe = it % a.nstripes, chunk = it / a.nstripes;
+      const int i0s = a.ib + stripe * BI, ja = a.j0 + chunk * a.JCH, jb = min(ja + a.JCH - 1, a.j1);
+      const int nrows = jb - ja + 1;
+      const bool act = (i0s + col >= a.i0) && (i0s + col <= a.i1);
+      const int ic = min(max(i0s + col, a.i0), a.i1);   // idle lanes shadow an active column for the 2-D metric loads
+      const bool southw = a.wallS && ja == a.Jstr;
+      for (int r = 0; r < nrows + 4; ++r, ++g) {
+        const int n = ja - 2 + r;
+        mbar_wait(&ring_full[g % RING], (g / RING) & 1u, a.err);
+        if (r < 2) continue;
+        const double* R0 = ring + ((g - 2) % RING) * rowD + col + 2;    // row n-2
+        const double* R1 = ring + ((g - 1) % RING) * rowD + col + 2;    // row n-1
+        const double* R2 = ring + (g % RING) * rowD + col + 2;          // row n
+        if (r == 2) {
+          // start of a chunk, part 1 (rows ja-2, ja-1, ja): cm1 = curv(ja-1), e0 = FE-gradient at ja  (step3d_t.F:697-724)
+#pragma unroll
+          for (int m = 0; m < KP; ++m) {
+            const int kb = 2 * (p + m * NP) + 1;
+            if (kb > N) break;
+            const int o = (min(kb + h, N) - 1) * TW;
+#pragma unroll
+            for (int c = 0; c < NTR; ++c) {
+              const double tm2 = R0[c * trD + o], tm1 = R1[c * trD + o], tA = R2[c * trD + o];
+              const double e0 = tA - tm1;
+              const double em1 = southw ? e0 : (tm1 - tm2);           // FE(i,Jstr-1)=FE(i,Jstr) on the southern wall
+              Cj[m][c] = e0 - em1; FEs[m][c] = e0;
+            }
+          }
+        } else if (r == 3) {
+          // part 2 (rows ja-1, ja, ja+1; Hvom(ja) in the slot of the row below the chunk): FE(ja), curv(ja)
+          const int sl = q % S;
+          mbar_wait(&slot_full[sl], (q / S) & 1u, a.err);
+          const double* sp = slots + (size_t)sl * slotD;
+#pragma unroll
+          for (int m = 0; m < KP; ++m) {
+            const int kb = 2 * (p + m * NP) + 1;
+            if (kb > N) break;
+            const int kc = min(kb + h, N), o = (kc - 1) * TW;
+            const double hv = sp[L.hv() + (kc - 1) * LS + col];
+            const double hvx = hv > 0.0 ? hv : 0.0, hvn = hv < 0.0 ? hv : 0.0, hvh = hv * 0.5;
+#pragma unroll
+            for (int c = 0; c < NTR; ++c) {
+              const double tm1 = R0[c * trD + o], tA = R1[c * trD + o], tB = R2[c * trD + o];
+              const double e1 = tB - tA, c0 = e1 - FEs[m][c];
+              FEs[m][c] = hvh * (tm1 + tA) - c16 * (Cj[m][c] * hvx + c0 * hvn);
+              Cj[m][c] = c0;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&slot_ready[sl]);
+          ++q;
+        } else {
+          // ---- row j = n-2: q = (t(nnew) - dt*pm*pn*(div_h F + d_k FC)) / Hz  into the slot, in place
+          const int j = n - 2, sl = q % S;
+          const bool lastN = a.wallN && (j == a.Jend);                // FE(i,Jend+2)=FE(i,Jend+1) (step3d_t.F:718-724)
+          const int o2 = (ic - a.LBi) + a.ni * (j - a.LBj);
+          const double cff = dt * __ldg(a.pm + o2) * __ldg(a.pn + o2);
+          mbar_wait(&slot_full[sl], (q / S) & 1u, a.err);
+          double* sp = slots + (size_t)sl * slotD;
+#pragma unroll
+          for (int m = 0; m < KP; ++m) {
+            const int kb = 2 * (p + m * NP) + 1;
+            if (kb > N) break;
+            const int k = kb + h;
+            const bool valid = (k <= N);
+            const int kc = min(k, N), o = (kc - 1) * TW;
+            const int om2 = (max(kc - 2, 1) - 1) * TW, om1 = (max(kc - 1, 1) - 1) * TW, op1 = (min(kc + 1, N) - 1) * TW, op2 = (min(kc + 2, N) - 1) * TW;
+            // ---- load phase (shared memory only)
+            const int so = (kc - 1) * LS + col;
+            const double hu = sp[L.hu() + (kc - 1) * HUW + col], hup = sp[L.hu() + (kc - 1) * HUW + col + 1];
+            const double hvn_ = sp[L.hv() + so], hz = sp[L.hz() + so];
+            const double wk = sp[L.w() + kc * LS + col], wkm = sp[L.w() + (kc - 1) * LS + col];   // W: level index 0..N
+            double qm2[NTR], qm1[NTR], A[NTR], qp1[NTR], qp2[NTR], Bv[NTR], T2[NTR], tm2[NTR], tm1[NTR], tp1[NTR], tp2[NTR], twv[NTR];
+#pragma unroll
+            for (int c = 0; c < NTR; ++c) {
+              const double* pr = R0 + c * trD;
+              qm2[c] = pr[o - 2]; qm1[c] = pr[o - 1]; A[c] = pr[o]; qp1[c] = pr[o + 1]; qp2[c] = pr[o + 2];
+              tm2[c] = pr[om2]; tm1[c] = pr[om1]; tp1[c] = pr[op1]; tp2[c] = pr[op2];
+              Bv[c] = R1[c * trD + o]; T2[c] = R2[c * trD + o];
+              twv[c] = sp[L.q(c) + so];
+            }
+            // ---- compute phase (k_step3d_t6.cu: max/min(H,0) as compare+select, same values)
+            const double hux = hu > 0.0 ? hu : 0.0, hun = hu < 0.0 ? hu : 0.0, huh = hu * 0.5;
+            const double hpx = hup > 0.0 ? hup : 0.0, hpn = hup < 0.0 ? hup : 0.0, hph = hup * 0.5;
+            const double hvx = hvn_ > 0.0 ? hvn_ : 0.0, hvm = hvn_ < 0.0 ? hvn_ : 0.0, hvh = hvn_ * 0.5;
+            int badl = 0;
+            const double ohz = rcp_ieee(hz, badl);
+            if (act && valid) bad |= badl;
+#pragma unroll
+            for (int c = 0; c < NTR; ++c) {
+              const double d0 = qm1[c] - qm2[c], d1 = A[c] - qm1[c], d2 = qp1[c] - A[c], d3 = qp2[c] - qp1[c];
+              const double cvm = d1 - d0, cv0 = d2 - d1, cvp = d3 - d2;
+              const double FXi = huh * (qm1[c] + A[c]) - c16 * (cvm * hux + cv0 * hun);
+              const double FXp = hph * (A[c] + qp1[c]) - c16 * (cv0 * hpx + cvp * hpn);
+              const double e1 = Bv[c] - A[c];
+              const double e2 = lastN ? e1 : (T2[c] - Bv[c]);
+              const double c1 = e2 - e1;
+              const double FEn = hvh * (A[c] + Bv[c]) - c16 * (Cj[m][c] * hvx + c1 * hvm);
+              const double x1 = cff * (FXp - FXi), x2 = cff * (FEn - FEs[m][c]), x3 = x1 + x2;
+              double tv = twv[c] - x3;
+              const double FCm = vflux8(k - 1, N, tm2[c], tm1[c], A[c], tp1[c], wkm);
+              const double FCk = vflux8(k, N, tm1[c], A[c], tp1[c], tp2[c], wk);
+              const double cv = cff * (FCk - FCm);
+              tv = tv - cv;
+              if (valid) sp[L.q(c) + so] = tv * ohz;
+              Cj[m][c] = c1; FEs[m][c] = FEn;
+            }
+            if (valid) sp[L.hv() + so] = ohz;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&slot_ready[sl]);
+          ++q;
+        }
+        // ---- the oldest row of the ring is no longer needed (the last step of a chunk frees all three)
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&ring_empty[(g - 2) % RING]);
+          if (r == nrows + 3) { mbar_arrive(&ring_empty[(g - 1) % RING]); mbar_arrive(&ring_empty[g % RING]); }
+        }
+      }
+    }
+  } else {
+    // ======================= consumers: spline tridiagonal per (column, tracer) =======================
+    const int cw = warp - 1, col = lane & 15, c = (NTR == 2) ? (lane >> 4) : 0;
+    const bool dup = (NTR == 1) && lane >= 16;                        // one tracer: the upper half-warp only shadows the lower one
+    const double c13 = 1.0 / 3.0;
+    const int ni = a.ni, sk = a.sk, Lm = a.Lm;
+    unsigned q = 0;
+    for (int it = blockIdx.x; it < a.nitems; it += gridDim.x) {
+      const int stripe = it % a.nstripes, chunk = it / a.nstripes;
+      const int i0s = a.ib + stripe * BI, ja = a.j0 + chunk * a.JCH, jb = min(ja + a.JCH - 1, a.j1);
+      const int nrows = jb - ja + 1, i = i0s + col;
+      const bool act = (i >= a.i0) && (i <= a.i1) && !dup;
+      const bool wE = a.wrapEW && i >= 1 && i <= 2, wW = a.wrapEW && i >= Lm - 2 && i <= Lm;
+      for (int rr = -1; rr < nrows; ++rr, ++q) {
+        if ((int)(q % (unsigned)NC) != cw) continue;
+        const int sl = q % S;
+        mbar_wait(&slot_ready[sl], (q / S) & 1u, a.err);
+        if (rr >= 0) {
+          const int j = ja + rr;
+          double* sp = slots + (size_t)sl * slotD;
+          const double* pq = sp + L.q(c) + col;          // q(k)    at pq[(k-1)*LS]
+          const double* pa = sp + L.ak(c) + col;         // Akt(k)  at pa[k*LS], k = 0..N
+          const double* ph = sp + L.hz() + col;          // Hz(k)   at ph[(k-1)*LS]
+          const double* po = sp + L.hv() + col;          // 1/Hz(k) at po[(k-1)*LS]
+          double* pcf = sp + L.cf(c) + col;              // CF(k)   at pcf[(k-1)*LS]
+          double* pdc = sp + L.dc(c) + col;              // DC(k)   at pdc[(k-1)*LS]
+          // Software-pipelined forward elimination (k_step3d_t6.cu): while the recurrence of level k runs (mul, add, rcp, mul:
+          // ~90 cycles of dependent latency), the coefficients FC,CF,BC,dq of level k+1 are formed and the operands of level
+          // k+2 are fetched (level N+1 does not exist: the clamped index re-reads level N, the values are not used).
+          double dtakK, hzN, ohzN, c16N, dtakN, qN, akN;
+          double FC, CF, BC, dq;
+          {
+            const double hz1 = ph[0], ohz1 = po[0], ak1 = pa[LS], q1 = pq[0], ak0 = pa[0];
+            hzN = ph[LS]; ohzN = po[LS]; akN = pa[2 * LS]; qN = pq[LS];
+            dtakK = dt * ak1; c16N = c16 * hzN; dtakN = dt * akN;
+            FC = c16 * hz1 - dt * ak0 * ohz1;                            // 1/6*Hz(k)   - dt*Akt(k-1)*oHz(k)
+            CF = c16N - dtakN * ohzN;                                    // 1/6*Hz(k+1) - dt*Akt(k+1)*oHz(k+1)
+            BC = c13 * (hz1 + hzN) + dtakK * (ohz1 + ohzN);
+            dq = qN - q1;
+          }
+          double cf_prev = 0.0, dc_prev = 0.0;
+          double ak_top = akN, q_top = qN, ohz_top = ohzN;
+          int badl = 0;
+#pragma unroll 4
+          for (int k = 1; k <= N - 1; ++k) {
+            ak_top = akN; q_top = qN; ohz_top = ohzN;                    // level k+1 (== N on the last pass)
+            const int lv = min(k + 2, N);
+            const double hzL = ph[(lv - 1) * LS], ohzL = po[(lv - 1) * LS], akL = pa[lv * LS], qL = pq[(lv - 1) * LS];
+            const double cf = rcp_ieee(BC - FC * cf_prev, badl);
+            cf_prev = cf * CF;
+            dc_prev = cf * (dq - FC * dc_prev);
+            pcf[(k - 1) * LS] = cf_prev; pdc[(k - 1) * LS] = dc_prev;
+            const double c16L = c16 * hzL, dtakL = dt * akL;
+            FC = c16N - dtakK * ohzN;
+            CF = c16L - dtakL * ohzL;
+            BC = c13 * (hzN + hzL) + dtakN * (ohzN + ohzL);
+            dq = qL - qN;
+            dtakK = dtakN; hzN = hzL; ohzN = ohzL; c16N = c16L; dtakN = dtakL; qN = qL; akN = akL;
+          }
+          if (act) bad |= badl;
+          // back substitution + final update, level N first
+          const bool south = a.wallS && j == a.Jstr, north = a.wallN && j == a.Jend;
+          double* tw = a.out[c] + ((i - a.LBi) + (size_t)ni * (j - a.LBj)) + (size_t)sk * (N - 1);   // t(nnew)(i,j,N)
+          double dc_next = 0.0;                                          // DC(N)
+          double a_next = dc_next * ak_top;                              // DC(N)*Akt(N)
+          double q_next = q_top, dtohz_next = dt * ohz_top;
+          double Xk = pcf[(N - 2) * LS], Yk = pdc[(N - 2) * LS], akk = pa[(N - 1) * LS], qk = pq[(N - 2) * LS], ohzk = po[(N - 2) * LS];
+          const bool plain = !__any_sync(0xffffffffu, wE || wW || south || north);   // interior stripe and row: one store per level
+          auto put = [&](double out) {                                   // st() + t3dbc wall rows (t3dbc_im.F:334-341,415-422)
+            if (act) {
+              tw[0] = out;
+              if (!plain) {
+                if (wE) tw[Lm] = out;
+                if (wW) tw[-Lm] = out;
+                if (south) { tw[-ni] = out; if (wE) tw[Lm - ni] = out; if (wW) tw[-Lm - ni] = out; }
+                if (north) { tw[ni] = out; if (wE) tw[Lm + ni] = out; if (wW) tw[-Lm + ni] = out; }
+              }
+            }
+            tw -= sk;
+          };
+#pragma unroll 4
+          for (int k = N - 1; k >= 1; --k) {
+            const int lv = max(k - 1, 1);
+            const double Xm = pcf[(lv - 1) * LS], Ym = pdc[(lv - 1) * LS], akm = pa[lv * LS], qm = pq[(lv - 1) * LS], ohzm = po[(lv - 1) * LS];
+            const double dc_k = Yk - Xk * dc_next;
+            const double a_k = dc_k * akk;
+            put(q_next + dtohz_next * (a_next - a_k));                   // level k+1
+            dc_next = dc_k; a_next = a_k; q_next = qk; dtohz_next = dt * ohzk;
+            Xk = Xm; Yk = Ym; akk = akm; qk = qm; ohzk = ohzm;
+          }
+          put(q_next + dtohz_next * (a_next - 0.0));                     // level 1; DC(0)=0 is not scaled by Akt
+        }
+        fence_proxy_async();                     // generic-proxy accesses of the slot are ordered before the TMA refill
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&slot_empty[sl]);
+      }
+    }
+  }
+  if (bad) atomicOr(a.err, 1);
+}
+
+namespace {
+#ifndef ROMS_B200_EMU
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr; static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr; cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+#endif
+// tensor map of a (ni, nj, nk) fp64 volume, box = (bw, 1, bk)
+int make_map(TMap* m, const double* base, int ni, int nj, int nk, int bw, int bk) {
+#ifdef ROMS_B200_EMU
+  m->base = base; m->dim[0] = ni; m->dim[1] = nj; m->dim[2] = nk; m->stride[0] = 1; m->stride[1] = ni; m->stride[2] = (long)ni * nj;
+  m->box[0] = bw; m->box[1] = 1; m->box[2] = bk;
+  return 0;
+#else
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return 2;
+  const cuuint64_t dim[3] = {(cuuint64_t)ni, (cuuint64_t)nj, (cuuint64_t)nk};
+  const cuuint64_t str[2] = {(cuuint64_t)ni * 8, (cuuint64_t)ni * nj * 8};
+  const cuuint32_t box[3] = {(cuuint32_t)bw, 1, (cuuint32_t)bk}, es[3] = {1, 1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { fprintf(stderr, "roms_b200: cuTensorMapEncodeTiled failed (%d) for a %dx%dx%d volume, box %dx1x%d\n", (int)r, ni, nj, nk, bw, bk); return 2; }
+  return 0;
+#endif
+}
+
+template <int NTR, int KP>
+int launch_v8(roms_b200_ctx* c, const A8& a, int grid, size_t smem) {
+  static size_t set = 0;
+  if (smem > set) { CUDA_OK(cudaFuncSetAttribute(step3d_t_v8_kernel<NTR, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = smem; }
+  step3d_t_v8_kernel<NTR, KP><<<dim3(grid), dim3(32 * (1 + a.NC + a.NP)), smem, c->stream>>>(a);
+  return 0;
+}
+}  // namespace
+
+// returns 0 on success, 2 if this layout does not apply (caller falls back to k_step3d_t6.cu / k_step3d_t4.cu)
+int k_step3d_t_v8(roms_b200_ctx* c, int nnew) {
+  const Dev& D = c->D; const roms_b200_bounds& b = D.b;
+  const int N = b.N;
+  if (N < 4 || N > 254) return 2;
+  if (!b.EWperiodic && (b.Western_Edge || b.Eastern_Edge)) return 2;     // closed W/E walls: FX edge copies not implemented here
+  if (D.nij * (size_t)(N + 1) >= (size_t)1 << 31) return 2;              // 32-bit element offsets inside one volume
+  if (D.ni & 1) return 2;                                                // TMA: global strides must be multiples of 16 bytes
+  static int max_smem = -1, nsm = 148;
+  if (max_smem < 0) {
+    int dev = 0; cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) max_smem = 48 * 1024;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  static const int force_s = getenv("ROMS_B200_S3T_SLOTS") ? atoi(getenv("ROMS_B200_S3T_SLOTS")) : 0;
+  static const int force_np = getenv("ROMS_B200_S3T_NP") ? atoi(getenv("ROMS_B200_S3T_NP")) : 0;
+  static const int force_jch = getenv("ROMS_B200_S3T_JCH") ? atoi(getenv("ROMS_B200_S3T_JCH")) : 0;
+  for (int itr0 = 1; itr0 <= b.NT; itr0 += 2) {
+    const int ntr = (itr0 + 1 <= b.NT) ? 2 : 1;
+    // slots: as many as fit (at most 6); consumers: every slot that is neither being loaded nor being produced
+    int S = 0;
+    for (int s = (force_s ? force_s : 6); s >= 2 && !S; --s) {
+      const size_t need = (ntr == 2) ? Lay<2>{N}.bytes(s) : Lay<1>{N}.bytes(s);
+      if (need <= (size_t)max_smem) S = s;
+    }
+    if (!S) return 2;
+    const int NC = S >= 4 ? S - 2 : 1;
+    // producer warps x level-pair batches per warp: NP*KP >= ceil(N/2), at most 12 warps per CTA (170 registers per thread)
+    const int nb = (N + 1) / 2;
+    int KP = 0, NP = 0;
+    for (int kp = 1; kp <= 4 && !KP; kp *= 2) {
+      const int np = force_np ? force_np : (nb + kp - 1) / kp;
+      if (np * kp >= nb && 1 + NC + np <= 12) { KP = kp; NP = np; }
+    }
+    if (!KP) return 2;
+    // TMA: the first element of a box must be 16-byte aligned in global memory (measured on B200, tools/ubench/tma3d_test.cu: an odd
+    // fp64 start column raises "illegal instruction"), so stripes start at an even array column; a column left of Istr is masked
+    const int ib = b.Istr - ((b.Istr - b.LBi) & 1);
+    const int rows = b.Jend - b.Jstr + 1, nstripes = (b.Iend - ib + BI) / BI;
+    // j-chunks: persistent CTAs take items round-robin; cost ~ rounds * (rows per chunk + ~2 rows of pipeline start-up)
+    int best_jch = rows; long best = -1;
+    for (int nc = 1; nc <= rows; ++nc) {
+      const int jch = (rows + nc - 1) / nc, ncr = (rows + jch - 1) / jch;
+      if (jch < 4 && nc > 1) break;
+      const long items = (long)nstripes * ncr, rounds = (items + nsm - 1) / nsm;
+      const long cost = rounds * (jch + 2);
+      if (best < 0 || cost < best) { best = cost; best_jch = jch; }
+    }
+    if (force_jch) best_jch = force_jch;
+    A8 a;
+    memset(&a, 0, sizeof(a));
+    a.N = N; a.ni = D.ni; a.sk = (int)D.nij; a.LBi = b.LBi; a.LBj = b.LBj; a.Lm = b.Lm;
+    a.i0 = b.Istr; a.i1 = b.Iend; a.ib = ib; a.j0 = b.Jstr; a.j1 = b.Jend; a.Jstr = b.Jstr; a.Jend = b.Jend;
+    a.wallS = b.Southern_Edge && !b.NSperiodic; a.wallN = b.Northern_Edge && !b.NSperiodic; a.wrapEW = D.wrapEW;
+    a.nstripes = nstripes; a.JCH = best_jch; a.nitems = nstripes * ((rows + best_jch - 1) / best_jch);
+    a.S = S; a.NC = NC; a.NP = NP; a.dt = D.p.dt; a.err = D.err;
+    a.pm = D.f[FID(pm)]; a.pn = D.f[FID(pn)];
+    const size_t vol = D.nij * (size_t)N;
+    int rc = 0;
+    for (int qt = 0; qt < ntr; ++qt) {
+      const int itrc = itr0 + qt;
+      const double* t3 = D.f[FID(t)] + vol * ((3 - 1) + (size_t)3 * (itrc - 1));
+      double* tw = D.f[FID(t)] + vol * ((nnew - 1) + (size_t)3 * (itrc - 1));
+      const double* ak = D.f[FID(Akt)] + D.nij * (size_t)(N + 1) * (size_t)((itrc <= b.NAT ? itrc : b.NAT) - 1);
+      a.out[qt] = tw;
+      rc |= make_map(&a.t3[qt], t3, D.ni, D.nj, N, TW, N);
+      rc |= make_map(&a.tw[qt], tw, D.ni, D.nj, N, BI, N);
+      rc |= make_map(&a.ak[qt], ak, D.ni, D.nj, N + 1, BI, N + 1);
+    }
+    rc |= make_map(&a.hz, D.f[FID(Hz)], D.ni, D.nj, N, BI, N);
+    rc |= make_map(&a.hv, D.f[FID(Hvom)], D.ni, D.nj, N, BI, N);
+    rc |= make_map(&a.hu, D.f[FID(Huon)], D.ni, D.nj, N, HUW, N);
+    rc |= make_map(&a.w, D.f[FID(W)], D.ni, D.nj, N + 1, BI, N + 1);
+    if (rc) return 2;
+    const int grid = a.nitems < nsm ? a.nitems : nsm;
+    static const bool verbose = (getenv("ROMS_B200_S3T_VERBOSE") != nullptr);
+    if (verbose) fprintf(stderr, "step3d_t v8: N=%d ntr=%d stripes=%d JCH=%d items=%d grid=%d slots=%d consumers=%d producers=%dx%d smem=%zu\n", N, ntr, nstripes,
+                         a.JCH, a.nitems, grid, S, NC, NP, KP, (ntr == 2) ? Lay<2>{N}.bytes(S) : Lay<1>{N}.bytes(S));
+    const size_t smem = (ntr == 2) ? Lay<2>{N}.bytes(S) : Lay<1>{N}.bytes(S);
+    if (ntr == 2) {
+      if (KP == 1) rc = launch_v8<2, 1>(c, a, grid, smem); else if (KP == 2) rc = launch_v8<2, 2>(c, a, grid, smem); else rc = launch_v8<2, 4>(c, a, grid, smem);
+    } else {
+      if (KP == 1) rc = launch_v8<1, 1>(c, a, grid, smem); else if (KP == 2) rc = launch_v8<1, 2>(c, a, grid, smem); else rc = launch_v8<1, 4>(c, a, grid, smem);
+    }
+    if (rc) return rc;
+    c->launches++;
+  }
+  return 0;
+}

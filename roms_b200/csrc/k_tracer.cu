@@ -199,6 +199,8 @@ int k_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew) {
   static const bool use_v1 = (getenv("ROMS_B200_STEP3D_T_V1") != nullptr);   // first (local-memory) version
   static const bool use_v4 = (getenv("ROMS_B200_STEP3D_T_V4") != nullptr);   // one-thread-per-column checkpointed Thomas
   static const bool use_v7 = (getenv("ROMS_B200_STEP3D_T_V7") != nullptr);   // experimental variant of v6 (k_step3d_t7.cu)
+  static const bool no_v8 = (getenv("ROMS_B200_S3T_V8") != nullptr && atoi(getenv("ROMS_B200_S3T_V8")) == 0);   // TMA/mbarrier layout (k_step3d_t8.cu)
+  if (!use_v1 && !use_v4 && !use_v7 && !no_v8) { const int rc = k_step3d_t_v8(c, nnew); if (rc != 2) return rc; }
   if (!use_v1 && !use_v4) { const int rc = use_v7 ? k_step3d_t_v7(c, nnew) : k_step3d_t_v6(c, nnew); if (rc != 2) return rc; }
   if (!use_v1) return k_step3d_t_v4(c, nnew);
   const roms_b200_bounds& b = c->D.b;

@@ -12,8 +12,10 @@ if "v4" in sys.argv:                          # the column-march fallback (close
     os.environ["ROMS_B200_STEP3D_T_V4"] = "1"
 elif "v7" in sys.argv:                        # experimental variant of v6 (k_step3d_t7.cu)
     os.environ["ROMS_B200_STEP3D_T_V7"] = "1"
-elif "v6" not in sys.argv:                      # "v6": step3d_t through the production kernel k_step3d_t6.cu (named barriers and
-    os.environ["ROMS_B200_STEP3D_T_V1"] = "1"  # the warp vote emulated by thread teams: slow), else the plain column kernel
+elif "v6" in sys.argv:                        # the round-1 production kernel k_step3d_t6.cu (named barriers, warp vote emulated)
+    os.environ["ROMS_B200_S3T_V8"] = "0"
+elif "v8" not in sys.argv:                    # "v8": the production kernel k_step3d_t8.cu (mbarriers and TMA boxes emulated),
+    os.environ["ROMS_B200_STEP3D_T_V1"] = "1"  # else the plain column kernel
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(HERE))
