@@ -33,6 +33,7 @@ constexpr int HUW = BI + 2;       // Huon row: columns i0 .. i0+17 (i0+16 is use
 constexpr int RING = 4;           // t(3) rows resident per stripe
 constexpr int MAXS = 8;           // most slots
 constexpr int LS = BI;            // doubles per level of a slot array
+constexpr int RPAD = 48;          // doubles in front of the ring: the vertical stencil of level 1 reaches two (unused) levels below a row
 __host__ __device__ constexpr int pad16(int n) { return (n + 15) & ~15; }
 
 #ifdef ROMS_B200_EMU
@@ -66,7 +67,7 @@ template <int NTR> struct Lay {
   __host__ __device__ int cf(int c) const { return c == 0 ? hu() : w(); }
   __host__ __device__ int ring_tr() const { return pad16(N * TW); }                           // one tracer of a ring row [N][20]
   __host__ __device__ int ring_row() const { return NTR * ring_tr(); }
-  __host__ __device__ size_t bytes(int S) const { return 256 + 128 + sizeof(double) * ((size_t)RING * ring_row() + (size_t)S * slot()); }
+  __host__ __device__ size_t bytes(int S) const { return 256 + 128 + sizeof(double) * (RPAD + (size_t)RING * ring_row() + (size_t)S * slot()); }
   __host__ __device__ unsigned slot_tx() const {                                              // bytes TMA delivers into a full slot
     return 8u * (unsigned)(NTR * N * LS + NTR * (N + 1) * LS + N * LS + N * LS + N * HUW + (N + 1) * LS);
   }
@@ -93,20 +94,25 @@ __device__ __forceinline__ void tma3d(double* dst, const TMap* m, int c0, int c1
 }
 __device__ __forceinline__ void fence_barrier_init() {}
 __device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ int __double2hiint(double x) { uint64_t u; memcpy(&u, &x, 8); return (int)(u >> 32); }
+__device__ __forceinline__ int __double2loint(double x) { uint64_t u; memcpy(&u, &x, 8); return (int)(u & 0xffffffffu); }
+__device__ __forceinline__ double __hiloint2double(int hi, int lo) { uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &u, 8); return x; }
 __device__ __forceinline__ double* align128(double* p) { return (double*)(((uintptr_t)p + 127) & ~(uintptr_t)127); }
 #else
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory"); }
-// try_wait suspends the warp in hardware until the phase completes or a time limit passes; a wait that lasts longer than
-// ~4 s (a lost arrival: a bug) raises the device error word and traps instead of hanging the GPU
+// try_wait suspends the warp in hardware until the phase completes or the time hint (ns) passes, so a waiting warp takes no
+// issue slots from the working warps of its scheduler; a wait that lasts longer than ~4 s (a lost arrival: a bug) raises the
+// device error word and traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int* err) {
   uint32_t ok; unsigned spins = 0; unsigned long long t0 = 0;
   for (;;) {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(s32(b)), "r"(parity) : "memory");
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(s32(b)), "r"(parity), "r"(20000u) : "memory");
     if (ok) return;
-    if ((++spins & 1023u) == 0) {
+    if ((++spins & 255u) == 0) {
       unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       if (!t0) t0 = t; else if (t - t0 > 4000000000ull) { atomicOr(err, 4); __threadfence(); asm volatile("trap;"); }
     }
@@ -118,8 +124,19 @@ __device__ __forceinline__ void tma3d(double* dst, const TMap* m, int c0, int c1
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ double* align128(double* p) { return (double*)(((uintptr_t)p + 127) & ~(uintptr_t)127); }
+// pointer arithmetic on the shared array (a round trip through uintptr_t would lose the address space: generic LD/ST instead of LDS/STS)
+__device__ __forceinline__ double* align128(double* p) { return p + (((128u - (s32(p) & 127u)) & 127u) >> 3); }
 #endif
+
+// max(h,0) and min(h,0) by masking with the sign: 5 integer instructions for both (the compare+select form is turned into
+// DSETP.MAX/MIN + NaN fix-ups by the compiler, ~6 each).  Same values as max/min up to the sign of a zero, which contributes
+// nothing to a flux (as in k_step3d_t6.cu).
+__device__ __forceinline__ void posneg(double h, double& hp, double& hn) {
+  const int hi = __double2hiint(h), lo = __double2loint(h);
+  const int m = hi >> 31;                       // all ones for a negative value
+  hp = __hiloint2double(hi & ~m, lo & ~m);
+  hn = __hiloint2double(hi & m, lo & m);
+}
 
 // C4 vertical flux at w-level k from t(k-1),t(k),t(k+1),t(k+2) (step3d_t.F:1150-1185)
 __device__ __forceinline__ double vflux8(int k, int N, double tm1, double t0, double tp1, double tp2, double w) {
@@ -129,6 +146,13 @@ __device__ __forceinline__ double vflux8(int k, int N, double tm1, double t0, do
   return w * ((7.0 / 12.0) * (t0 + tp1) - (1.0 / 12.0) * (tm1 + tp2));
 }
 }  // namespace
+
+// ring of n entries walked in order: index and phase parity without integer division
+struct Ring8 {
+  int i, n; unsigned ph;
+  __device__ __forceinline__ Ring8(int n_) : i(0), n(n_), ph(0) {}
+  __device__ __forceinline__ void next() { if (++i == n) { i = 0; ph ^= 1u; } }
+};
 
 // KP: level-pair batches per producer warp (NP * KP >= ceil(N/2))
 template <int NTR, int KP>
@@ -144,7 +168,7 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
   uint64_t* slot_empty = slot_ready + MAXS;     // [MAXS]  the consumer warp is done with the slot
   const Lay<NTR> L{N};
   const int trD = L.ring_tr(), rowD = L.ring_row(), slotD = L.slot();
-  double* ring = sm + 32;                       // 32 x 8 bytes of barriers
+  double* ring = sm + 32 + RPAD;                // 32 x 8 bytes of barriers, padding
   double* slots = ring + RING * rowD;
   if (threadIdx.x == 0) {
     for (int q = 0; q < RING; ++q) { mbar_init(&ring_full[q], 1); mbar_init(&ring_empty[q], NP); }
@@ -158,7 +182,7 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
   if (warp == 0) {
     // ======================= loader: one thread issues every TMA copy of the CTA =======================
     if (lane == 0) {
-      unsigned g = 0, q = 0;                    // ring rows / slots issued so far
+      Ring8 g(RING), q(S);                      // ring rows / slots issued so far
       for (int it = blockIdx.x; it < a.nitems; it += gridDim.x) {
         const int stripe = it % a.nstripes, chunk = it / a.nstripes;
         const int i0s = a.ib + stripe * BI, ja = a.j0 + chunk * a.JCH, jb = min(ja + a.JCH - 1, a.j1);
@@ -166,17 +190,16 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
         for (int r = 0; r < nrows + 4; ++r) {
           const int n = ja - 2 + r;             // t(3) row that arrives at this step
           {
-            const int buf = g % RING;
-            mbar_wait(&ring_empty[buf], ((g / RING) & 1u) ^ 1u, a.err);
-            mbar_arrive_expect_tx(&ring_full[buf], 8u * (unsigned)(NTR * N * TW));
+            mbar_wait(&ring_empty[g.i], g.ph ^ 1u, a.err);
+            mbar_arrive_expect_tx(&ring_full[g.i], 8u * (unsigned)(NTR * N * TW));
 #pragma unroll
-            for (int c = 0; c < NTR; ++c) tma3d(ring + buf * rowD + c * trD, &a.t3[c], ci - 2, n - a.LBj, 0, &ring_full[buf]);
-            ++g;
+            for (int c = 0; c < NTR; ++c) tma3d(ring + g.i * rowD + c * trD, &a.t3[c], ci - 2, n - a.LBj, 0, &ring_full[g.i]);
+            g.next();
           }
           if (r >= 3) {                         // operands of row j = n-2 (r == 3: the row below the chunk, only its Hvom(j+1) is needed)
-            const int cj = n - 2 - a.LBj, sl = q % S;
-            mbar_wait(&slot_empty[sl], ((q / S) & 1u) ^ 1u, a.err);
-            double* sp = slots + (size_t)sl * slotD;
+            const int cj = n - 2 - a.LBj, sl = q.i;
+            mbar_wait(&slot_empty[sl], q.ph ^ 1u, a.err);
+            double* sp = slots + sl * slotD;
             if (r == 3) {
               mbar_arrive_expect_tx(&slot_full[sl], 8u * (unsigned)(N * LS));
               tma3d(sp + L.hv(), &a.hv, ci, cj + 1, 0, &slot_full[sl]);
@@ -192,7 +215,7 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
               tma3d(sp + L.hu(), &a.hu, ci, cj, 0, &slot_full[sl]);
               tma3d(sp + L.w(), &a.w, ci, cj, 0, &slot_full[sl]);
             }
-            ++q;
+            q.next();
           }
         }
       }
@@ -201,7 +224,23 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
     // ======================= producers: advection, level-parallel =======================
     const int p = warp - 1 - NC, h = lane >> 4, col = lane & 15;
     double Cj[KP][NTR], FEs[KP][NTR];           // eta-direction carry per (batch, tracer): curv(j), FE(j) (south face of the next row)
-    unsigned g = 0, q = 0;
+    // per batch: level k; element offset of (level k, this column) inside one tracer of a ring row / inside a slot array / inside
+    // the Huon array.  The vertical neighbours k-2..k+2 sit at fixed distances; at k <= 2 and k >= N-1 they fall outside the
+    // tracer's levels (padding, the neighbouring tracer or row): those values are not used by the C4 flux at these levels.
+    int kk[KP], o0[KP], so[KP], sh[KP];
+#pragma unroll
+    for (int m = 0; m < KP; ++m) {
+      const int kb = 2 * (p + m * NP) + 1;
+      kk[m] = (kb <= N) ? kb + h : 0;           // 0: this warp has no such batch; N+1 (odd N): shadow of level N, not stored
+      const int kc = min(max(kk[m], 1), N);
+      o0[m] = (kc - 1) * TW + col + 2;
+      so[m] = (kc - 1) * LS + col;
+      sh[m] = (kc - 1) * HUW + col;
+    }
+    const int oq = L.q(0), dq_ = L.q(1) - L.q(0), ohz_ = L.hz(), ohv = L.hv(), ohu = L.hu(), ow = L.w();
+    int gi = 0;                                 // ring buffer of the row that arrives at this step
+    unsigned gph = 0;
+    Ring8 q(S);
     for (int it = blockIdx.x; it < a.nitems; it += gridDim.x) {
       const int stripe = it % a.nstripes, chunk = it / a.nstripes;
       const int i0s = a.ib + stripe * BI, ja = a.j0 + chunk * a.JCH, jb = min(ja + a.JCH - 1, a.j1);
@@ -209,23 +248,24 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
       const bool act = (i0s + col >= a.i0) && (i0s + col <= a.i1);
       const int ic = min(max(i0s + col, a.i0), a.i1);   // idle lanes shadow an active column for the 2-D metric loads
       const bool southw = a.wallS && ja == a.Jstr;
-      for (int r = 0; r < nrows + 4; ++r, ++g) {
-        const int n = ja - 2 + r;
-        mbar_wait(&ring_full[g % RING], (g / RING) & 1u, a.err);
+      int o2 = (ic - a.LBi) + a.ni * (ja - a.LBj);
+      for (int r = 0; r < nrows + 4; ++r) {
+        mbar_wait(&ring_full[gi], gph, a.err);
+        const int g0 = gi;                                            // row n
+        const int g1 = (gi + RING - 1) & (RING - 1), g2 = (gi + RING - 2) & (RING - 1);   // rows n-1, n-2
+        if (++gi == RING) { gi = 0; gph ^= 1u; }
         if (r < 2) continue;
-        const double* R0 = ring + ((g - 2) % RING) * rowD + col + 2;    // row n-2
-        const double* R1 = ring + ((g - 1) % RING) * rowD + col + 2;    // row n-1
-        const double* R2 = ring + (g % RING) * rowD + col + 2;          // row n
+        const double* R0 = ring + g2 * rowD;    // row n-2
+        const double* R1 = ring + g1 * rowD;    // row n-1
+        const double* R2 = ring + g0 * rowD;    // row n
         if (r == 2) {
           // start of a chunk, part 1 (rows ja-2, ja-1, ja): cm1 = curv(ja-1), e0 = FE-gradient at ja  (step3d_t.F:697-724)
 #pragma unroll
           for (int m = 0; m < KP; ++m) {
-            const int kb = 2 * (p + m * NP) + 1;
-            if (kb > N) break;
-            const int o = (min(kb + h, N) - 1) * TW;
+            if (kk[m] == 0) break;
 #pragma unroll
             for (int c = 0; c < NTR; ++c) {
-              const double tm2 = R0[c * trD + o], tm1 = R1[c * trD + o], tA = R2[c * trD + o];
+              const double tm2 = R0[c * trD + o0[m]], tm1 = R1[c * trD + o0[m]], tA = R2[c * trD + o0[m]];
               const double e0 = tA - tm1;
               const double em1 = southw ? e0 : (tm1 - tm2);           // FE(i,Jstr-1)=FE(i,Jstr) on the southern wall
               Cj[m][c] = e0 - em1; FEs[m][c] = e0;
@@ -233,19 +273,18 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
           }
         } else if (r == 3) {
           // part 2 (rows ja-1, ja, ja+1; Hvom(ja) in the slot of the row below the chunk): FE(ja), curv(ja)
-          const int sl = q % S;
-          mbar_wait(&slot_full[sl], (q / S) & 1u, a.err);
-          const double* sp = slots + (size_t)sl * slotD;
+          const int sl = q.i;
+          mbar_wait(&slot_full[sl], q.ph, a.err);
+          const double* sp = slots + sl * slotD;
 #pragma unroll
           for (int m = 0; m < KP; ++m) {
-            const int kb = 2 * (p + m * NP) + 1;
-            if (kb > N) break;
-            const int kc = min(kb + h, N), o = (kc - 1) * TW;
-            const double hv = sp[L.hv() + (kc - 1) * LS + col];
-            const double hvx = hv > 0.0 ? hv : 0.0, hvn = hv < 0.0 ? hv : 0.0, hvh = hv * 0.5;
+            if (kk[m] == 0) break;
+            const double hv = sp[ohv + so[m]];
+            double hvx, hvn; posneg(hv, hvx, hvn);
+            const double hvh = hv * 0.5;
 #pragma unroll
             for (int c = 0; c < NTR; ++c) {
-              const double tm1 = R0[c * trD + o], tA = R1[c * trD + o], tB = R2[c * trD + o];
+              const double tm1 = R0[c * trD + o0[m]], tA = R1[c * trD + o0[m]], tB = R2[c * trD + o0[m]];
               const double e1 = tB - tA, c0 = e1 - FEs[m][c];
               FEs[m][c] = hvh * (tm1 + tA) - c16 * (Cj[m][c] * hvx + c0 * hvn);
               Cj[m][c] = c0;
@@ -253,41 +292,38 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&slot_ready[sl]);
-          ++q;
+          q.next();
         } else {
           // ---- row j = n-2: q = (t(nnew) - dt*pm*pn*(div_h F + d_k FC)) / Hz  into the slot, in place
-          const int j = n - 2, sl = q % S;
+          const int j = ja + r - 4, sl = q.i;
           const bool lastN = a.wallN && (j == a.Jend);                // FE(i,Jend+2)=FE(i,Jend+1) (step3d_t.F:718-724)
-          const int o2 = (ic - a.LBi) + a.ni * (j - a.LBj);
           const double cff = dt * __ldg(a.pm + o2) * __ldg(a.pn + o2);
-          mbar_wait(&slot_full[sl], (q / S) & 1u, a.err);
-          double* sp = slots + (size_t)sl * slotD;
+          o2 += a.ni;
+          mbar_wait(&slot_full[sl], q.ph, a.err);
+          double* sp = slots + sl * slotD;
 #pragma unroll
           for (int m = 0; m < KP; ++m) {
-            const int kb = 2 * (p + m * NP) + 1;
-            if (kb > N) break;
-            const int k = kb + h;
+            if (kk[m] == 0) break;
+            const int k = kk[m];
             const bool valid = (k <= N);
-            const int kc = min(k, N), o = (kc - 1) * TW;
-            const int om2 = (max(kc - 2, 1) - 1) * TW, om1 = (max(kc - 1, 1) - 1) * TW, op1 = (min(kc + 1, N) - 1) * TW, op2 = (min(kc + 2, N) - 1) * TW;
             // ---- load phase (shared memory only)
-            const int so = (kc - 1) * LS + col;
-            const double hu = sp[L.hu() + (kc - 1) * HUW + col], hup = sp[L.hu() + (kc - 1) * HUW + col + 1];
-            const double hvn_ = sp[L.hv() + so], hz = sp[L.hz() + so];
-            const double wk = sp[L.w() + kc * LS + col], wkm = sp[L.w() + (kc - 1) * LS + col];   // W: level index 0..N
+            const int sm_ = so[m];
+            const double hu = sp[ohu + sh[m]], hup = sp[ohu + sh[m] + 1];
+            const double hvn_ = sp[ohv + sm_], hz = sp[ohz_ + sm_];
+            const double wk = sp[ow + sm_ + LS], wkm = sp[ow + sm_];    // W: level index 0..N
             double qm2[NTR], qm1[NTR], A[NTR], qp1[NTR], qp2[NTR], Bv[NTR], T2[NTR], tm2[NTR], tm1[NTR], tp1[NTR], tp2[NTR], twv[NTR];
 #pragma unroll
             for (int c = 0; c < NTR; ++c) {
-              const double* pr = R0 + c * trD;
-              qm2[c] = pr[o - 2]; qm1[c] = pr[o - 1]; A[c] = pr[o]; qp1[c] = pr[o + 1]; qp2[c] = pr[o + 2];
-              tm2[c] = pr[om2]; tm1[c] = pr[om1]; tp1[c] = pr[op1]; tp2[c] = pr[op2];
-              Bv[c] = R1[c * trD + o]; T2[c] = R2[c * trD + o];
-              twv[c] = sp[L.q(c) + so];
+              const double* pr = R0 + c * trD + o0[m];
+              qm2[c] = pr[-2]; qm1[c] = pr[-1]; A[c] = pr[0]; qp1[c] = pr[1]; qp2[c] = pr[2];
+              tm2[c] = pr[-2 * TW]; tm1[c] = pr[-TW]; tp1[c] = pr[TW]; tp2[c] = pr[2 * TW];
+              Bv[c] = R1[c * trD + o0[m]]; T2[c] = R2[c * trD + o0[m]];
+              twv[c] = sp[oq + c * dq_ + sm_];
             }
-            // ---- compute phase (k_step3d_t6.cu: max/min(H,0) as compare+select, same values)
-            const double hux = hu > 0.0 ? hu : 0.0, hun = hu < 0.0 ? hu : 0.0, huh = hu * 0.5;
-            const double hpx = hup > 0.0 ? hup : 0.0, hpn = hup < 0.0 ? hup : 0.0, hph = hup * 0.5;
-            const double hvx = hvn_ > 0.0 ? hvn_ : 0.0, hvm = hvn_ < 0.0 ? hvn_ : 0.0, hvh = hvn_ * 0.5;
+            // ---- compute phase
+            double hux, hun, hpx, hpn, hvx, hvm;
+            posneg(hu, hux, hun); posneg(hup, hpx, hpn); posneg(hvn_, hvx, hvm);
+            const double huh = hu * 0.5, hph = hup * 0.5, hvh = hvn_ * 0.5;
             int badl = 0;
             const double ohz = rcp_ieee(hz, badl);
             if (act && valid) bad |= badl;
@@ -307,20 +343,20 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
               const double FCk = vflux8(k, N, tm1[c], A[c], tp1[c], tp2[c], wk);
               const double cv = cff * (FCk - FCm);
               tv = tv - cv;
-              if (valid) sp[L.q(c) + so] = tv * ohz;
+              if (valid) sp[oq + c * dq_ + sm_] = tv * ohz;
               Cj[m][c] = c1; FEs[m][c] = FEn;
             }
-            if (valid) sp[L.hv() + so] = ohz;
+            if (valid) sp[ohv + sm_] = ohz;
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&slot_ready[sl]);
-          ++q;
+          q.next();
         }
         // ---- the oldest row of the ring is no longer needed (the last step of a chunk frees all three)
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&ring_empty[(g - 2) % RING]);
-          if (r == nrows + 3) { mbar_arrive(&ring_empty[(g - 1) % RING]); mbar_arrive(&ring_empty[g % RING]); }
+          mbar_arrive(&ring_empty[g2]);
+          if (r == nrows + 3) { mbar_arrive(&ring_empty[g1]); mbar_arrive(&ring_empty[g0]); }
         }
       }
     }
@@ -330,29 +366,33 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
     const bool dup = (NTR == 1) && lane >= 16;                        // one tracer: the upper half-warp only shadows the lower one
     const double c13 = 1.0 / 3.0;
     const int ni = a.ni, sk = a.sk, Lm = a.Lm;
-    unsigned q = 0;
+    const int oq = L.q(c) + col, oa = L.ak(c) + col, oh = L.hz() + col, oo = L.hv() + col, ocf = L.cf(c) + col, odc = L.dc(c) + col;
+    Ring8 q(S);
+    int turn = 0;                                                     // consumer warp that owns the next slot
     for (int it = blockIdx.x; it < a.nitems; it += gridDim.x) {
       const int stripe = it % a.nstripes, chunk = it / a.nstripes;
       const int i0s = a.ib + stripe * BI, ja = a.j0 + chunk * a.JCH, jb = min(ja + a.JCH - 1, a.j1);
       const int nrows = jb - ja + 1, i = i0s + col;
       const bool act = (i >= a.i0) && (i <= a.i1) && !dup;
       const bool wE = a.wrapEW && i >= 1 && i <= 2, wW = a.wrapEW && i >= Lm - 2 && i <= Lm;
-      for (int rr = -1; rr < nrows; ++rr, ++q) {
-        if ((int)(q % (unsigned)NC) != cw) continue;
-        const int sl = q % S;
-        mbar_wait(&slot_ready[sl], (q / S) & 1u, a.err);
+      const bool edge_stripe = __any_sync(0xffffffffu, wE || wW);
+      for (int rr = -1; rr < nrows; ++rr, q.next(), turn = (turn + 1 == NC) ? 0 : turn + 1) {
+        if (turn != cw) continue;
+        const int sl = q.i;
+        mbar_wait(&slot_ready[sl], q.ph, a.err);
         if (rr >= 0) {
           const int j = ja + rr;
-          double* sp = slots + (size_t)sl * slotD;
-          const double* pq = sp + L.q(c) + col;          // q(k)    at pq[(k-1)*LS]
-          const double* pa = sp + L.ak(c) + col;         // Akt(k)  at pa[k*LS], k = 0..N
-          const double* ph = sp + L.hz() + col;          // Hz(k)   at ph[(k-1)*LS]
-          const double* po = sp + L.hv() + col;          // 1/Hz(k) at po[(k-1)*LS]
-          double* pcf = sp + L.cf(c) + col;              // CF(k)   at pcf[(k-1)*LS]
-          double* pdc = sp + L.dc(c) + col;              // DC(k)   at pdc[(k-1)*LS]
+          double* sp = slots + sl * slotD;
+          const double* pq = sp + oq;                    // q(k)    at pq[(k-1)*LS]
+          const double* pa = sp + oa;                    // Akt(k)  at pa[k*LS], k = 0..N
+          const double* ph = sp + oh;                    // Hz(k)   at ph[(k-1)*LS]
+          const double* po = sp + oo;                    // 1/Hz(k) at po[(k-1)*LS]
+          double* pcf = sp + ocf;                        // CF(k)   at pcf[(k-1)*LS]
+          double* pdc = sp + odc;                        // DC(k)   at pdc[(k-1)*LS]
           // Software-pipelined forward elimination (k_step3d_t6.cu): while the recurrence of level k runs (mul, add, rcp, mul:
           // ~90 cycles of dependent latency), the coefficients FC,CF,BC,dq of level k+1 are formed and the operands of level
-          // k+2 are fetched (level N+1 does not exist: the clamped index re-reads level N, the values are not used).
+          // k+2 are fetched.  On the last pass "level N+1" reads the first level of the array that follows in the slot (every
+          // array here is followed by another one): the values are not used.
           double dtakK, hzN, ohzN, c16N, dtakN, qN, akN;
           double FC, CF, BC, dq;
           {
@@ -364,18 +404,20 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
             BC = c13 * (hz1 + hzN) + dtakK * (ohz1 + ohzN);
             dq = qN - q1;
           }
+          pq += 2 * LS; pa += 3 * LS; ph += 2 * LS; po += 2 * LS;        // -> level 3
           double cf_prev = 0.0, dc_prev = 0.0;
           double ak_top = akN, q_top = qN, ohz_top = ohzN;
           int badl = 0;
 #pragma unroll 4
           for (int k = 1; k <= N - 1; ++k) {
             ak_top = akN; q_top = qN; ohz_top = ohzN;                    // level k+1 (== N on the last pass)
-            const int lv = min(k + 2, N);
-            const double hzL = ph[(lv - 1) * LS], ohzL = po[(lv - 1) * LS], akL = pa[lv * LS], qL = pq[(lv - 1) * LS];
+            const double hzL = *ph, ohzL = *po, akL = *pa, qL = *pq;     // level k+2
+            ph += LS; po += LS; pa += LS; pq += LS;
             const double cf = rcp_ieee(BC - FC * cf_prev, badl);
             cf_prev = cf * CF;
             dc_prev = cf * (dq - FC * dc_prev);
-            pcf[(k - 1) * LS] = cf_prev; pdc[(k - 1) * LS] = dc_prev;
+            *pcf = cf_prev; *pdc = dc_prev;
+            pcf += LS; pdc += LS;
             const double c16L = c16 * hzL, dtakL = dt * akL;
             FC = c16N - dtakK * ohzN;
             CF = c16L - dtakL * ohzL;
@@ -384,37 +426,52 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
             dtakK = dtakN; hzN = hzL; ohzN = ohzL; c16N = c16L; dtakN = dtakL; qN = qL; akN = akL;
           }
           if (act) bad |= badl;
-          // back substitution + final update, level N first
+          // back substitution + final update, level N first.  pcf/pdc point one past level N-1; pq/po/pa at level N+2.
           const bool south = a.wallS && j == a.Jstr, north = a.wallN && j == a.Jend;
           double* tw = a.out[c] + ((i - a.LBi) + (size_t)ni * (j - a.LBj)) + (size_t)sk * (N - 1);   // t(nnew)(i,j,N)
           double dc_next = 0.0;                                          // DC(N)
           double a_next = dc_next * ak_top;                              // DC(N)*Akt(N)
           double q_next = q_top, dtohz_next = dt * ohz_top;
-          double Xk = pcf[(N - 2) * LS], Yk = pdc[(N - 2) * LS], akk = pa[(N - 1) * LS], qk = pq[(N - 2) * LS], ohzk = po[(N - 2) * LS];
-          const bool plain = !__any_sync(0xffffffffu, wE || wW || south || north);   // interior stripe and row: one store per level
-          auto put = [&](double out) {                                   // st() + t3dbc wall rows (t3dbc_im.F:334-341,415-422)
-            if (act) {
-              tw[0] = out;
-              if (!plain) {
+          pcf -= LS; pdc -= LS; pq -= 3 * LS; po -= 3 * LS; pa -= 3 * LS;    // level N-1
+          double Xk = *pcf, Yk = *pdc, akk = *pa, qk = *pq, ohzk = *po;
+          // operands of level k-1 are fetched one level ahead; for k = 1 that is "level 0" = the array space just below (not used)
+          if (!(edge_stripe || south || north)) {
+            // interior stripe and row: one store per level
+#pragma unroll 4
+            for (int k = N - 1; k >= 1; --k) {
+              pcf -= LS; pdc -= LS; pq -= LS; po -= LS; pa -= LS;
+              const double Xm = *pcf, Ym = *pdc, akm = *pa, qm = *pq, ohzm = *po;
+              const double dc_k = Yk - Xk * dc_next;
+              const double a_k = dc_k * akk;
+              if (act) *tw = q_next + dtohz_next * (a_next - a_k);       // level k+1
+              tw -= sk;
+              dc_next = dc_k; a_next = a_k; q_next = qk; dtohz_next = dt * ohzk;
+              Xk = Xm; Yk = Ym; akk = akm; qk = qm; ohzk = ohzm;
+            }
+            if (act) *tw = q_next + dtohz_next * (a_next - 0.0);         // level 1; DC(0)=0 is not scaled by Akt
+          } else {
+            auto put = [&](double out) {                                 // st() + t3dbc wall rows (t3dbc_im.F:334-341,415-422)
+              if (act) {
+                tw[0] = out;
                 if (wE) tw[Lm] = out;
                 if (wW) tw[-Lm] = out;
                 if (south) { tw[-ni] = out; if (wE) tw[Lm - ni] = out; if (wW) tw[-Lm - ni] = out; }
                 if (north) { tw[ni] = out; if (wE) tw[Lm + ni] = out; if (wW) tw[-Lm + ni] = out; }
               }
+              tw -= sk;
+            };
+#pragma unroll 1
+            for (int k = N - 1; k >= 1; --k) {
+              pcf -= LS; pdc -= LS; pq -= LS; po -= LS; pa -= LS;
+              const double Xm = *pcf, Ym = *pdc, akm = *pa, qm = *pq, ohzm = *po;
+              const double dc_k = Yk - Xk * dc_next;
+              const double a_k = dc_k * akk;
+              put(q_next + dtohz_next * (a_next - a_k));
+              dc_next = dc_k; a_next = a_k; q_next = qk; dtohz_next = dt * ohzk;
+              Xk = Xm; Yk = Ym; akk = akm; qk = qm; ohzk = ohzm;
             }
-            tw -= sk;
-          };
-#pragma unroll 4
-          for (int k = N - 1; k >= 1; --k) {
-            const int lv = max(k - 1, 1);
-            const double Xm = pcf[(lv - 1) * LS], Ym = pdc[(lv - 1) * LS], akm = pa[lv * LS], qm = pq[(lv - 1) * LS], ohzm = po[(lv - 1) * LS];
-            const double dc_k = Yk - Xk * dc_next;
-            const double a_k = dc_k * akk;
-            put(q_next + dtohz_next * (a_next - a_k));                   // level k+1
-            dc_next = dc_k; a_next = a_k; q_next = qk; dtohz_next = dt * ohzk;
-            Xk = Xm; Yk = Ym; akk = akm; qk = qm; ohzk = ohzm;
+            put(q_next + dtohz_next * (a_next - 0.0));
           }
-          put(q_next + dtohz_next * (a_next - 0.0));                     // level 1; DC(0)=0 is not scaled by Akt
         }
         fence_proxy_async();                     // generic-proxy accesses of the slot are ordered before the TMA refill
         __syncwarp();
