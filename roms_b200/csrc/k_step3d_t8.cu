@@ -33,6 +33,7 @@ constexpr int HUW = BI + 2;       // Huon row: columns i0 .. i0+17 (i0+16 is use
 constexpr int RING = 4;           // t(3) rows resident per stripe
 constexpr int MAXS = 8;           // most slots
 constexpr int LS = BI;            // doubles per level of a slot array
+constexpr int BARD = 48;          // doubles reserved for the mbarriers (32) and the tensor-memory base word
 constexpr int RPAD = 48;          // doubles in front of the ring: the vertical stencil of level 1 reaches two (unused) levels below a row
 __host__ __device__ constexpr int pad16(int n) { return (n + 15) & ~15; }
 
@@ -54,7 +55,7 @@ struct alignas(64) A8 {
 };
 
 // shared-memory layout of one slot (offsets in doubles; every TMA destination is a multiple of 16 doubles = 128 bytes)
-template <int NTR> struct Lay {
+template <int NTR, bool TM> struct Lay {
   int N;
   __host__ __device__ int q(int c) const { return c * N * LS; }                               // t(nnew) -> q           [N][16]
   __host__ __device__ int ak(int c) const { return NTR * N * LS + c * (N + 1) * LS; }         // Akt, levels 0..N       [N+1][16]
@@ -63,11 +64,11 @@ template <int NTR> struct Lay {
   __host__ __device__ int hu() const { return hv() + N * LS; }                                // Huon -> CF of tracer 0 [N][18]
   __host__ __device__ int w() const { return hu() + pad16(N * HUW); }                         // W 0..N -> CF of tracer 1 [N+1][16]
   __host__ __device__ int dc(int c) const { return w() + (N + 1) * LS + c * N * LS; }         // DC                     [N][16]
-  __host__ __device__ int slot() const { return dc(0) + NTR * N * LS; }
+  __host__ __device__ int slot() const { return TM ? w() + (N + 1) * LS : dc(0) + NTR * N * LS; }
   __host__ __device__ int cf(int c) const { return c == 0 ? hu() : w(); }
   __host__ __device__ int ring_tr() const { return pad16(N * TW); }                           // one tracer of a ring row [N][20]
   __host__ __device__ int ring_row() const { return NTR * ring_tr(); }
-  __host__ __device__ size_t bytes(int S) const { return 256 + 128 + sizeof(double) * (RPAD + (size_t)RING * ring_row() + (size_t)S * slot()); }
+  __host__ __device__ size_t bytes(int S) const { return 8 * BARD + 128 + sizeof(double) * (RPAD + (size_t)RING * ring_row() + (size_t)S * slot()); }
   __host__ __device__ unsigned slot_tx() const {                                              // bytes TMA delivers into a full slot
     return 8u * (unsigned)(NTR * N * LS + NTR * (N + 1) * LS + N * LS + N * LS + N * HUW + (N + 1) * LS);
   }
@@ -97,6 +98,24 @@ __device__ __forceinline__ void fence_proxy_async() {}
 __device__ __forceinline__ int __double2hiint(double x) { uint64_t u; memcpy(&u, &x, 8); return (int)(u >> 32); }
 __device__ __forceinline__ int __double2loint(double x) { uint64_t u; memcpy(&u, &x, 8); return (int)(u & 0xffffffffu); }
 __device__ __forceinline__ double __hiloint2double(int hi, int lo) { uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &u, 8); return x; }
+// tensor memory of the running CTA: 128 lanes x 512 32-bit columns; a warp reaches the 32 lanes of its quadrant (warp % 4)
+static uint32_t emu_tmem[128][512];
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst, uint32_t ncols) { if (ncols > 512) abort(); *dst = 0; }
+__device__ __forceinline__ void tmem_dealloc(uint32_t, uint32_t) {}
+__device__ __forceinline__ void tmem_fence_before() {}
+__device__ __forceinline__ void tmem_fence_after() {}
+__device__ __forceinline__ void tmem_wait_ld() {}
+__device__ __forceinline__ void tmem_wait_st() {}
+__device__ __forceinline__ void tmem_st2d(uint32_t taddr, double x, double y) {
+  const int ln = (int)(taddr >> 16) + (int)(threadIdx.x & 31), col = (int)(taddr & 0xffffu);
+  if (ln < 0 || ln > 127 || col < 0 || col + 4 > 512 || ((taddr >> 16) != 32u * ((threadIdx.x >> 5) & 3u))) { fprintf(stderr, "emu: tensor-memory access outside the warp's quadrant or the columns\n"); abort(); }
+  memcpy(&emu_tmem[ln][col], &x, 8); memcpy(&emu_tmem[ln][col + 2], &y, 8);
+}
+__device__ __forceinline__ void tmem_ld2d(uint32_t taddr, double& x, double& y) {
+  const int ln = (int)(taddr >> 16) + (int)(threadIdx.x & 31), col = (int)(taddr & 0xffffu);
+  if (ln < 0 || ln > 127 || col < 0 || col + 4 > 512 || ((taddr >> 16) != 32u * ((threadIdx.x >> 5) & 3u))) { fprintf(stderr, "emu: tensor-memory access outside the warp's quadrant or the columns\n"); abort(); }
+  memcpy(&x, &emu_tmem[ln][col], 8); memcpy(&y, &emu_tmem[ln][col + 2], 8);
+}
 __device__ __forceinline__ double* align128(double* p) { return (double*)(((uintptr_t)p + 127) & ~(uintptr_t)127); }
 #else
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -124,6 +143,28 @@ __device__ __forceinline__ void tma3d(double* dst, const TMap* m, int c0, int c1
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// ---- tensor memory (TMEM, 256 KB per SM: 128 lanes x 512 32-bit columns) as per-thread scratch of the consumer warps: a warp
+// reaches the 32 lanes of its quadrant (warp % 4), thread i its lane i, columns are addressed dynamically.  The Thomas
+// coefficients CF(k), DC(k) of a (column, tracer) live in 4 consecutive columns per level: one tcgen05.st per level in the forward
+// sweep, one tcgen05.ld per level in the backward sweep, no shared-memory space or bandwidth.
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst, uint32_t ncols) {                 // one full warp; ncols: power of two >= 32
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) { asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory"); }
+__device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st2d(uint32_t taddr, double x, double y) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(__double2loint(x)), "r"(__double2hiint(x)), "r"(__double2loint(y)), "r"(__double2hiint(y)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2d(uint32_t taddr, double& x, double& y) {            // values valid after tmem_wait_ld()
+  int a, b, c, d;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr) : "memory");
+  x = __hiloint2double(b, a); y = __hiloint2double(d, c);
+}
 // pointer arithmetic on the shared array (a round trip through uintptr_t would lose the address space: generic LD/ST instead of LDS/STS)
 __device__ __forceinline__ double* align128(double* p) { return p + (((128u - (s32(p) & 127u)) & 127u) >> 3); }
 #endif
@@ -155,8 +196,10 @@ struct Ring8 {
 };
 
 // KP: level-pair batches per producer warp (NP * KP >= ceil(N/2))
-template <int NTR, int KP>
-__global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_constant__ A8 a) {
+// TM: CF/DC of the tridiagonal solve in tensor memory instead of the slot (smaller slots -> more of them, more consumer warps)
+// MAXT: launch bound (384: up to 12 warps with up to 168 registers per thread; 512: up to 16 warps with 128)
+template <int NTR, int KP, bool TM, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_constant__ A8 a) {
   extern __shared__ __align__(128) double sm_raw[];
   double* sm = align128(sm_raw);
   const int N = a.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -166,16 +209,23 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
   uint64_t* slot_full = ring_empty + RING;      // [MAXS]  TMA has filled the slot
   uint64_t* slot_ready = slot_full + MAXS;      // [MAXS]  every producer warp has written q, 1/Hz
   uint64_t* slot_empty = slot_ready + MAXS;     // [MAXS]  the consumer warp is done with the slot
-  const Lay<NTR> L{N};
+  const Lay<NTR, TM> L{N};
   const int trD = L.ring_tr(), rowD = L.ring_row(), slotD = L.slot();
-  double* ring = sm + 32 + RPAD;                // 32 x 8 bytes of barriers, padding
+  uint32_t* tmem_word = (uint32_t*)(sm + 32);   // base address of the tensor-memory allocation (TM)
+  double* ring = sm + BARD + RPAD;
   double* slots = ring + RING * rowD;
   if (threadIdx.x == 0) {
     for (int q = 0; q < RING; ++q) { mbar_init(&ring_full[q], 1); mbar_init(&ring_empty[q], NP); }
     for (int q = 0; q < MAXS; ++q) { mbar_init(&slot_full[q], 1); mbar_init(&slot_ready[q], NP); mbar_init(&slot_empty[q], 1); }
     fence_barrier_init();
   }
+  uint32_t tm_cols = 32;                        // 4 32-bit columns per level (CF, DC), a power of two
+  while (tm_cols < 4u * (unsigned)N) tm_cols *= 2;
+  if (TM && warp == 1) tmem_alloc(tmem_word, tm_cols);
+  if (TM) tmem_fence_before();
   __syncthreads();
+  if (TM) tmem_fence_after();
+  const uint32_t tm_base = TM ? *tmem_word : 0u;
   const double dt = a.dt, c16 = 1.0 / 6.0;
   int bad = 0;
 
@@ -366,7 +416,8 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
     const bool dup = (NTR == 1) && lane >= 16;                        // one tracer: the upper half-warp only shadows the lower one
     const double c13 = 1.0 / 3.0;
     const int ni = a.ni, sk = a.sk, Lm = a.Lm;
-    const int oq = L.q(c) + col, oa = L.ak(c) + col, oh = L.hz() + col, oo = L.hv() + col, ocf = L.cf(c) + col, odc = L.dc(c) + col;
+    const int oq = L.q(c) + col, oa = L.ak(c) + col, oh = L.hz() + col, oo = L.hv() + col, ocf = TM ? 0 : L.cf(c) + col, odc = TM ? 0 : L.dc(c) + col;
+    const uint32_t tm0 = tm_base + ((32u * (unsigned)(warp & 3)) << 16);      // this warp's lanes, level 1
     Ring8 q(S);
     int turn = 0;                                                     // consumer warp that owns the next slot
     for (int it = blockIdx.x; it < a.nitems; it += gridDim.x) {
@@ -408,6 +459,7 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
           double cf_prev = 0.0, dc_prev = 0.0;
           double ak_top = akN, q_top = qN, ohz_top = ohzN;
           int badl = 0;
+          uint32_t tmc = tm0;                                            // tensor-memory address of (CF, DC)(k)
 #pragma unroll 4
           for (int k = 1; k <= N - 1; ++k) {
             ak_top = akN; q_top = qN; ohz_top = ohzN;                    // level k+1 (== N on the last pass)
@@ -416,8 +468,8 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
             const double cf = rcp_ieee(BC - FC * cf_prev, badl);
             cf_prev = cf * CF;
             dc_prev = cf * (dq - FC * dc_prev);
-            *pcf = cf_prev; *pdc = dc_prev;
-            pcf += LS; pdc += LS;
+            if (TM) { tmem_st2d(tmc, cf_prev, dc_prev); tmc += 4; }
+            else { *pcf = cf_prev; *pdc = dc_prev; pcf += LS; pdc += LS; }
             const double c16L = c16 * hzL, dtakL = dt * akL;
             FC = c16N - dtakK * ohzN;
             CF = c16L - dtakL * ohzL;
@@ -433,19 +485,26 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
           double a_next = dc_next * ak_top;                              // DC(N)*Akt(N)
           double q_next = q_top, dtohz_next = dt * ohz_top;
           pcf -= LS; pdc -= LS; pq -= 3 * LS; po -= 3 * LS; pa -= 3 * LS;    // level N-1
-          double Xk = *pcf, Yk = *pdc, akk = *pa, qk = *pq, ohzk = *po;
+          double Xk, Yk;
+          if (TM) { tmem_wait_st(); tmc -= 4; tmem_ld2d(tmc, Xk, Yk); tmem_wait_ld(); }
+          else { Xk = *pcf; Yk = *pdc; }
+          double akk = *pa, qk = *pq, ohzk = *po;
           // operands of level k-1 are fetched one level ahead; for k = 1 that is "level 0" = the array space just below (not used)
           if (!(edge_stripe || south || north)) {
             // interior stripe and row: one store per level
 #pragma unroll 4
             for (int k = N - 1; k >= 1; --k) {
-              pcf -= LS; pdc -= LS; pq -= LS; po -= LS; pa -= LS;
-              const double Xm = *pcf, Ym = *pdc, akm = *pa, qm = *pq, ohzm = *po;
+              pq -= LS; po -= LS; pa -= LS;
+              double Xm, Ym;
+              if (TM) { if (k > 1) tmc -= 4; tmem_ld2d(tmc, Xm, Ym); }   // k == 1: "level 0", re-reads level 1 (not used)
+              else { pcf -= LS; pdc -= LS; Xm = *pcf; Ym = *pdc; }
+              const double akm = *pa, qm = *pq, ohzm = *po;
               const double dc_k = Yk - Xk * dc_next;
               const double a_k = dc_k * akk;
               if (act) *tw = q_next + dtohz_next * (a_next - a_k);       // level k+1
               tw -= sk;
               dc_next = dc_k; a_next = a_k; q_next = qk; dtohz_next = dt * ohzk;
+              if (TM) tmem_wait_ld();
               Xk = Xm; Yk = Ym; akk = akm; qk = qm; ohzk = ohzm;
             }
             if (act) *tw = q_next + dtohz_next * (a_next - 0.0);         // level 1; DC(0)=0 is not scaled by Akt
@@ -462,12 +521,16 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
             };
 #pragma unroll 1
             for (int k = N - 1; k >= 1; --k) {
-              pcf -= LS; pdc -= LS; pq -= LS; po -= LS; pa -= LS;
-              const double Xm = *pcf, Ym = *pdc, akm = *pa, qm = *pq, ohzm = *po;
+              pq -= LS; po -= LS; pa -= LS;
+              double Xm, Ym;
+              if (TM) { if (k > 1) tmc -= 4; tmem_ld2d(tmc, Xm, Ym); }
+              else { pcf -= LS; pdc -= LS; Xm = *pcf; Ym = *pdc; }
+              const double akm = *pa, qm = *pq, ohzm = *po;
               const double dc_k = Yk - Xk * dc_next;
               const double a_k = dc_k * akk;
               put(q_next + dtohz_next * (a_next - a_k));
               dc_next = dc_k; a_next = a_k; q_next = qk; dtohz_next = dt * ohzk;
+              if (TM) tmem_wait_ld();
               Xk = Xm; Yk = Ym; akk = akm; qk = qm; ohzk = ohzm;
             }
             put(q_next + dtohz_next * (a_next - 0.0));
@@ -480,6 +543,11 @@ __global__ void __launch_bounds__(384, 1) step3d_t_v8_kernel(const __grid_consta
     }
   }
   if (bad) atomicOr(a.err, 1);
+  if (TM) {
+    tmem_fence_before();
+    __syncthreads();                              // every consumer warp is done with its tensor-memory columns
+    if (warp == 1) tmem_dealloc(tm_base, tm_cols);
+  }
 }
 
 namespace {
@@ -515,12 +583,26 @@ int make_map(TMap* m, const double* base, int ni, int nj, int nk, int bw, int bk
 #endif
 }
 
-template <int NTR, int KP>
-int launch_v8(roms_b200_ctx* c, const A8& a, int grid, size_t smem) {
+template <int NTR, int KP, bool TM, int MAXT>
+int launch_v8_t(roms_b200_ctx* c, const A8& a, int grid, size_t smem) {
   static size_t set = 0;
-  if (smem > set) { CUDA_OK(cudaFuncSetAttribute(step3d_t_v8_kernel<NTR, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = smem; }
-  step3d_t_v8_kernel<NTR, KP><<<dim3(grid), dim3(32 * (1 + a.NC + a.NP)), smem, c->stream>>>(a);
+  if (smem > set) { CUDA_OK(cudaFuncSetAttribute(step3d_t_v8_kernel<NTR, KP, TM, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = smem; }
+  step3d_t_v8_kernel<NTR, KP, TM, MAXT><<<dim3(grid), dim3(32 * (1 + a.NC + a.NP)), smem, c->stream>>>(a);
   return 0;
+}
+template <int NTR, int KP, bool TM>
+int launch_v8(roms_b200_ctx* c, const A8& a, int grid, size_t smem) {
+  return 32 * (1 + a.NC + a.NP) <= 384 ? launch_v8_t<NTR, KP, TM, 384>(c, a, grid, smem) : launch_v8_t<NTR, KP, TM, 512>(c, a, grid, smem);
+}
+template <int NTR, bool TM>
+int launch_v8_kp(roms_b200_ctx* c, const A8& a, int grid, size_t smem, int KP) {
+  if (KP == 1) return launch_v8<NTR, 1, TM>(c, a, grid, smem);
+  if (KP == 2) return launch_v8<NTR, 2, TM>(c, a, grid, smem);
+  return launch_v8<NTR, 4, TM>(c, a, grid, smem);
+}
+size_t smem_v8(int ntr, bool tm, int N, int S) {
+  if (ntr == 2) return tm ? Lay<2, true>{N}.bytes(S) : Lay<2, false>{N}.bytes(S);
+  return tm ? Lay<1, true>{N}.bytes(S) : Lay<1, false>{N}.bytes(S);
 }
 }  // namespace
 
@@ -543,20 +625,23 @@ int k_step3d_t_v8(roms_b200_ctx* c, int nnew) {
   static const int force_jch = getenv("ROMS_B200_S3T_JCH") ? atoi(getenv("ROMS_B200_S3T_JCH")) : 0;
   for (int itr0 = 1; itr0 <= b.NT; itr0 += 2) {
     const int ntr = (itr0 + 1 <= b.NT) ? 2 : 1;
-    // slots: as many as fit (at most 6); consumers: every slot that is neither being loaded nor being produced
+    // CF/DC of the tridiagonal solve in tensor memory (4 32-bit columns per level, <= 512 columns) unless switched off
+    static const bool no_tm = (getenv("ROMS_B200_S3T_TMEM") != nullptr && atoi(getenv("ROMS_B200_S3T_TMEM")) == 0);
+    const bool tm = !no_tm && 4 * N <= 512;
+    // slots: as many as fit (at most 6); consumers: every slot that is neither being loaded nor being produced, at most 4
+    // (with tensor memory each consumer warp needs its own lane quadrant: warps 1..4)
     int S = 0;
-    for (int s = (force_s ? force_s : 6); s >= 2 && !S; --s) {
-      const size_t need = (ntr == 2) ? Lay<2>{N}.bytes(s) : Lay<1>{N}.bytes(s);
-      if (need <= (size_t)max_smem) S = s;
-    }
+    for (int s = (force_s ? force_s : 6); s >= 2 && !S; --s) if (smem_v8(ntr, tm, N, s) <= (size_t)max_smem) S = s;
     if (!S) return 2;
-    const int NC = S >= 4 ? S - 2 : 1;
-    // producer warps x level-pair batches per warp: NP*KP >= ceil(N/2), at most 12 warps per CTA (170 registers per thread)
+    static const int force_nc = getenv("ROMS_B200_S3T_NC") ? atoi(getenv("ROMS_B200_S3T_NC")) : 0;
+    const int NC = force_nc ? force_nc : (S >= 4 ? S - 2 : 1);
+    if (NC > 4 || NC >= S) return 2;
+    // producer warps x level-pair batches per warp: NP*KP >= ceil(N/2), at most 16 warps per CTA
     const int nb = (N + 1) / 2;
     int KP = 0, NP = 0;
     for (int kp = 1; kp <= 4 && !KP; kp *= 2) {
       const int np = force_np ? force_np : (nb + kp - 1) / kp;
-      if (np * kp >= nb && 1 + NC + np <= 12) { KP = kp; NP = np; }
+      if (np * kp >= nb && 1 + NC + np <= 16) { KP = kp; NP = np; }
     }
     if (!KP) return 2;
     // TMA: the first element of a box must be 16-byte aligned in global memory (measured on B200, tools/ubench/tma3d_test.cu: an odd
@@ -600,14 +685,11 @@ int k_step3d_t_v8(roms_b200_ctx* c, int nnew) {
     if (rc) return 2;
     const int grid = a.nitems < nsm ? a.nitems : nsm;
     static const bool verbose = (getenv("ROMS_B200_S3T_VERBOSE") != nullptr);
-    if (verbose) fprintf(stderr, "step3d_t v8: N=%d ntr=%d stripes=%d JCH=%d items=%d grid=%d slots=%d consumers=%d producers=%dx%d smem=%zu\n", N, ntr, nstripes,
-                         a.JCH, a.nitems, grid, S, NC, NP, KP, (ntr == 2) ? Lay<2>{N}.bytes(S) : Lay<1>{N}.bytes(S));
-    const size_t smem = (ntr == 2) ? Lay<2>{N}.bytes(S) : Lay<1>{N}.bytes(S);
-    if (ntr == 2) {
-      if (KP == 1) rc = launch_v8<2, 1>(c, a, grid, smem); else if (KP == 2) rc = launch_v8<2, 2>(c, a, grid, smem); else rc = launch_v8<2, 4>(c, a, grid, smem);
-    } else {
-      if (KP == 1) rc = launch_v8<1, 1>(c, a, grid, smem); else if (KP == 2) rc = launch_v8<1, 2>(c, a, grid, smem); else rc = launch_v8<1, 4>(c, a, grid, smem);
-    }
+    if (verbose) fprintf(stderr, "step3d_t v8: N=%d ntr=%d stripes=%d JCH=%d items=%d grid=%d slots=%d consumers=%d producers=%dx%d smem=%zu tmem=%d\n", N, ntr, nstripes,
+                         a.JCH, a.nitems, grid, S, NC, NP, KP, smem_v8(ntr, tm, N, S), (int)tm);
+    const size_t smem = smem_v8(ntr, tm, N, S);
+    if (ntr == 2) rc = tm ? launch_v8_kp<2, true>(c, a, grid, smem, KP) : launch_v8_kp<2, false>(c, a, grid, smem, KP);
+    else rc = tm ? launch_v8_kp<1, true>(c, a, grid, smem, KP) : launch_v8_kp<1, false>(c, a, grid, smem, KP);
     if (rc) return rc;
     c->launches++;
   }
