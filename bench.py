@@ -2,11 +2,16 @@
 """bench.py -- baroclinic-step throughput of the roms_b200 main3d path.
 
     python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
-    python bench.py --impl reference --gpus N ...          # the reference's own CPU algorithm (oracle port)
+    python bench.py --impl reference --gpus N ...          # the reference's own CPU algorithm (oracle port, -O3 build)
 
 Metric (BASELINE.json): 3-D cell-updates/s of the baroclinic step = Lm*Mm*N*K / time(K steps of main3d),
 workload BENCHMARK1 (512x64x30, full main3d loop: EOS, KPP, bulk fluxes, 59 barotropic sub-steps, ...).
-Prints ONE JSON line (rank 0).
+Prints ONE JSON line (rank 0).  The line is self-checking:
+  N = 1: "parity"               -- zeta,ubar,vbar,u,v,T,S after --parity-steps steps against the oracle (the CHECKER build of oracle/,
+                                   -O2 -ffp-contract=off), max-norm relative to the field's range, bar 1e-10 (BASELINE.json);
+  N > 1: "tiling_bit_identical" -- every rank also integrates the WHOLE grid as one tile on its own GPU through the same call
+                                   sequence and compares its tile's interior bit for bit (the reference's acceptance criterion,
+                                   ROMS/Bin/verify.sh:12-14, check_nc.sh:35-43).
 """
 import argparse
 import json
@@ -23,6 +28,7 @@ sys.path.insert(0, ROOT)
 METRIC = "3D cell-updates/sec (baroclinic step)"
 UNIT = "cell-updates/s"
 WORKLOADS = {"BENCHMARK1": (512, 64, 30), "BENCHMARK2": (1024, 128, 30), "BENCHMARK3": (2048, 256, 30)}
+PROGNOSTIC = ["zeta", "ubar", "vbar", "u", "v", "t"]
 
 
 def measured_peak():
@@ -70,19 +76,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(workload, nsteps, warm=1):
-    """The oracle (CPU restatement of the reference algorithm, kind="port") on this box's host cores."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as ol
-    Lm, Mm, N = WORKLOADS[workload]
-    cores = os.cpu_count() or 1
+def _oracle_tiling(cores):
     nti, ntj = 1, 1
     while nti * ntj < cores:            # tiles = host threads, like the reference's NtileI*NtileJ = cores
         if nti <= ntj * 4:
             nti *= 2
         else:
             ntj *= 2
-    o = ol.Oracle(ol.BENCHMARK, Lm, Mm, N, NtileI=nti, NtileJ=ntj)
+    return nti, ntj
+
+
+def cpu_baseline(workload, nsteps, warm=1, world=1):
+    """The oracle (CPU restatement of the reference algorithm, kind="port": the Fortran cannot be built in this image) on this
+    box's host cores, compiled like the reference's own build (-O3, contraction on, -march=native when the box has a compiler)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    Lm, Mm, N = grid_for(workload, world)[:3]
+    cores = os.cpu_count() or 1
+    nti, ntj = _oracle_tiling(cores)
+    flags = ol.fast_lib()[1]
+    o = ol.Oracle(ol.BENCHMARK, Lm, Mm, N, NtileI=nti, NtileJ=ntj, fast=True)
     o.set_threads(cores)
     o.initial()
     o.step(warm)
@@ -90,26 +103,81 @@ def cpu_baseline(workload, nsteps, warm=1):
     o.step(nsteps)
     dt = time.perf_counter() - t0
     return {"value": Lm * Mm * N * nsteps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d baroclinic steps of %s (%dx%dx%d), %dx%d tiles on %d threads, %.2f s" % (nsteps, workload, Lm, Mm, N, nti, ntj, cores, dt)}, dt / nsteps
+            "sample": "%d baroclinic steps on the %dx%dx%d grid, %dx%d tiles on %d host threads, %.2f s; oracle (C++ restatement of the "
+                      "Fortran, which cannot be built in this image) compiled %s" % (nsteps, Lm, Mm, N, nti, ntj, cores, dt, flags)}, dt / nsteps
+
+
+def parity_vs_oracle(rb, workload, nsteps):
+    """zeta,ubar,vbar,u,v,t after nsteps baroclinic steps from the analytical start state: this library (device-resident loop)
+    against the checker build of the oracle."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import oracle_lib as ol
+    Lm, Mm, N = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    nti, ntj = _oracle_tiling(cores)
+    o = ol.Oracle(ol.BENCHMARK, Lm, Mm, N, NtileI=nti, NtileJ=ntj)      # tiling-invariant bit for bit (tests/test_cpu.py)
+    o.set_threads(cores)
+    o.initial()
+    o.step(nsteps)
+    d = rb.Driver(rb.default_config(rb.APP_BENCHMARK, Lm, Mm, N), device=0)
+    d.run(nsteps)
+    d.ctx.sync()
+    rel = {}
+    for n in PROGNOSTIC:
+        a, g = o.get(n), d.ctx.download(n)
+        rel[n] = float(np.max(np.abs(a - g))) / max(float(a.max() - a.min()), 1e-300)
+    d.finalize()
+    worst = max(rel.values())
+    return {"against": "oracle (checker build -O2 -ffp-contract=off, %dx%d tiles)" % (nti, ntj), "workload": "%s %dx%dx%d" % (workload, Lm, Mm, N),
+            "steps": nsteps, "max_rel": worst, "tolerance": 1e-10, "ok": bool(worst <= 1e-10), "per_field": rel}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cb, sps = cpu_baseline(args.workload, args.steps, max(1, min(args.warmup, 2)))
-    Lm, Mm, N = WORKLOADS[args.workload]
+    world = world if world > 1 else max(1, args.gpus)      # the grid of OUR arm at this GPU count
+    cb, sps = cpu_baseline(args.workload, args.steps, max(1, min(args.warmup, 2)), world)
     line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic (analytical BENCHMARK grid/initial state/forcing)", "impl": "reference",
-            "config": {"workload": "%s %dx%dx%d full main3d loop" % (args.workload, Lm, Mm, N)},
+            "data": "synthetic (analytical BENCHMARK grid/initial state/forcing, random-free)", "impl": "reference",
+            "config": workload_config(args.workload, world),
             "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-# DRAM bytes per launch of the graded kernel from `ncu --set full` (profiles/r01_step3d_t_v6_*): dram__bytes_read.sum +
-# dram__bytes_write.sum of ONE launch on the same grid (ncu cannot run inside the timed bench)
-NCU_TRAFFIC = {(2048, 256, 30): 1.320e9 + 0.248e9, (1024, 512, 50): 2.312e9 + 0.416e9}
+TILINGS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}     # BENCHMARK2 = 2x2 on 4 GPUs, 4x2 on 8 (BASELINE.json configs)
+
+
+def grid_for(workload, world):
+    """Global grid and tiling of a run on `world` GPUs: the BENCHMARK1 series is weak-scaled (every GPU holds one 512x64x30 tile,
+    N=4 is exactly BENCHMARK2 1024x128x30 on 2x2 tiles); any other workload keeps its grid (strong-scaling style)."""
+    nti, ntj = TILINGS[world]
+    Lm, Mm, N = WORKLOADS[workload]
+    if workload == "BENCHMARK1":
+        Lm, Mm = Lm * nti, Mm * ntj
+    return Lm, Mm, N, nti, ntj
+
+
+def workload_config(workload, world):
+    """The same `config` object for both arms (the driver compares them)."""
+    Lm, Mm, N, nti, ntj = grid_for(workload, world)
+    name = workload if world == 1 else "%s-sized tile per GPU" % workload if workload == "BENCHMARK1" else workload
+    return {"workload": "%s: %dx%dx%d grid, full main3d loop (rho_eos, diag every step, bulk_flux, KPP, omega, wvelocity, 2*nfast+1 step2d "
+                        "sub-steps, rhs3d, step3d_uv, step3d_t)" % (name, Lm, Mm, N),
+            "grid": "%dx%dx%d" % (Lm, Mm, N), "gpu_tiles": "%dx%d" % (nti, ntj)}
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the graded kernel: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from an
+    `ncu --set full` capture (ncu cannot run inside the timed bench); written by tools/ncu_traffic.py together with the commit
+    the capture was taken at."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "step3d_t_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 def _time_step3d_t(rb, Lm, Mm, N, reps):
@@ -127,14 +195,17 @@ def _time_step3d_t(rb, Lm, Mm, N, reps):
 def roofline_step3d_t(rb, peak, peak_kind):
     """step3d_t (the graded kernel) on grids whose working set is >> L2 (126 MB), so every launch streams from HBM:
     96 B algorithmic per cell per call (NT=2).  Primary: the BENCHMARK3 grid (N=30); also the
-    N=50 basin-like tile, where the kernel's shared-memory ring leaves room for only one row in flight."""
+    N=50 basin-like tile.  The timing loop re-applies the kernel to its own output (same traffic, arithmetic not meaningful)."""
     out = None
+    traffic = ncu_traffic()
     for (Lm, Mm, N) in ((2048, 256, 30), (1024, 512, 50)):
         ms = _time_step3d_t(rb, Lm, Mm, N, 20)
         cells = Lm * Mm * N
         achieved = 96.0 * cells / (ms * 1e-3) / 1e9
-        r = {"bound": "hbm", "kernel": "step3d_t_v6_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-             "peak_kind": peak_kind, "traffic": NCU_TRAFFIC.get((Lm, Mm, N)),
+        tr = traffic.get("%dx%dx%d" % (Lm, Mm, N), {})
+        r = {"bound": "hbm", "kernel": "step3d_t_v8_kernel (TMA-staged j x k tiles, mbarrier pipeline, CF/DC in tensor memory)", "achieved": achieved,
+             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind, "traffic": tr.get("dram_bytes"),
+             "traffic_source": tr.get("source"),
              "grid": "%dx%dx%d (t working set %.2f GB >> L2)" % (Lm, Mm, N, 6 * cells * 8 / 1e9),
              "ms_per_launch": ms, "cell_updates_per_s": cells / (ms * 1e-3), "algorithmic_bytes_per_cell": 96,
              "algorithmic_bytes_per_launch": 96 * cells}
@@ -173,62 +244,85 @@ def run_ours(args, rank, world):
     diag = d.run(args.steps, host_forcing=True)
     d.ctx.sync()
     e2e_s = time.perf_counter() - t0
-    ni, nj = cfg.Lm + 6 + (0 if cfg.Lm % 2 else 0), cfg.Mm + 3
     b = rb.tile_bounds(Lm, Mm, N)
     ni, nj = b.UBi - b.LBi + 1, b.UBj - b.LBj + 1
     e2e = {"value": cells * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ni * nj * 8, "d2h_bytes_per_step": (3 * (b.Iend - b.Istr + 1) + 9) * 8,
            "ms_per_step": 1e3 * e2e_s / args.steps, "last_diag": {"avgke": diag[0], "avgpe": diag[1], "volume": diag[2]}}
+    nfast = d.nfast
     d.finalize()
     peak, peak_kind = measured_peak()
     roof = roofline_step3d_t(rb, peak, peak_kind) if not args.no_roofline else None
-    cb = None
+    cb = parity = None
     if not args.no_cpu:
         cb, _ = cpu_baseline(args.workload, args.cpu_steps)
+        parity = parity_vs_oracle(rb, args.workload, args.parity_steps)
+    cfgd = workload_config(args.workload, 1)
+    notes = {"nfast": nfast, "l2": "state 0.3 GB per step > 126 MB L2, no explicit flush", "fmad": "false (parity build)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (analytical BENCHMARK grid/initial state/forcing, random-free)",
-            "config": {"workload": "%s %dx%dx%d full main3d loop (rho_eos, diag every step, bulk_flux, KPP, omega, wvelocity, %d step2d sub-steps, rhs3d, step3d_uv, step3d_t)"
-                       % (args.workload, Lm, Mm, N, 2 * d.nfast + 1), "tiles": "1x1", "l2": "state 0.3 GB per step > 126 MB L2, no explicit flush",
-                       "fmad": "false (parity build)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb}
+            "config": cfgd, "notes": notes, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb,
+            "parity": parity}
     print(json.dumps(line))
 
 
-TILINGS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}     # BENCHMARK2 = 2x2 on 4 GPUs, 4x2 on 8 (BASELINE.json configs)
+TILING_FIELDS = [("zeta", 1, 1), ("zeta", 2, 1), ("ubar", 1, 1), ("ubar", 2, 1), ("vbar", 1, 1), ("vbar", 2, 1), ("u", 1, 1), ("u", 2, 1),
+                 ("v", 1, 1), ("v", 2, 1), ("t", 1, 1), ("t", 2, 1), ("t", 1, 2), ("t", 2, 2)]
+
+
+def _make_distributed(rb, dist, torch, cfg, rank, world, local):
+    """One tile per rank: NCCL id broadcast + all-gather of the CUDA IPC handles of the NVLink mailboxes (what MPI_Bcast /
+    MPI_Allgather do in a Fortran host)."""
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(rb.comm_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(idt, 0)
+    d = rb.Driver(cfg, tile=rank, device=local)
+    d.comm_init(rank, world, bytes(idt.cpu().numpy().tobytes()))
+    hnd = torch.frombuffer(bytearray(d.p2p_handle()), dtype=torch.uint8).cuda()
+    allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    dist.all_gather(allh, hnd)
+    d.p2p_connect(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh), world)
+    dist.barrier()
+    return d
+
+
+def _tiling_check(rb, dist, torch, d, gcfg, local, sequence):
+    """Tiling invariance on the benchmarked grid: this rank integrates the whole grid as ONE tile on its own GPU through the same
+    call sequence the tiled run went through, then compares its tile's interior of every prognostic field bit for bit."""
+    import numpy as np
+    one = rb.Driver(gcfg, device=local)
+    for n, host in sequence:
+        one.run(n, host_forcing=host)
+    one.ctx.sync()
+    one.ctx._bounds = one.bounds()
+    b = d.bounds()
+    d.ctx._bounds = b
+    ok, worst = True, 0.0
+    for name, l, m in TILING_FIELDS:
+        ref = one.ctx.download_interior(name, l, m)[:, b.Jstr - 1:b.Jend, b.Istr - 1:b.Iend]
+        got = d.ctx.download_interior(name, l, m)
+        if not np.array_equal(ref, got):
+            ok = False
+            worst = max(worst, float(np.max(np.abs(ref - got))))
+    one.finalize()
+    flag = torch.tensor([1.0 if ok else 0.0, -worst], dtype=torch.float64, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag[0] > 0.5), float(-flag[1])
 
 
 def run_ours_multi(args, rank, world):
-    """Weak scaling: every GPU holds one BENCHMARK1-sized tile (512x64x30); the global grid grows with N
-    (N=4 is exactly BENCHMARK2 1024x128x30 on 2x2 tiles).  Halo swaps = NCCL send/recv inside the library."""
+    """Weak scaling: every GPU holds one BENCHMARK1-sized tile (512x64x30); the global grid grows with N (N=4 is exactly
+    BENCHMARK2 1024x128x30 on 2x2 tiles).  Halo swaps: NVLink peer mailboxes inside the library (k_halo.cu)."""
     import torch
     import torch.distributed as dist
     import roms_b200 as rb
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    nti, ntj = TILINGS[world]
-    tLm, tMm, N = WORKLOADS["BENCHMARK1"]
-    if args.workload != "BENCHMARK1":                      # e.g. --workload BENCHMARK3 --gpus 8 (strong-scaling style run)
-        gLm, gMm, N = WORKLOADS[args.workload]
-    else:
-        gLm, gMm = tLm * nti, tMm * ntj
-    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        idt = torch.frombuffer(bytearray(rb.comm_unique_id()), dtype=torch.uint8).cuda()
-    dist.broadcast(idt, 0)
-    cfg = rb.default_config(rb.APP_BENCHMARK, gLm, gMm, N)
-    cfg.NtileI, cfg.NtileJ = nti, ntj
-    d = rb.Driver(cfg, tile=rank, device=local)
-    d.comm_init(rank, world, bytes(idt.cpu().numpy().tobytes()))
-    # NVLink peer mailboxes: all-gather the CUDA IPC handles (what MPI_Allgather does in a Fortran host)
-    hnd = torch.frombuffer(bytearray(d.p2p_handle()), dtype=torch.uint8).cuda()
-    allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
-    dist.all_gather(allh, hnd)
-    d.p2p_connect(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh), world)
-    dist.barrier()
-    cells = gLm * gMm * N
+    gLm, gMm, N, nti, ntj = grid_for(args.workload, world)
 
-    def timed(fn):
+    def timed(d, fn):
         d.ctx.sync(); dist.barrier(); torch.cuda.synchronize()
         d.timer_start(); t0 = time.perf_counter()
         fn()
@@ -238,36 +332,73 @@ def run_ours_multi(args, rank, world):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt[0]), float(tt[1])
 
-    clk = ClockSampler(local)
-    if rank == 0:
-        clk.start()
-    d.run(max(args.warmup, 3))
-    l0 = d.ctx.launches()
-    dev_s, _ = timed(lambda: d.run(args.steps))
-    clocks = clk.stop() if rank == 0 else None
-    launches = d.ctx.launches() - l0
-    d.run(2, host_forcing=True)
-    _, e2e_s = timed(lambda: d.run(args.steps, host_forcing=True))
-    b = d.bounds()
-    ni, nj = b.UBi - b.LBi + 1, b.UBj - b.LBj + 1
-    d.finalize()
+    def one_grid(gLm, gMm, N, steps, warm, check):
+        cfg = rb.default_config(rb.APP_BENCHMARK, gLm, gMm, N)
+        gcfg = rb.default_config(rb.APP_BENCHMARK, gLm, gMm, N)
+        cfg.NtileI, cfg.NtileJ = nti, ntj
+        d = _make_distributed(rb, dist, torch, cfg, rank, world, local)
+        clk = ClockSampler(local)
+        if rank == 0:
+            clk.start()
+        d.run(warm)
+        l0 = d.ctx.launches()
+        dev_s, _ = timed(d, lambda: d.run(steps))
+        clocks = clk.stop() if rank == 0 else None
+        launches = d.ctx.launches() - l0
+        d.run(2, host_forcing=True)
+        _, e2e_s = timed(d, lambda: d.run(steps, host_forcing=True))
+        b = d.bounds()
+        ident, worst = (None, None)
+        if check:
+            ident, worst = _tiling_check(rb, dist, torch, d, gcfg, local, [(warm, False), (steps, False), (2, True), (steps, True)])
+        d.finalize()
+        dist.barrier()
+        return {"dev_s": dev_s, "e2e_s": e2e_s, "launches": launches, "clocks": clocks, "bounds": b, "ident": ident, "worst": worst,
+                "cells": gLm * gMm * N}
+
+    warm = max(args.warmup, 3)
+    r = one_grid(gLm, gMm, N, args.steps, warm, not args.no_check)
+    also = None
+    if world == 8 and args.workload == "BENCHMARK1" and not args.no_also:
+        # BASELINE.json config 4: BENCHMARK3 (2048x256x30) on 4x2 tiles of 512x128, and the same tile alone on one GPU
+        b3 = one_grid(2048, 256, 30, args.steps, warm, not args.no_check)
+        t1 = None
+        if rank == 0:
+            s = rb.Driver(rb.default_config(rb.APP_BENCHMARK, 512, 128, 30), device=local)
+            s.run(warm); s.ctx.sync(); s.timer_start(); s.run(args.steps); t1 = s.timer_stop() * 1e-3; s.finalize()
+        dist.barrier()
+        also = {"workload": "BENCHMARK3 2048x256x30 full main3d loop, 4x2 tiles of 512x128 (one per GPU)", "ms_per_step": 1e3 * b3["dev_s"] / args.steps,
+                "value": b3["cells"] * args.steps / b3["dev_s"], "unit": UNIT, "tiling_bit_identical": b3["ident"],
+                "one_gpu_512x128x30_ms_per_step": (1e3 * t1 / args.steps) if t1 else None,
+                "weak_scaling_efficiency_vs_one_tile": (t1 / b3["dev_s"]) if t1 else None}
     roof = None
     if rank == 0 and not args.no_roofline:
         peak, peak_kind = measured_peak()
         roof = roofline_step3d_t(rb, peak, peak_kind)      # single-GPU kernel measurement on rank 0's GPU
     dist.barrier()
     if rank == 0:
-        line = {"metric": METRIC, "value": cells * args.steps / dev_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+        b = r["bounds"]
+        ni, nj = b.UBi - b.LBi + 1, b.UBj - b.LBj + 1
+        cells = r["cells"]
+        cfgd = workload_config(args.workload, world)
+        notes = {"tiles": "%dx%d tiles of %dx%d, one per GPU (the N=1 line of this series is BENCHMARK1 512x64x30)" % (nti, ntj, gLm // nti, gMm // ntj),
+                "halo": ("NVLink peer mailboxes (CUDA IPC): one kernel per exchange stores the strips and corner blocks of all 8 neighbours "
+                         "into their mailboxes and raises flags; mirror halo 6, deep-halo fast loop (one 3-field swap per barotropic sub-step "
+                         "pair); NCCL only for diag's all-reduce; fast loop replayed as a CUDA graph") if os.environ.get("ROMS_B200_HALO_NCCL") is None
+                        else "NCCL send/recv (pack kernel, grouped send/recv, unpack kernel), W/E then S/N",
+                "l2": "state 0.3 GB per GPU per step > 126 MB L2, no explicit flush", "fmad": "false (parity build)"}
+        line = {"metric": METRIC, "value": cells * args.steps / r["dev_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": warm, "ms_per_step": 1e3 * r["dev_s"] / args.steps, "higher_is_better": True,
                 "scaling": "weak" if args.workload == "BENCHMARK1" else "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic (analytical BENCHMARK grid/initial state/forcing, random-free)",
-                "config": {"workload": "%dx%dx%d full main3d loop, %dx%d tiles of %dx%d (one per GPU)" % (gLm, gMm, N, nti, ntj, gLm // nti, gMm // ntj),
-                           "halo": "NVLink peer mailboxes (CUDA IPC, remote stores from the pack kernel + flags), 2-phase W/E then S/N, width 3, aggregated per kernel; NCCL for the diag all-reduce; fast loop in a CUDA graph" if os.environ.get("ROMS_B200_HALO_NCCL") is None else "NCCL send/recv, 2-phase W/E then S/N, width 3",
-                           "l2": "state 0.3 GB per GPU per step > 126 MB L2, no explicit flush", "fmad": "false (parity build)"},
-                "clocks": clocks,
-                "e2e": {"value": cells * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": ni * nj * 8 * world,
-                        "d2h_bytes_per_step": (3 * (b.Iend - b.Istr + 1) + 9) * 8 * world, "ms_per_step": 1e3 * e2e_s / args.steps},
-                "gpu_launches": launches * world, "roofline": roof, "cpu_baseline": None}
+                "config": cfgd, "notes": notes, "clocks": r["clocks"],
+                "e2e": {"value": cells * args.steps / r["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": ni * nj * 8 * world,
+                        "d2h_bytes_per_step": (3 * (b.Iend - b.Istr + 1) + 9) * 8 * world, "ms_per_step": 1e3 * r["e2e_s"] / args.steps},
+                "gpu_launches": r["launches"] * world, "roofline": roof, "cpu_baseline": None,
+                "tiling_bit_identical": r["ident"],
+                "tiling_check": {"against": "the whole grid as ONE tile on each rank's own GPU, same call sequence", "fields": "zeta,ubar,vbar,u,v,t (both time levels), tile interiors",
+                                 "steps": warm + 2 * args.steps + 2, "max_abs_diff": r["worst"]},
+                "also": also}
         print(json.dumps(line))
     dist.destroy_process_group()
 
@@ -280,8 +411,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="BENCHMARK1", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--parity-steps", type=int, default=100)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--no-also", action="store_true")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":

@@ -24,6 +24,8 @@
 #include <vector>
 #ifndef ROMS_B200_EMU
 #include <cuda.h>       // CUtensorMap and its enums (types only: the encoder is fetched with cudaGetDriverEntryPoint)
+#else
+#include <mutex>
 #endif
 
 namespace {
@@ -78,12 +80,18 @@ template <int NTR, bool TM> struct Lay {
 // ---- host emulation of mbarriers and TMA box loads (tests/emu): the threads of a block are cooperative fibers, a wait yields.
 // word: bit 63 phase, bits 48..62 arrival count per phase, bits 32..47 pending arrivals, bits 0..31 pending transaction bytes (signed)
 struct EmuBar { int32_t tx; uint16_t pending; uint16_t init_phase; };
+static std::mutex emu_bar_mu;                    // the AddressSanitizer build runs the threads of a block as OS threads
 __device__ __forceinline__ EmuBar* eb(uint64_t* b) { return (EmuBar*)b; }
 __device__ __forceinline__ void eb_check(EmuBar* e) { if (e->pending == 0 && e->tx == 0) { e->pending = e->init_phase & 0x7fff; e->init_phase ^= 0x8000; } }
-__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) { EmuBar* e = eb(b); e->tx = 0; e->pending = (uint16_t)count; e->init_phase = (uint16_t)count; }
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) { EmuBar* e = eb(b); if (e->pending == 0) abort(); --e->pending; eb_check(e); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) { EmuBar* e = eb(b); e->tx += (int32_t)bytes; if (e->pending == 0) abort(); --e->pending; eb_check(e); }
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int*) { while (((eb(b)->init_phase >> 15) & 1u) == parity) emu::yield(); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) { std::lock_guard<std::mutex> lk(emu_bar_mu); EmuBar* e = eb(b); e->tx = 0; e->pending = (uint16_t)count; e->init_phase = (uint16_t)count; }
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) { std::lock_guard<std::mutex> lk(emu_bar_mu); EmuBar* e = eb(b); if (e->pending == 0) abort(); --e->pending; eb_check(e); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) { std::lock_guard<std::mutex> lk(emu_bar_mu); EmuBar* e = eb(b); e->tx += (int32_t)bytes; if (e->pending == 0) abort(); --e->pending; eb_check(e); }
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int*) {
+  for (;;) {
+    { std::lock_guard<std::mutex> lk(emu_bar_mu); if (((eb(b)->init_phase >> 15) & 1u) != parity) return; }
+    emu::yield();
+  }
+}
 __device__ __forceinline__ void tma3d(double* dst, const TMap* m, int c0, int c1, int c2, uint64_t* bar) {
   if ((c0 & 1) || ((uintptr_t)dst & 127)) { fprintf(stderr, "emu: TMA box start not 16-byte aligned in global memory (column %d) or destination not 128-byte aligned\n", c0); abort(); }
   for (int z = 0; z < m->box[2]; ++z) for (int y = 0; y < m->box[1]; ++y) for (int x = 0; x < m->box[0]; ++x) {
@@ -91,6 +99,7 @@ __device__ __forceinline__ void tma3d(double* dst, const TMap* m, int c0, int c1
     const bool in = X >= 0 && X < m->dim[0] && Y >= 0 && Y < m->dim[1] && Z >= 0 && Z < m->dim[2];
     dst[((size_t)z * m->box[1] + y) * m->box[0] + x] = in ? m->base[X + m->stride[1] * Y + m->stride[2] * Z] : 0.0;
   }
+  std::lock_guard<std::mutex> lk(emu_bar_mu);
   EmuBar* e = eb(bar); e->tx -= 8 * m->box[0] * m->box[1] * m->box[2]; eb_check(e);
 }
 __device__ __forceinline__ void fence_barrier_init() {}
@@ -299,6 +308,7 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
       const int ic = min(max(i0s + col, a.i0), a.i1);   // idle lanes shadow an active column for the 2-D metric loads
       const bool southw = a.wallS && ja == a.Jstr;
       int o2 = (ic - a.LBi) + a.ni * (ja - a.LBj);
+      double cffn = dt * __ldg(a.pm + o2) * __ldg(a.pn + o2);         // dt*pm*pn of the chunk's first row (later rows: one row ahead)
       for (int r = 0; r < nrows + 4; ++r) {
         mbar_wait(&ring_full[gi], gph, a.err);
         const int g0 = gi;                                            // row n
@@ -347,8 +357,11 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
           // ---- row j = n-2: q = (t(nnew) - dt*pm*pn*(div_h F + d_k FC)) / Hz  into the slot, in place
           const int j = ja + r - 4, sl = q.i;
           const bool lastN = a.wallN && (j == a.Jend);                // FE(i,Jend+2)=FE(i,Jend+1) (step3d_t.F:718-724)
-          const double cff = dt * __ldg(a.pm + o2) * __ldg(a.pn + o2);
+          const double cff = cffn;
           o2 += a.ni;
+          const bool more = (r < nrows + 3);
+          double pmn = 0.0, pnn = 0.0;
+          if (more) { pmn = __ldg(a.pm + o2); pnn = __ldg(a.pn + o2); }    // metrics of the next row: requested now, used after the batches
           mbar_wait(&slot_full[sl], q.ph, a.err);
           double* sp = slots + sl * slotD;
 #pragma unroll
@@ -401,6 +414,7 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(&slot_ready[sl]);
           q.next();
+          if (more) cffn = dt * pmn * pnn;
         }
         // ---- the oldest row of the ring is no longer needed (the last step of a chunk frees all three)
         __syncwarp();
@@ -634,7 +648,7 @@ int k_step3d_t_v8(roms_b200_ctx* c, int nnew) {
     for (int s = (force_s ? force_s : 6); s >= 2 && !S; --s) if (smem_v8(ntr, tm, N, s) <= (size_t)max_smem) S = s;
     if (!S) return 2;
     static const int force_nc = getenv("ROMS_B200_S3T_NC") ? atoi(getenv("ROMS_B200_S3T_NC")) : 0;
-    const int NC = force_nc ? force_nc : (S >= 4 ? S - 2 : 1);
+    const int NC = force_nc ? force_nc : (S >= 5 ? 3 : (S == 4 ? 2 : 1));      // measured: 3 consumer warps are enough for 8 producer warps
     if (NC > 4 || NC >= S) return 2;
     // producer warps x level-pair batches per warp: NP*KP >= ceil(N/2), at most 16 warps per CTA
     const int nb = (N + 1) / 2;

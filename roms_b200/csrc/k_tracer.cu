@@ -142,71 +142,17 @@ int k_pre_step3d(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int nt
   return 0;
 }
 
-// ---- step3d_t_tile: step3d_t.F:393-399,641-916,1150-1365,1672-1721,1858-1924 ---
-// One pass: read t(3) (+halo through L1), Huon,Hvom,W,Hz,Akt once; read+write
-// t(nnew) once.  Algorithmic traffic 48 B per tracer-cell + 32 B per cell.
-__global__ void __launch_bounds__(256) step3d_t_kernel(const Dev D, Box bx, int nnew) {
-  IJ_FROM_BOX(bx);
-  const int itrc = 1 + blockIdx.z, N = D.b.N; const double dt = D.p.dt;
-  const Edges e = edges(D);
-  V3 Hz = v3(D, FID(Hz)), Huon = v3(D, FID(Huon)), Hvom = v3(D, FID(Hvom)), W = v3(D, FID(W));
-  V3 t3 = v3l(D, FID(t), 3, itrc), tw = v3l(D, FID(t), nnew, itrc), Akt = v3l(D, FID(Akt), min(D.b.NAT, itrc));
-  const double cff = dt * v2(D, FID(pm))(i, j) * v2(D, FID(pn))(i, j);
-  double q[RB_MAXN + 2], oHz[RB_MAXN + 2], CF[RB_MAXN + 1], DC[RB_MAXN + 1];
-  double FCm = 0.0;
-  for (int k = 1; k <= N; ++k) {
-    const double FXi = fluxX_u3(t3, Huon, i, j, k), FXp = fluxX_u3(t3, Huon, i + 1, j, k);
-    const double FEj = fluxE_u3(t3, Hvom, i, j, k, e), FEp = fluxE_u3(t3, Hvom, i, j + 1, k, e);
-    const double c1 = cff * (FXp - FXi), c2 = cff * (FEp - FEj), c3 = c1 + c2;
-    double tv = tw(i, j, k) - c3;
-    const double FCk = fluxZ_c4(t3, W, i, j, k, N);
-    const double cv = cff * (FCk - FCm);
-    oHz[k] = 1.0 / Hz(i, j, k);
-    tv = tv - cv;
-    q[k] = tv * oHz[k];
-    FCm = FCk;
-  }
-  // spline implicit vertical diffusion (step3d_t.F:1672-1721)
-  CF[0] = 0.0; DC[0] = 0.0;
-  {
-    double hz_k = Hz(i, j, 1), ak_km = Akt(i, j, 0), ak_k = Akt(i, j, 1);
-    for (int k = 1; k <= N - 1; ++k) {
-      const double hz_kp = Hz(i, j, k + 1), ak_kp = Akt(i, j, k + 1);
-      const double FC = (1.0 / 6.0) * hz_k - dt * ak_km * oHz[k];
-      const double CFk = (1.0 / 6.0) * hz_kp - dt * ak_kp * oHz[k + 1];
-      const double BC = (1.0 / 3.0) * (hz_k + hz_kp) + dt * ak_k * (oHz[k] + oHz[k + 1]);
-      const double cf = 1.0 / (BC - FC * CF[k - 1]);
-      CF[k] = cf * CFk;
-      DC[k] = cf * (q[k + 1] - q[k] - FC * DC[k - 1]);
-      hz_k = hz_kp; ak_km = ak_k; ak_k = ak_kp;
-    }
-  }
-  DC[N] = 0.0;
-  for (int k = N - 1; k >= 1; --k) DC[k] = DC[k] - CF[k] * DC[k + 1];
-  double dcm = DC[0];
-  for (int k = 1; k <= N; ++k) {
-    const double dck = DC[k] * Akt(i, j, k);
-    const double c1 = dt * oHz[k] * (dck - dcm);
-    st_tbc(D, tw, i, j, k, q[k] + c1, e);
-    dcm = dck;
-  }
-}
+// ---- step3d_t_tile: step3d_t.F:393-1924 -> k_step3d_t8.cu (production), k_step3d_t6.cu, k_step3d_t4.cu
 int k_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew) {
   (void)nrhs; (void)nstp;
-  // production: the warp-specialised 2.5-D j-march of k_step3d_t6.cu; it declines (rc 2) closed W/E walls and N < 4, which fall
-  // back to the column march of k_step3d_t4.cu.  ROMS_B200_STEP3D_T_V4 / _V1 select the older layouts for A/B timing
-  // (the shared-memory column variants v2/v3 and the TMA-tensor variant v5 of the first session were slower or broken and are gone).
-  static const bool use_v1 = (getenv("ROMS_B200_STEP3D_T_V1") != nullptr);   // first (local-memory) version
+  // production: the TMA/mbarrier layout of k_step3d_t8.cu; it declines (rc 2) closed W/E walls, N < 4 and level counts whose
+  // slots do not fit shared memory (N > ~60), which fall back to the warp-specialised j-march of k_step3d_t6.cu (round 1) and
+  // from there to the column march of k_step3d_t4.cu.  ROMS_B200_S3T_V8=0 / ROMS_B200_STEP3D_T_V4=1 select them for A/B timing.
   static const bool use_v4 = (getenv("ROMS_B200_STEP3D_T_V4") != nullptr);   // one-thread-per-column checkpointed Thomas
-  static const bool use_v7 = (getenv("ROMS_B200_STEP3D_T_V7") != nullptr);   // experimental variant of v6 (k_step3d_t7.cu)
-  static const bool no_v8 = (getenv("ROMS_B200_S3T_V8") != nullptr && atoi(getenv("ROMS_B200_S3T_V8")) == 0);   // TMA/mbarrier layout (k_step3d_t8.cu)
-  if (!use_v1 && !use_v4 && !use_v7 && !no_v8) { const int rc = k_step3d_t_v8(c, nnew); if (rc != 2) return rc; }
-  if (!use_v1 && !use_v4) { const int rc = use_v7 ? k_step3d_t_v7(c, nnew) : k_step3d_t_v6(c, nnew); if (rc != 2) return rc; }
-  if (!use_v1) return k_step3d_t_v4(c, nnew);
-  const roms_b200_bounds& b = c->D.b;
-  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT;
-  step3d_t_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nnew); c->launches++;
-  return 0;
+  static const bool no_v8 = (getenv("ROMS_B200_S3T_V8") != nullptr && atoi(getenv("ROMS_B200_S3T_V8")) == 0);
+  if (!use_v4 && !no_v8) { const int rc = k_step3d_t_v8(c, nnew); if (rc != 2) return rc; }
+  if (!use_v4) { const int rc = k_step3d_t_v6(c, nnew); if (rc != 2) return rc; }
+  return k_step3d_t_v4(c, nnew);
 }
 
 // ---- t3dmix2_s_tile, t3dmix2_s.h:198-301 (MIX_S_TS, UPWELLING) ---------------

@@ -1,8 +1,8 @@
 """Child process of tests/test_emu.py -- TEST INFRASTRUCTURE ONLY.
 Loads tests/emu/libroms_b200_emu.so (the kernel SOURCES of roms_b200/csrc built with g++, see tests/emu/include/cuda_runtime.h)
 in place of the CUDA library and runs the per-kernel parity protocol of tests/test_gpu_parity.py against the oracle.
-Runs in its own process because the switches it needs (no CUDA graph, no programmatic launch, column step3d_t) are read once
-per process by the library.   usage: emu_worker.py [driver] APP Lm Mm N NSTEPS [v6]"""
+Runs in its own process because the switches it needs (no CUDA graph, no programmatic launch, step3d_t layout) are read once
+per process by the library.   usage: emu_worker.py [driver|tiles|eos] APP Lm Mm N NSTEPS [v8|v6|v4]"""
 import os
 import sys
 
@@ -10,12 +10,9 @@ os.environ["ROMS_B200_NO_GRAPH"] = "1"
 os.environ["ROMS_B200_NO_PDL"] = "1"
 if "v4" in sys.argv:                          # the column-march fallback (closed W/E walls, N < 4): k_step3d_t4.cu
     os.environ["ROMS_B200_STEP3D_T_V4"] = "1"
-elif "v7" in sys.argv:                        # experimental variant of v6 (k_step3d_t7.cu)
-    os.environ["ROMS_B200_STEP3D_T_V7"] = "1"
-elif "v6" in sys.argv:                        # the round-1 production kernel k_step3d_t6.cu (named barriers, warp vote emulated)
-    os.environ["ROMS_B200_S3T_V8"] = "0"
-elif "v8" not in sys.argv:                    # "v8": the production kernel k_step3d_t8.cu (mbarriers and TMA boxes emulated),
-    os.environ["ROMS_B200_STEP3D_T_V1"] = "1"  # else the plain column kernel
+elif "v6" in sys.argv:                        # the round-1 warp-specialised kernel k_step3d_t6.cu (fallback for shapes the production
+    os.environ["ROMS_B200_S3T_V8"] = "0"      # kernel declines): named barriers and the warp vote emulated
+# default ("v8"): the production dispatch -> k_step3d_t8.cu (mbarriers, TMA boxes and tensor memory emulated)
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(HERE))

@@ -10,20 +10,34 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIB = None
+_FAST = None
 
 UPWELLING, BENCHMARK = 0, 1
 
 
 def build():
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(ROOT, "oracle"), "all"])
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        path = os.path.join(ROOT, "oracle", "liboracle.so")
-        if not os.path.exists(path):
-            build()
+def fast_lib_path():
+    """The timed CPU-baseline build (bench.py only, never a checker): -O3, FMA contraction; built with -march=native on the box that
+    runs the benchmark when a compiler is there (make native), else the x86-64-v3 build shipped with the snapshot."""
+    native = os.path.join(ROOT, "oracle", "_native", "liboracle_fast.so")
+    try:
+        subprocess.run(["make", "-s", "-j8", "-C", os.path.join(ROOT, "oracle"), "native"], check=True, timeout=300,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except Exception:
+        pass
+    if os.path.exists(native):
+        return native, "-O3 -march=native -ffp-contract=fast"
+    path = os.path.join(ROOT, "oracle", "liboracle_fast.so")
+    if not os.path.exists(path):
+        build()
+    return path, "-O3 -march=x86-64-v3 -ffp-contract=fast"
+
+
+def _bind(path):
+    if True:
         L = C.CDLL(path)
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.c_int] * 6
@@ -39,8 +53,26 @@ def lib():
             f.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
         for f in (L.orc_get_dims, L.orc_get_stepping, L.orc_set_stepping, L.orc_get_scalars, L.orc_get_ksbl, L.orc_get_diag):
             f.argtypes = [C.c_void_p, C.c_void_p]
-        _LIB = L
+    return L
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(ROOT, "oracle", "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = _bind(path)
     return _LIB
+
+
+def fast_lib():
+    """(library, compiler flags) of the timed CPU-baseline build."""
+    global _FAST
+    if _FAST is None:
+        path, flags = fast_lib_path()
+        _FAST = (_bind(path), flags)
+    return _FAST
 
 
 PHASES = ["begin", "set_massflux", "rho_eos", "diag", "bulk_flux", "set_vbc", "vmix", "omega", "wvelocity", "set_zeta",
@@ -59,8 +91,8 @@ ALL_FIELDS = FIELDS_2D + FIELDS_ND
 
 
 class Oracle:
-    def __init__(self, app, Lm=0, Mm=0, N=0, NtileI=1, NtileJ=1, dt=None, ndtfast=None):
-        self.L = lib()
+    def __init__(self, app, Lm=0, Mm=0, N=0, NtileI=1, NtileJ=1, dt=None, ndtfast=None, fast=False):
+        self.L = fast_lib()[0] if fast else lib()
         self.h = self.L.orc_create(app, Lm, Mm, N, NtileI, NtileJ)
         if dt is not None:
             self.L.orc_set_dt(self.h, dt, ndtfast)

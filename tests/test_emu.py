@@ -3,7 +3,7 @@ run through the same per-kernel parity protocol as tests/test_gpu_parity.py -- p
 point through the C ABI, compare every field of the mirror with the oracle.  This pins loop bounds, stencil indices and
 operation order of a kernel before it ever reaches a GPU (the build container has none).  It says nothing about speed, about
 races between blocks, or about the halo transport (k_halo.cu is not built; the multi-tile test replaces it by in-process
-copies), which only the GPU runs cover.  The production step3d_t (k_step3d_t6.cu) IS built: its PTX helpers have host alternates.
+copies), which only the GPU runs cover.  The production step3d_t (k_step3d_t8.cu) IS built: its PTX helpers have host alternates.
 The emulation library is test infrastructure: the product never loads it."""
 import os
 import subprocess
@@ -22,17 +22,17 @@ def emu_lib():
 
 
 # app, Lm, Mm, N, steps, step3d_t kernel, emulated SM count: UPWELLING (linear EOS, ana_vmix, t3dmix2_s) on a small channel;
-# BENCHMARK (UNESCO EOS, KPP, bulk fluxes, geopotential mixing, curvilinear terms) on ragged grids: Lm not a multiple of 32,
-# fewer rows than a block, N = 30.  "v6" = the production warp-specialised step3d_t (k_step3d_t6.cu: 10-18 warps per CTA as a
-# team of real threads, named barriers and the warp vote emulated); with 2-3 "SMs" a CTA marches many rows (ring reuse,
-# EMPTY barriers), with 148 every CTA gets one or two rows (start-up path).  "v1" = the plain column kernel, "v4" = the
-# shuffle-based column march (the production kernel's fallback for closed W/E walls and N < 4).
-# "v7" = the experimental build of the same source (k_step3d_t7.cu: producers decoupled through a per-slot counter, x-neighbours
-# by warp shuffle on full stripes, loads on the ragged last stripe), opt-in on the GPU with ROMS_B200_STEP3D_T_V7=1.
-CASES = [(0, 24, 10, 8, 3, "v6", 3), (0, 0, 0, 0, 2, "v6", 148),                       # UPWELLING small and as shipped (41x80x16)
-         (1, 20, 6, 8, 3, "v6", 2), (1, 33, 5, 9, 3, "v6", 2), (1, 70, 9, 30, 3, "v6", 148), (1, 45, 7, 50, 2, "v6", 2),
-         (1, 40, 6, 64, 2, "v6", 148),                                                      # the ragged shapes of the GPU tests
-         (1, 33, 9, 10, 2, "v1", 148), (1, 33, 9, 10, 2, "v4", 148), (1, 70, 9, 30, 2, "v7", 2), (1, 45, 7, 50, 1, "v7", 2)]
+# BENCHMARK (UNESCO EOS, KPP, bulk fluxes, geopotential mixing, curvilinear terms) on ragged grids: Lm not a multiple of 16,
+# fewer rows than a chunk, N = 30.  "v8" = the production step3d_t (k_step3d_t8.cu: loader / producer / consumer warps as fibers,
+# mbarriers with transaction counts, TMA boxes with out-of-bound fill and the 16-byte start rule, tensor-memory lanes emulated):
+# with 1-3 "SMs" a persistent CTA walks several work items (ring and slot recycling across items), with 148 every CTA gets one.
+# N = 9 / 50: odd level count / four level pairs per producer warp; N = 64: the slots do not fit -> falls back to "v6", the
+# round-1 warp-specialised kernel (k_step3d_t6.cu: named barriers, warp vote), which is also run on its own; "v4" = the
+# shuffle-based column march (the fallback for closed W/E walls and N < 4).
+CASES = [(0, 24, 10, 8, 3, "v8", 3), (0, 0, 0, 0, 2, "v8", 148),                       # UPWELLING small and as shipped (41x80x16)
+         (1, 20, 6, 8, 3, "v8", 2), (1, 33, 5, 9, 3, "v8", 2), (1, 70, 9, 30, 3, "v8", 148), (1, 70, 9, 30, 2, "v8", 1),
+         (1, 45, 7, 50, 2, "v8", 2), (1, 40, 6, 64, 2, "v8", 148),                          # the ragged shapes of the GPU tests
+         (1, 70, 9, 30, 2, "v6", 2), (1, 45, 7, 50, 1, "v6", 2), (1, 33, 9, 10, 2, "v4", 148)]
 
 
 @pytest.mark.parametrize("app,Lm,Mm,N,steps,s3t,nsm", CASES)
@@ -55,12 +55,14 @@ def test_tiling_invariance_on_emulated_kernels(emu_lib, app, Lm, Mm, N, steps, n
     assert r.returncode == 0 and "EMU-TILES-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
-@pytest.mark.parametrize("seed,s3t", [(1, "v6"), (2, "v7")])
-def test_step3d_t_synchronisation_under_random_schedules(emu_lib, seed, s3t):
-    """The warp-specialised step3d_t (ring slots, named barriers, per-slot counters in the experimental variant) with the threads
-    of a block resumed in a pseudo-random order at every scheduling pass: results must not depend on the schedule."""
+@pytest.mark.parametrize("seed,s3t,extra", [(1, "v8", {"ROMS_B200_S3T_JCH": "3"}), (2, "v8", {"ROMS_B200_S3T_SLOTS": "2"}),
+                                            (3, "v8", {"ROMS_B200_S3T_TMEM": "0"}), (4, "v6", {})])
+def test_step3d_t_synchronisation_under_random_schedules(emu_lib, seed, s3t, extra):
+    """The pipelined step3d_t (TMA ring and slots handed over through full/ready/empty mbarriers; named barriers in the round-1
+    kernel) with the threads of a block resumed in a pseudo-random order at every scheduling pass, with short chunks (many work
+    items per CTA), the minimum number of slots, and the shared-memory CF/DC variant: results must not depend on the schedule."""
     r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "1", "70", "9", "30", "2", s3t], capture_output=True, text=True,
-                       timeout=900, env=dict(os.environ, EMU_SM_COUNT="2", EMU_SCHED_SEED=str(seed)))
+                       timeout=900, env=dict(os.environ, EMU_SM_COUNT="1", EMU_SCHED_SEED=str(seed), **extra))
     assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
@@ -87,7 +89,10 @@ def test_kernel_sources_memory_safe_under_asan(emu_lib):
     subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(HERE, "emu"), "ASAN=1"])
     env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0", EMU_WORKER_LIB="libroms_b200_emu_asan.so", EMU_SM_COUNT="2",
                EMU_TEAM="threads")          # AddressSanitizer does not follow swapcontext: OS-thread teams
-    r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "1", "33", "9", "10", "2", "v6"], capture_output=True, text=True,
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "1", "33", "9", "10", "2", "v8"], capture_output=True, text=True,
+                       timeout=900, env=env)
+    assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout and "AddressSanitizer" not in r.stderr, r.stdout[-2000:] + r.stderr[-4000:]
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "1", "33", "9", "10", "1", "v6"], capture_output=True, text=True,
                        timeout=900, env=env)
     assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout and "AddressSanitizer" not in r.stderr, r.stdout[-2000:] + r.stderr[-4000:]
 
