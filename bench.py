@@ -123,14 +123,14 @@ def parity_vs_oracle(rb, workload, nsteps):
     d = rb.Driver(rb.default_config(rb.APP_BENCHMARK, Lm, Mm, N), device=0)
     d.run(nsteps)
     d.ctx.sync()
-    rel = {}
-    for n in PROGNOSTIC:
-        a, g = o.get(n), d.ctx.download(n)
-        rel[n] = float(np.max(np.abs(a - g))) / max(float(a.max() - a.min()), 1e-300)
+    from parity_common import prognostic_errors
+    rel, own = prognostic_errors(o.get, d.ctx.download)
     d.finalize()
     worst = max(rel.values())
     return {"against": "oracle (checker build -O2 -ffp-contract=off, %dx%d tiles)" % (nti, ntj), "workload": "%s %dx%dx%d" % (workload, Lm, Mm, N),
-            "steps": nsteps, "max_rel": worst, "tolerance": 1e-10, "ok": bool(worst <= 1e-10), "per_field": rel}
+            "steps": nsteps, "max_rel": worst, "tolerance": 1e-10, "ok": bool(worst <= 1e-10), "per_field": rel,
+            "scale": "max-norm of the difference / range of the field; velocity components / range of the larger component of their vector",
+            "per_field_over_own_range": own}
 
 
 def run_reference(args, rank, world):

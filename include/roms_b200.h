@@ -111,9 +111,11 @@ int roms_b200_halo_plan(const roms_b200_bounds* b, int halo, int* ranks8, int* s
  *      after ROMS_allocate_arrays, Drivers/nl_roms.h:180, and from ROMS_finalize) */
 int roms_b200_create(const roms_b200_bounds* b, const roms_b200_params* p, int device, roms_b200_ctx** out);
 int roms_b200_destroy(roms_b200_ctx* ctx);
-/* S-coordinate vectors sc_r,Cs_r(1:N) and sc_w,Cs_w(0:N): SCALARS(ng)%... (Utility/set_scoord.F) */
+/* S-coordinate vectors exactly as the reference allocates them (mod_scalars.F:1950-1968): sc_r, Cs_r hold N values (levels 1:N,
+ * first element = level 1), sc_w, Cs_w hold N+1 values (levels 0:N): SCALARS(ng)%... (Utility/set_scoord.F) */
 int roms_b200_set_scoord(roms_b200_ctx* ctx, const double* sc_r, const double* Cs_r, const double* sc_w, const double* Cs_w);
-/* weight(1,1:nfast+1,ng), weight(2,...) (Utility/set_weights.F); arrays are 1-based: w[0] unused, length >= nfast+2 */
+/* weight(1,:,ng), weight(2,:,ng) (Utility/set_weights.F); arrays are 1-based: w[0] unused, entries 1..nfast+2 are read
+ * (length >= nfast+3) */
 int roms_b200_set_weights(roms_b200_ctx* ctx, int nfast, const double* weight1, const double* weight2);
 
 /* ---- host <-> device mirror (c_loc of the module array) */

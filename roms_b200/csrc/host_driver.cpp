@@ -315,7 +315,7 @@ int roms_b200_ROMS_initialize(const roms_b200_config* cfg, int tile, int distrib
   p.Akt_bak[0] = cfg->Akt_bak[0]; p.Akt_bak[1] = cfg->Akt_bak[1]; p.Akv_bak = cfg->Akv_bak;
   p.blk_ZQ = cfg->blk_ZQ; p.blk_ZT = cfg->blk_ZT; p.blk_ZW = cfg->blk_ZW; p.dstart = 0.0;
   if (roms_b200_create(&d->b, &p, device, &d->ctx)) { delete d; return 2; }
-  int rc = roms_b200_set_scoord(d->ctx, d->sc_r.data(), d->Cs_r.data(), d->sc_w.data(), d->Cs_w.data());
+  int rc = roms_b200_set_scoord(d->ctx, d->sc_r.data() + 1, d->Cs_r.data() + 1, d->sc_w.data(), d->Cs_w.data());   // (1:N), (1:N), (0:N), (0:N)
   rc |= roms_b200_set_weights(d->ctx, d->nfast, d->w1.data(), d->w2.data());
   rc |= host_grid(d);
   // Nonlinear/initial.F:277-577: set_depth -> ana_initial -> set_depth -> set_massflux -> omega, rho_eos
@@ -347,6 +347,13 @@ int roms_b200_ROMS_run(roms_b200_driver* d, int nsteps, int host_forcing, double
     // diag is launched at its place in every step (NINFO=1 as shipped, roms_benchmark1.in:264) but only the last one is read
     rc = roms_b200_main3d(d->ctx, nsteps, 1, 2);
     rc |= roms_b200_diag_end(d->ctx, d->last_diag);
+    double full[ROMS_B200_NDIAG];
+    roms_b200_diag_last(d->ctx, full);
+    if (!rc && full[12] != 0.0) {                     // diag.F:512-542 on the last step's start state (earlier steps are not read back)
+      fprintf(stderr, "roms_b200: blow-up detected by diag (avgke %g, avgpe %g, maxspeed %g, maxrho %g)\n", full[0], full[1], full[10], full[11]);
+      rc = 1;
+    }
+    if (!rc) rc = roms_b200_sync(d->ctx);             // device error word (non-finite reciprocal operands in the tridiagonal solves)
   } else {
     // Software pipeline over steps: the host evaluates set_data of step s+1 into the other pinned slot while the device
     // runs step s; uploads and the diag read-back are asynchronous copies on the launch stream (same data, same order).

@@ -646,7 +646,7 @@ int k_step3d_t_v8(roms_b200_ctx* c, int nnew) {
     // (with tensor memory each consumer warp needs its own lane quadrant: warps 1..4)
     int S = 0;
     for (int s = (force_s ? force_s : 6); s >= 2 && !S; --s) if (smem_v8(ntr, tm, N, s) <= (size_t)max_smem) S = s;
-    if (!S) return 2;
+    if (!S || (S < 4 && !force_s)) return 2;       // fewer than 4 slots (N > ~40) cannot overlap load, advection and solve: k_step3d_t6.cu is faster there
     static const int force_nc = getenv("ROMS_B200_S3T_NC") ? atoi(getenv("ROMS_B200_S3T_NC")) : 0;
     const int NC = force_nc ? force_nc : (S >= 5 ? 3 : (S == 4 ? 2 : 1));      // measured: 3 consumer warps are enough for 8 producer warps
     if (NC > 4 || NC >= S) return 2;

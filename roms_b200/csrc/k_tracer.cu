@@ -132,14 +132,23 @@ __global__ void __launch_bounds__(256) pre_step3d_uv_kernel(const Dev D, Box bx,
   qn(i, j, k) = val;
 }
 
-int k_pre_step3d(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntfirst) {
+// pre_step3d_tile in its two independent halves: tracers (pre_step3d.F:329-957) and momentum (:960-1168)
+int k_pre_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntfirst) {
+  (void)nrhs;
   const roms_b200_bounds& b = c->D.b;
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT * b.N;
   pre_step3d_t_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nstp, nnew, iic == ntfirst ? 1 : 0); c->launches++;
-  g.z = 2 * b.N;
+  return 0;
+}
+int k_pre_step3d_uv(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntfirst) {
+  const roms_b200_bounds& b = c->D.b;
+  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = 2 * b.N;
   const int mode = (iic == ntfirst) ? 0 : (iic == ntfirst + 1 ? 1 : 2);
   pre_step3d_uv_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs, nstp, nnew, mode); c->launches++;
   return 0;
+}
+int k_pre_step3d(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntfirst) {
+  return k_pre_step3d_t(c, nrhs, nstp, nnew, iic, ntfirst) | k_pre_step3d_uv(c, nrhs, nstp, nnew, iic, ntfirst);
 }
 
 // ---- step3d_t_tile: step3d_t.F:393-1924 -> k_step3d_t8.cu (production), k_step3d_t6.cu, k_step3d_t4.cu
@@ -265,9 +274,10 @@ int k_t3dmix2(roms_b200_ctx* c, int nrhs, int nstp, int nnew) {
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT;
   if (c->D.p.app == ROMS_B200_APP_UPWELLING) t3dmix2_s_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs, nnew);
   else {
-    // dTdz once per point into the KPP scratch volumes (free between lmd_vmix calls; 4 volumes of (ni,nj,0:N)), on the points
-    // the fluxes of the interior reach: i-1..i+1, j-1..j+1
-    double* scratch = (c->D.kpp4 && b.NT <= 4) ? c->D.kpp4 : nullptr;
+    // dTdz once per point into its own scratch volumes (NT volumes of (ni,nj,0:N); not the KPP scratch: the tracer branch of
+    // main3d runs beside uv3dmix2, which parks its column terms there), on the points the fluxes of the interior reach:
+    // i-1..i+1, j-1..j+1
+    double* scratch = c->D.dtdz;
     if (scratch) {
       Box bd{b.Istr - 1, b.Iend + 1, b.Jstr - 1, b.Jend + 1}; dim3 gd = grid2(bd, blk); gd.z = b.NT * (b.N + 1);
       geo_dTdz_kernel<<<gd, blk, 0, c->stream>>>(c->D, bd, nrhs, scratch); c->launches++;

@@ -72,6 +72,8 @@ int roms_b200_create(const roms_b200_bounds* b, const roms_b200_params* p, int d
   CUDA_OK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  for (int q = 0; q < 6; ++q) CUDA_OK(cudaEventCreateWithFlags(&c->ev[q], cudaEventDisableTiming));
+  c->two_streams = (getenv("ROMS_B200_ONE_STREAM") == nullptr);
   for (int f = 0; f < ROMS_B200_NFIELDS; ++f) {
     const int nk = resolve(kFields[f].nk, *b), nl = resolve(kFields[f].nl, *b), nm = resolve(kFields[f].nm, *b);
     D.kLB[f] = kFields[f].kLB; D.nk[f] = nk; D.nl[f] = nl;
@@ -87,8 +89,9 @@ int roms_b200_create(const roms_b200_bounds* b, const roms_b200_params* p, int d
   if (dev_alloc(&D.scratch2, D.nij * 8)) return 4;
   // four 3-D scratch volumes (ni,nj,0:N): KPP {dR, dU, dV, FC}, t3dmix2_geo dTdz per tracer, uv3dmix2's rufrc/rvfrc terms
   if (dev_alloc(&D.kpp4, D.nij * (size_t)(b->N + 1) * 4)) return 4;
-  if (p->app == ROMS_B200_APP_BENCHMARK) {          // KPP surface buoyancy flux profile Bflux
+  if (p->app == ROMS_B200_APP_BENCHMARK) {          // KPP surface buoyancy flux profile Bflux ; dTdz of t3dmix2_geo per tracer
     if (dev_alloc(&D.swdk, D.nij * (size_t)(b->N + 1))) return 4;
+    if (dev_alloc(&D.dtdz, D.nij * (size_t)(b->N + 1) * b->NT)) return 4;
   }
   // diag (k_grid.cu): 3 sums per interior column i + 9 maxima + 9 per block of 128 columns of a row
   const size_t nred = (size_t)3 * D.ni + 16 + 12 * 64 + (size_t)9 * ((D.ni + 127) / 128) * D.nj;   // + one 12-double slot per tile (<= 64)
@@ -109,22 +112,25 @@ int roms_b200_destroy(roms_b200_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (int a = 0; a < 12; ++a) if (c->graph2d[a]) cudaGraphExecDestroy(c->graph2d[a]);
   for (int f = 0; f < ROMS_B200_NFIELDS; ++f) cudaFree(c->D.f[f]);
-  cudaFree((void*)c->D.sc_r); cudaFree((void*)c->D.w1); cudaFree(c->D.P); cudaFree(c->D.scratch2); cudaFree(c->D.swdk); cudaFree(c->D.kpp4); cudaFree(c->D.red); cudaFree(c->D.ksbl); cudaFree(c->D.err);
+  cudaFree((void*)c->D.sc_r); cudaFree((void*)c->D.w1); cudaFree(c->D.P); cudaFree(c->D.scratch2); cudaFree(c->D.swdk); cudaFree(c->D.dtdz); cudaFree(c->D.kpp4); cudaFree(c->D.red); cudaFree(c->D.ksbl); cudaFree(c->D.err);
   cudaFreeHost(c->h_red);
   if (c->snap_stream) { cudaStreamSynchronize(c->snap_stream); cudaStreamDestroy(c->snap_stream); cudaEventDestroy(c->snap_ready); cudaEventDestroy(c->snap_done); }
   cudaFree(c->snap_buf);
   roms_b200_comm_destroy(c);
   cudaStreamDestroy(c->stream); cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
+  for (int q = 0; q < 6; ++q) cudaEventDestroy(c->ev[q]);
   delete c;
   return 0;
 }
 
 int roms_b200_set_scoord(roms_b200_ctx* c, const double* sc_r, const double* Cs_r, const double* sc_w, const double* Cs_w) {
-  const int n = c->D.b.N + 1;   // host arrays are indexed k (sc_r[0], Cs_r[0] unused)
-  CUDA_OK(cudaMemcpy((void*)c->D.sc_r, sc_r, n * sizeof(double), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy((void*)c->D.Cs_r, Cs_r, n * sizeof(double), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy((void*)c->D.sc_w, sc_w, n * sizeof(double), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy((void*)c->D.Cs_w, Cs_w, n * sizeof(double), cudaMemcpyHostToDevice));
+  // the reference allocates SCALARS(ng)%sc_r, Cs_r as (1:N) and sc_w, Cs_w as (0:N) (mod_scalars.F:1950-1968): the host passes the
+  // arrays as they are; the kernels index all four by level k, so the rho-level vectors go to device offset 1
+  const int N = c->D.b.N;
+  CUDA_OK(cudaMemcpy((void*)(c->D.sc_r + 1), sc_r, N * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy((void*)(c->D.Cs_r + 1), Cs_r, N * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy((void*)c->D.sc_w, sc_w, (N + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy((void*)c->D.Cs_w, Cs_w, (N + 1) * sizeof(double), cudaMemcpyHostToDevice));
   return 0;
 }
 int roms_b200_set_weights(roms_b200_ctx* c, int nfast, const double* w1, const double* w2) {
@@ -319,39 +325,82 @@ int roms_b200_set_stepping(roms_b200_ctx* c, const int* in, double time) {
   c->iic = in[0]; c->ntfirst = in[1]; c->nstp = in[2]; c->nnew = in[3]; c->nrhs = in[4]; c->indx1 = in[5]; c->time = time; return 0;
 }
 
+// Independent branches of a step run side by side on a second stream (on benchmark-size tiles every kernel is latency-bound
+// and leaves most of the GPU idle):
+//   start of the step : [set_massflux -> omega -> wvelocity]  beside  [rho_eos -> diag -> bulk_flux -> set_vbc -> vertical mixing]
+//                       (wvelocity waits for diag, which reads the old wvel)
+//   after set_zeta    : the TRACER branch [pre_step3d (tracers) -> t3dmix2] beside the MOMENTUM branch [pre_step3d (momentum) ->
+//                       prsgrd -> rhs3d -> uv3dmix2] AND the whole barotropic fast loop (which needs rufrc/rvfrc only); it joins
+//                       before set_depth (which overwrites Hz, z_r, z_w).
+// Read/write sets: SURVEY Appendix D; scratch volumes are private to a branch (D.dtdz vs D.kpp4).  Halo swaps stay on the launch
+// stream in a fixed order (the mailbox protocol numbers them); the swap of t(3) therefore moves from behind pre_step3d
+// (pre_step3d.F:1171) to the swap behind step3d_uv -- its first reader is step3d_t.  Every point is still advanced by the same
+// operations on the same operands: results are bit-identical to the one-stream order (ROMS_B200_ONE_STREAM=1).
+namespace {
+struct OnStream2 {                        // launches of the k_* helpers go to c->stream: redirect them for a scope
+  roms_b200_ctx* c; cudaStream_t save;
+  explicit OnStream2(roms_b200_ctx* c_) : c(c_), save(c_->stream) { c->stream = c->stream2; }
+  ~OnStream2() { c->stream = save; }
+};
+}  // namespace
 // main3d.F:216-1148 on the device mirror (post_initial is the host's job: upload a state
 // that has been through ini_zeta/ini_fields, i.e. what the reference holds when the first
 // set_massflux is called).
 int roms_b200_main3d(roms_b200_ctx* c, int nsteps, int analytic_forcing, int with_diag) {
   ENTER(c);
   const bool bench = (c->D.p.app == ROMS_B200_APP_BENCHMARK);
+  const bool two = c->two_streams != 0;
+  static const bool swap_vbc = (getenv("ROMS_B200_SWAP_VBC") != nullptr);
   for (int s = 0; s < nsteps; ++s) {
     c->nstp = 1 + ((c->iic - c->ntfirst) % 2); c->nnew = 3 - c->nstp; c->nrhs = c->nstp;
     const int nstp = c->nstp, nnew = c->nnew, nrhs = c->nrhs, iic = c->iic, ntf = c->ntfirst;
     if (analytic_forcing) k_set_data(c, c->time / 86400.0);
-    k_set_massflux(c, nrhs); k_rho_eos(c, nrhs);
+    // ---- branch A (stream2): mass fluxes, omega ; branch B (launch stream): density, diag, surface fluxes, vertical mixing
+    if (two) {
+      CUDA_OK(cudaEventRecord(c->ev[0], c->stream)); CUDA_OK(cudaStreamWaitEvent(c->stream2, c->ev[0], 0));
+      OnStream2 on(c);
+      k_set_massflux(c, nrhs); k_omega(c);
+    } else k_set_massflux(c, nrhs);
+    k_rho_eos(c, nrhs);
     if (with_diag == 1) { double d[3]; if (k_diag(c, nstp, d)) return 1; }      // main3d.F:300 (diag with NINFO=1), host waits
     else if (with_diag) { if (k_diag_begin(c, nstp)) return 1; }                 // same place, reductions + D2H stay asynchronous:
                                                                                  // the caller collects them with roms_b200_diag_end
+    if (two) {                                                                   // wvelocity (main3d.F:535) overwrites what diag read
+      CUDA_OK(cudaEventRecord(c->ev[1], c->stream)); CUDA_OK(cudaStreamWaitEvent(c->stream2, c->ev[1], 0));
+      { OnStream2 on(c); if (k_wvelocity(c, nstp)) return 1; }
+      CUDA_OK(cudaEventRecord(c->ev[2], c->stream2));
+    }
     if (bench) k_bulk_flux(c, nrhs);
     k_set_vbc(c, nrhs);
     // no halo swap of the stresses (bulk_flux, set_vbc evaluated two points into the halo) nor of Akv (KPP evaluated on the
     // first halo ring; ana_vmix on the whole mirror): ROMS_B200_SWAP_VBC=1 restores the two messages of the reference
-    static const bool swap_vbc = (getenv("ROMS_B200_SWAP_VBC") != nullptr);
     if (swap_vbc) { const XF x[4] = {xf2(FID(sustr)), xf2(FID(svstr)), xf2(FID(bustr)), xf2(FID(bvstr))}; if (xchg(c, x, 4)) return 1; }
     if (bench) { if (k_lmd_vmix(c, nstp)) return 1; if (swap_vbc) { const XF x[1] = {xf3(c, FID(Akv))}; if (xchg(c, x, 1)) return 1; } } else k_ana_vmix(c);
-    k_omega(c);
-    if (k_wvelocity(c, nstp)) return 1;                                    // main3d.F:535
+    if (two) CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev[2], 0));              // join A
+    else { k_omega(c); if (k_wvelocity(c, nstp)) return 1; }
     k_set_zeta(c);
-    k_pre_step3d(c, nrhs, nstp, nnew, iic, ntf);
-    { XF x[HALO_MAXF]; int n = 0; for (int it = 1; it <= c->D.b.NT; ++it) x[n++] = xf3(c, FID(t), 3, it); if (xchg(c, x, n)) return 1; }   // pre_step3d.F:1171
-    k_prsgrd(c, nrhs); k_t3dmix2(c, nrhs, nstp, nnew); k_rhs3d_tile(c, nrhs); k_uv3dmix2(c, nrhs, nnew);
+    // ---- tracer branch (stream2) beside the momentum branch and the fast loop (launch stream)
+    if (two) {
+      CUDA_OK(cudaEventRecord(c->ev[3], c->stream)); CUDA_OK(cudaStreamWaitEvent(c->stream2, c->ev[3], 0));
+      { OnStream2 on(c); k_pre_step3d_t(c, nrhs, nstp, nnew, iic, ntf); k_t3dmix2(c, nrhs, nstp, nnew); }
+      CUDA_OK(cudaEventRecord(c->ev[4], c->stream2));
+      k_pre_step3d_uv(c, nrhs, nstp, nnew, iic, ntf);
+      k_prsgrd(c, nrhs); k_rhs3d_tile(c, nrhs); if (k_uv3dmix2(c, nrhs, nnew)) return 1;
+    } else {
+      k_pre_step3d(c, nrhs, nstp, nnew, iic, ntf);
+      { XF x[HALO_MAXF]; int n = 0; for (int it = 1; it <= c->D.b.NT; ++it) x[n++] = xf3(c, FID(t), 3, it); if (xchg(c, x, n)) return 1; }   // pre_step3d.F:1171
+      k_prsgrd(c, nrhs); k_t3dmix2(c, nrhs, nstp, nnew); k_rhs3d_tile(c, nrhs); if (k_uv3dmix2(c, nrhs, nnew)) return 1;
+    }
     if (c->deep) { const XF x[2] = {xf2(FID(rufrc)), xf2(FID(rvfrc))}; if (xchg(c, x, 2)) return 1; }   // read by the deep-halo predictor
     if (roms_b200_step2d_loop(c, nstp, nnew, iic, ntf, &c->indx1)) return 1;
+    if (two) CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev[4], 0));              // join the tracer branch
     k_set_depth(c);
     k_step3d_uv(c, nrhs, nstp, nnew, iic, ntf);
-    { const XF x[8] = {xf3(c, FID(u), nnew), xf3(c, FID(v), nnew), xf3(c, FID(Huon)), xf3(c, FID(Hvom)),       // step3d_uv.F:1805-1824
-                       xf2(FID(ubar), 1), xf2(FID(ubar), 2), xf2(FID(vbar), 1), xf2(FID(vbar), 2)}; if (xchg(c, x, 8)) return 1; }
+    { XF x[HALO_MAXF]; int n = 0;                                                                      // step3d_uv.F:1805-1824
+      x[n++] = xf3(c, FID(u), nnew); x[n++] = xf3(c, FID(v), nnew); x[n++] = xf3(c, FID(Huon)); x[n++] = xf3(c, FID(Hvom));
+      x[n++] = xf2(FID(ubar), 1); x[n++] = xf2(FID(ubar), 2); x[n++] = xf2(FID(vbar), 1); x[n++] = xf2(FID(vbar), 2);
+      if (two) for (int it = 1; it <= c->D.b.NT && n < HALO_MAXF; ++it) x[n++] = xf3(c, FID(t), 3, it);   // + t(3) (pre_step3d.F:1171)
+      if (xchg(c, x, n)) return 1; }
     k_omega(c);
     k_step3d_t(c, nrhs, nstp, nnew);
     { XF x[HALO_MAXF]; int n = 0; for (int it = 1; it <= c->D.b.NT; ++it) x[n++] = xf3(c, FID(t), nnew, it); if (xchg(c, x, n)) return 1; }   // step3d_t.F:1920

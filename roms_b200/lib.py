@@ -157,7 +157,12 @@ class Context:
         return out
 
     def set_scoord(self, sc_r, Cs_r, sc_w, Cs_w):
+        """sc_r, Cs_r: N values (levels 1:N) -- vectors indexed by level with an unused element 0 are accepted too; sc_w, Cs_w:
+        N+1 values (levels 0:N), as SCALARS(ng) holds them (mod_scalars.F:1950-1968)."""
+        N = self.bounds.N
+        sc_r, Cs_r = (np.asarray(a, dtype=np.float64)[-N:] for a in (sc_r, Cs_r))
         arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (sc_r, Cs_r, sc_w, Cs_w)]
+        assert arrs[0].size == N and arrs[1].size == N and arrs[2].size == N + 1 and arrs[3].size == N + 1
         self._chk(self.L.roms_b200_set_scoord(self.h, *[a.ctypes.data for a in arrs]), "set_scoord")
 
     def set_weights(self, nfast, w1, w2):

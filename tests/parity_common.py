@@ -32,6 +32,20 @@ FORCING_FIELDS = ["srflx", "sustr", "svstr", "stflux", "btflux", "cloud", "Tair"
 PROGNOSTIC = ["zeta", "ubar", "vbar", "u", "v", "t"]
 
 
+def prognostic_errors(get_ref, get_got):
+    """Max-norm differences of the prognostic fields, relative.  Scalars (zeta, t) are scaled by the field's own range; the two
+    components of a velocity vector ((ubar, vbar), (u, v)) by the larger of the two ranges -- a zonal flow has a meridional
+    component whose own range is orders of magnitude smaller than the velocity scale the error lives on.  Returns
+    ({field: error / scale}, {field: error / own range})."""
+    ref = {n: get_ref(n) for n in PROGNOSTIC}
+    rng = {n: float(ref[n].max() - ref[n].min()) for n in PROGNOSTIC}
+    scale = dict(rng)
+    for a, b in (("ubar", "vbar"), ("u", "v")):
+        scale[a] = scale[b] = max(rng[a], rng[b])
+    err = {n: float(np.max(np.abs(ref[n] - get_got(n)))) for n in PROGNOSTIC}
+    return ({n: err[n] / max(scale[n], 1e-300) for n in PROGNOSTIC}, {n: err[n] / max(rng[n], 1e-300) for n in PROGNOSTIC})
+
+
 def make_params(o):
     d, sc, c = o.dims(), o.scalars(), None
     p = rb.Params()

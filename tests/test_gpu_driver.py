@@ -90,6 +90,33 @@ def test_output_snapshot_does_not_disturb_the_time_loop():
     d.finalize(); d2.finalize()
 
 
+def test_two_stream_step_is_bit_identical_to_the_serial_order():
+    """roms_b200_main3d runs independent branches of a step on a second stream (tracer branch beside the momentum branch and the
+    fast loop; mass fluxes / omega beside density / surface fluxes / KPP).  A missing dependency would show up as a difference
+    from the serial launch order (ROMS_B200_ONE_STREAM=1, read once per process -> child process), also on a grid large enough
+    for kernels of both streams to be resident together."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    code = ("import sys, numpy as np; sys.path.insert(0, %r)\n"
+            "import roms_b200 as rb\n"
+            "for app, g in ((rb.APP_BENCHMARK, (512, 64, 30)), (rb.APP_UPWELLING, (0, 0, 0))):\n"
+            "    d = rb.Driver(rb.default_config(app, *g))\n"
+            "    d.run(12); d.run(3, host_forcing=True); d.ctx.sync()\n"
+            "    np.savez(sys.argv[1] + '_%%d.npz' %% app, **{n: d.ctx.download(n) for n in ('zeta', 'ubar', 'vbar', 'u', 'v', 't', 'W', 'Akv', 'wvel')})\n"
+            "    d.finalize()\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as tmp:
+        for tag, env in (("two", {}), ("one", {"ROMS_B200_ONE_STREAM": "1"})):
+            r = subprocess.run([sys.executable, "-c", code, os.path.join(tmp, tag)], capture_output=True, text=True, timeout=600,
+                               env=dict(os.environ, **env))
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+        for app in (rb.APP_BENCHMARK, rb.APP_UPWELLING):
+            a, b = np.load(os.path.join(tmp, "two_%d.npz" % app)), np.load(os.path.join(tmp, "one_%d.npz" % app))
+            bad = [n for n in a.files if not np.array_equal(a[n], b[n])]
+            assert not bad, (app, bad)
+
+
 def test_negative_control_detects_missing_kernel():
     """If a kernel is NOT run the comparison must fail: guards against a vacuous harness."""
     o, ctx = make_pair(ol.UPWELLING)
