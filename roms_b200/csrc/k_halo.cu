@@ -12,13 +12,10 @@
 // is captured in the fast-loop CUDA graph together with the step2d launches.
 // NCCL is dlopen'ed: single-GPU use never needs it.
 //
-// Second transport (default when the host connected the peers, roms_b200_p2p_*): NVLink peer MAILBOXES.  Every rank
-// exports one device allocation through CUDA IPC; a neighbour maps it and one exchange kernel per phase stores the
-// boundary strips straight into the receivers' mailboxes over NVLink (no staging, no NCCL proxy/launch), raises the
-// "strip complete" flags there, spins on its own flags and unpacks.  One kernel per phase instead of pack + ncclGroup +
-// unpack: the latency-bound 2-D swaps of the barotropic loop cost about one kernel launch plus one NVLink round trip.  Sequence numbers live on the device, so the
-// exchange is replayable inside the fast-loop CUDA graph; mailboxes are double-buffered by sequence parity (a sender can
-// only be two exchanges ahead after it has seen the receiver's flag of the previous one).
+// DEFAULT transport (when the host connected the peers, roms_b200_p2p_*): NVLink peer MAILBOXES.  Every rank exports one
+// device allocation through CUDA IPC; a neighbour maps it and ONE exchange kernel stores the boundary strips of all eight
+// neighbours straight into the receivers' mailboxes over NVLink as flag-in-data messages (see below) and unpacks what
+// arrives: no staging, no NCCL proxy, no fences.  The NCCL path above remains as ROMS_B200_HALO_NCCL=1 and for diag's all-reduce.
 #include "common.cuh"
 #include <dlfcn.h>
 #include <cstring>
@@ -101,34 +98,51 @@ __global__ void halo_unpack_kernel(const Dev D, HaloList L, int phase, int w, co
 }
 
 // ---- NVLink peer mailboxes ----------------------------------------------------------------------------------
-// exported allocation: [16 flags (dir*2+slot) as u64, padded to 256 B][16 data regions (dir*2+slot) of `cap` doubles]
+// exported allocation: [256-byte header][16 data regions (dir*2+slot) of `cap` elements of 16 bytes]
 // dir = the side the strip ARRIVES from: 0 W, 1 E, 2 S, 3 N, 4 SW, 5 SE, 6 NW, 7 NE.
 // Unlike the two-phase scheme of mp_exchange (W/E, then S/N over the full i-range so that corners propagate), all eight
 // neighbours are served in ONE exchange: the corner blocks travel as their own (w x w) messages.  W/E strips span the rows
 // [Jstr..Jend], extended to the array edge where the tile has no S/N neighbour (physical boundary rows); S/N strips
 // likewise in i -- so after the exchange the halo frame holds exactly what the two phases would have produced.
+//
+// Flag-in-data messages (the idea of NCCL's LL protocol): a double travels as two 8-byte words {low half | seq << 32},
+// {high half | seq << 32}, written with one 16-byte store straight into the receiver's mailbox over NVLink.  An 8-byte word
+// arrives atomically, so the receiver simply polls every element until both halves carry this exchange's sequence number:
+// no system fence, no flag round trip, no block that has to see all others finish, and no requirement that the blocks of the
+// kernel are co-resident (round 1: data + __threadfence_system + ticket + flags + spin).  Mailboxes are double-buffered by
+// sequence parity: a sender reaches exchange s+2 only after it has received its neighbour's data of s+1, which the neighbour
+// sent after it had unpacked s (stream order).  A poll that lasts ~2 s (a dead peer) raises bit 1 of the device error word
+// instead of hanging the node (the reference sets exit_flag=2, mp_exchange.F:544-553): roms_b200_sync reports it.
 constexpr size_t P2P_HDR = 256;
 constexpr int P2P_NDIR = 8;
 __host__ __device__ inline int p2p_opp(int d) { return d < 4 ? (d ^ 1) : (11 - d); }     // W<->E, S<->N, SW<->NE, SE<->NW
-struct P2PView { unsigned long long* flags; double* data; size_t cap; };
-__host__ __device__ inline P2PView p2p_view(void* mem, size_t cap) {
-  return P2PView{(unsigned long long*)mem, (double*)((char*)mem + P2P_HDR), cap};
-}
+struct P2PView { ulonglong2* data; size_t cap; };
+__host__ __device__ inline P2PView p2p_view(void* mem, size_t cap) { return P2PView{(ulonglong2*)((char*)mem + P2P_HDR), cap}; }
 struct Rect { int o, w, h; };              // element offset of the first point in an (i,j) plane, width (i), height (j)
 struct P2PArgs {
   void* mine; void* peer[P2P_NDIR];        // my mailbox ; the mailboxes of the 8 neighbours (null: none)
   Rect snd[P2P_NDIR], rcv[P2P_NDIR];       // what I send towards direction d / where the strip arriving from direction d goes
   size_t cap; unsigned long long* seq; unsigned int* ticket;
 };
-// ONE kernel per exchange: (1) store my boundary strips and corner blocks into the neighbours' mailboxes over NVLink,
-// (2) the last block to finish packing raises the "complete" flags at the neighbours, (3) every block waits for the flag
-// of the direction it unpacks, (4) unpack into my halo, (5) the last block commits the sequence number.  All blocks are
-// co-resident (a few hundred blocks of 256 threads at most), so the spin in (3) cannot starve blocks still packing.
-// Work items = (plane, direction); the grid is at most 4 blocks per SM so that every block is resident.
+__device__ __forceinline__ void ll_store(ulonglong2* p, double v, unsigned s) {
+  const unsigned long long f = (unsigned long long)s << 32;
+  const unsigned long long w0 = f | (unsigned)__double2loint(v), w1 = f | (unsigned)__double2hiint(v);
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ bool ll_load(const ulonglong2* p, unsigned s, double& v) {
+  unsigned long long w0, w1;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+  v = __hiloint2double((int)(unsigned)w1, (int)(unsigned)w0);
+  return (unsigned)(w0 >> 32) == s && (unsigned)(w1 >> 32) == s;
+}
+// ONE kernel per exchange; work items = (plane, direction).  (1) every block pushes the strips of its items into the
+// neighbours' mailboxes, (2) then polls and unpacks the strips that arrive for its items, (3) the last block to finish
+// commits the sequence number (device-side, so the kernel is replayable inside the fast-loop CUDA graph).
 __global__ void __launch_bounds__(256) halo_xchg_p2p_kernel(const Dev D, HaloList L, const __grid_constant__ P2PArgs a) {
   const int ni = D.ni;
-  const unsigned long long s = a.seq[0] + 1;          // this exchange's sequence number
-  const int slot = (int)(s & 1);
+  const unsigned long long s64 = a.seq[0] + 1;        // this exchange's sequence number
+  const unsigned s = (unsigned)s64;
+  const int slot = (int)(s & 1u);
   const P2PView me = p2p_view(a.mine, a.cap);
   const int nitems = L.total_planes * P2P_NDIR;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -140,26 +154,10 @@ __global__ void __launch_bounds__(256) halo_xchg_p2p_kernel(const Dev D, HaloLis
     const double* fld = L.base[f] + (size_t)p * D.nij;
     const Rect r = a.snd[d];
     const int n = r.w * r.h;
-    double* out = p2p_view(peer, a.cap).data + (size_t)(p2p_opp(d) * 2 + slot) * a.cap + (size_t)plane * n;
-    for (int x = threadIdx.x; x < n; x += blockDim.x) out[x] = fld[r.o + (x % r.w) + (size_t)ni * (x / r.w)];
+    ulonglong2* out = p2p_view(peer, a.cap).data + (size_t)(p2p_opp(d) * 2 + slot) * a.cap + (size_t)plane * n;
+    for (int x = threadIdx.x; x < n; x += blockDim.x) ll_store(out + x, fld[r.o + (x % r.w) + (size_t)ni * (x / r.w)], s);
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) {                            // all blocks have packed and fenced
-      a.ticket[0] = 0;
-#pragma unroll
-      for (int q = 0; q < P2P_NDIR; ++q)
-        if (a.peer[q]) { volatile unsigned long long* fl = p2p_view(a.peer[q], a.cap).flags + (p2p_opp(q) * 2 + slot); *fl = s; }
-      __threadfence_system();
-    }
-  }
-  if (threadIdx.x < P2P_NDIR && a.peer[threadIdx.x]) {
-    volatile unsigned long long* fl = me.flags + (threadIdx.x * 2 + slot);
-    while (*fl < s) { }
-    __threadfence_system();
-  }
-  __syncthreads();
+  bool dead = false;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int d = item % P2P_NDIR, plane = item / P2P_NDIR;
     if (!a.peer[d]) continue;
@@ -168,13 +166,24 @@ __global__ void __launch_bounds__(256) halo_xchg_p2p_kernel(const Dev D, HaloLis
     double* fld = L.base[f] + (size_t)p * D.nij;
     const Rect r = a.rcv[d];
     const int n = r.w * r.h;
-    const double* in = me.data + (size_t)(d * 2 + slot) * a.cap + (size_t)plane * n;
-    for (int x = threadIdx.x; x < n; x += blockDim.x) fld[r.o + (x % r.w) + (size_t)ni * (x / r.w)] = __ldcv(in + x);
+    const ulonglong2* in = me.data + (size_t)(d * 2 + slot) * a.cap + (size_t)plane * n;
+    for (int x = threadIdx.x; x < n; x += blockDim.x) {
+      double v; unsigned spins = 0; long long t0 = 0;
+      while (!ll_load(in + x, s, v)) {
+        if (dead) break;
+        if ((++spins & 0xfffu) == 0) {                                        // every 4096 polls: has this taken ~2 s?
+          const long long t = clock64();
+          if (!t0) t0 = t; else if (t - t0 > 4000000000ll) { dead = true; break; }
+        }
+      }
+      fld[r.o + (x % r.w) + (size_t)ni * (x / r.w)] = v;
+    }
   }
+  if (dead) atomicOr(D.err, 2);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    if (atomicAdd(a.ticket + 1, 1u) == gridDim.x - 1) { a.ticket[1] = 0; __threadfence(); a.seq[0] = s; }
+    if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) { a.ticket[0] = 0; __threadfence(); a.seq[0] = s64; }
   }
 }
 }  // namespace
@@ -188,7 +197,7 @@ int roms_b200_p2p_handle(roms_b200_ctx* c, char* handle64) {
   CUDA_OK(cudaSetDevice(c->device));
   const size_t strip = (size_t)c->D.halo * (size_t)((c->D.ni > c->D.nj) ? c->D.ni : c->D.nj);
   c->halo_cap = strip * HALO_MAXPLANES;
-  const size_t bytes = P2P_HDR + 2 * P2P_NDIR * c->halo_cap * sizeof(double);
+  const size_t bytes = P2P_HDR + 2 * P2P_NDIR * c->halo_cap * sizeof(ulonglong2);
   if (!c->p2p_mem) {
     CUDA_OK(cudaMalloc(&c->p2p_mem, bytes));
     CUDA_OK(cudaMemset(c->p2p_mem, 0, bytes));
@@ -293,9 +302,9 @@ int halo_exchange(roms_b200_ctx* c, double* const* bases, const int* nplanes, in
     }
     static int nsm = 0;
     if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
-    // one block per (plane, direction) item while they all fit on the GPU at once (a single block for the small 2-D swaps was
-    // measured much slower: the strip copies are latency-bound and want to run side by side)
-    int nblk = L.total_planes * P2P_NDIR; if (nblk > 4 * nsm) nblk = 4 * nsm;
+    // one block per (plane, direction) item, at most 8 per SM (a single block for the small 2-D swaps was measured much
+    // slower: the strip copies are latency-bound and want to run side by side)
+    int nblk = L.total_planes * P2P_NDIR; if (nblk > 8 * nsm) nblk = 8 * nsm;
     halo_xchg_p2p_kernel<<<nblk, 256, 0, c->stream>>>(c->D, L, a); c->launches++;
     return 0;
   }

@@ -175,9 +175,17 @@ int roms_b200_download_interior(roms_b200_ctx* c, int f, int plane0, int nplanes
 void* roms_b200_device_ptr(roms_b200_ctx* c, int f) { return (f < 0 || f >= ROMS_B200_NFIELDS) ? nullptr : (void*)c->D.f[f]; }
 int roms_b200_sync(roms_b200_ctx* c) {
   CUDA_OK(cudaStreamSynchronize(c->stream)); CUDA_OK(cudaGetLastError());
-  int err = 0;                                   // device-side "fatal algorithm result" word -> exit_flag=8 (mod_scalars.F:548-561)
+  int err = 0;                                   // device-side error word
   CUDA_OK(cudaMemcpy(&err, c->D.err, sizeof(int), cudaMemcpyDeviceToHost));
-  if (err) { fprintf(stderr, "roms_b200: device error word 0x%x (non-finite or out-of-range reciprocal operand: blown-up state)\n", err); return 8; }
+  if (err & 2) {                                 // a halo message never arrived: exit_flag=2 as mp_exchange.F:544-553
+    fprintf(stderr, "roms_b200: device error word 0x%x: a halo message from a neighbour tile did not arrive within ~2 s\n", err);
+    return 2;
+  }
+  if (err) {                                     // "fatal algorithm result" -> exit_flag=8 (mod_scalars.F:548-561)
+    fprintf(stderr, "roms_b200: device error word 0x%x (bit 0: non-finite or out-of-range reciprocal operand, a blown-up state; bit 2: "
+                    "a pipeline barrier of step3d_t timed out)\n", err);
+    return 8;
+  }
   return 0;
 }
 long roms_b200_launch_count(const roms_b200_ctx* c) { return c->launches; }
