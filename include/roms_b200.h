@@ -206,6 +206,69 @@ int roms_b200_p2p_connect(roms_b200_ctx* ctx, const char* handles, int nranks);
  * storage plane `plane0`, into a dense host buffer (nplanes, Jend-Jstr+1, Iend-Istr+1) */
 int roms_b200_download_interior(roms_b200_ctx* ctx, int field, int plane0, int nplanes, double* host);
 
+
+/* ---- the boundary as a Fortran MPI host sees it (roms_b200/csrc/tile_api.cu).
+ * Host arrays keep THEIR bounds: (LBi:UBi,LBj:UBj) of Utility/get_bounds.F:193-212 with NghostPoints = 2, while a distributed
+ * mirror carries a halo of 6.  upload/download_bounds move the intersection of the two index boxes, all planes of the field;
+ * exchange_field then refreshes the mirror's wider halo from the neighbour tiles.  register_field remembers c_loc(array) and its
+ * bounds: the *_registered calls and the argument checks of the *_tile entry points below use it. */
+int roms_b200_register_field(roms_b200_ctx* ctx, int field, const double* host, int LBi, int UBi, int LBj, int UBj);
+int roms_b200_upload_bounds(roms_b200_ctx* ctx, int field, const double* host, int LBi, int UBi, int LBj, int UBj);
+int roms_b200_download_bounds(roms_b200_ctx* ctx, int field, double* host, int LBi, int UBi, int LBj, int UBj);
+int roms_b200_upload_registered(roms_b200_ctx* ctx, int field);
+int roms_b200_download_registered(roms_b200_ctx* ctx, int field);
+int roms_b200_exchange_field(roms_b200_ctx* ctx, int field);
+/* array bounds {LBi,UBi,LBj,UBj} of a tile array in an MPI build of the reference (get_bounds.F:129-212, r2dvar) */
+int roms_b200_mpi_array_bounds(int Lm, int Mm, int NtileI, int NtileJ, int tile, int EWperiodic, int NSperiodic, int Nghost, int* lbub4);
+/* iif(ng), PREDICTOR_2D_STEP(ng) (mod_scalars, set by main3d.F:820-880) for the next step2d_tile; the rufrc/rvfrc swap the
+ * deep-halo predictor needs before the first sub-step of a baroclinic step (no-op on one tile) */
+int roms_b200_set_fast_step(roms_b200_ctx* ctx, int iif, int predictor_2d_step);
+int roms_b200_fast_loop_begin(roms_b200_ctx* ctx);
+
+/* ---- `_tile` entry points: the argument lists of the reference's X_tile routines for the UPWELLING / BENCHMARK cpp sets, so that
+ * the wrapper X(ng,tile) changes one token (CALL X_tile -> rc = roms_b200_ X _tile with ctx as first argument).  Array arguments are the HOST
+ * arrays; each is checked against its registration (address and bounds), then the call runs on the mirror and performs the halo
+ * swaps the reference routine ends with.  Arguments that exist only under cpp options one application lacks may be null:
+ * dndx, dmde (CURVGRID), rhoA, rhoS (VAR_RHO_2D), srflx (SOLAR_SOURCE), ghats (LMD_NONLOCAL).  iic, ntfirst: roms_b200_set_stepping. */
+int roms_b200_set_massflux_tile(roms_b200_ctx* ctx, int ng, int tile, int model, int LBi, int UBi, int LBj, int UBj, int IminS, int ImaxS, int JminS, int JmaxS,
+                                int nrhs, const double* u, const double* v, const double* Hz, const double* om_v, const double* on_u,
+                                double* Huon, double* Hvom);                                             /* set_massflux.F:73-82 */
+int roms_b200_omega_tile(roms_b200_ctx* ctx, int ng, int tile, int model, int LBi, int UBi, int LBj, int UBj, int IminS, int ImaxS, int JminS, int JmaxS,
+                         const double* Huon, const double* Hvom, const double* z_w, double* W);          /* omega.F:96-114 */
+int roms_b200_set_zeta_tile(roms_b200_ctx* ctx, int ng, int tile, int LBi, int UBi, int LBj, int UBj, int IminS, int ImaxS, int JminS, int JmaxS,
+                            const double* Zt_avg1, double* zeta);                                        /* set_zeta.F:59-62 */
+int roms_b200_set_depth_tile(roms_b200_ctx* ctx, int ng, int tile, int model, int LBi, int UBi, int LBj, int UBj, int IminS, int ImaxS, int JminS, int JmaxS,
+                             int nstp, int nnew, const double* h, const double* Zt_avg1, double* Hz, double* z_r, double* z_w);   /* set_depth.F:76-85 */
+int roms_b200_pre_step3d_tile(roms_b200_ctx* ctx, int ng, int tile, int LBi, int UBi, int LBj, int UBj, int IminS, int ImaxS, int JminS, int JmaxS,
+                              int nrhs, int nstp, int nnew, const double* pm, const double* pn, const double* Hz, const double* Huon, const double* Hvom,
+                              const double* z_r, const double* z_w, const double* btflx, const double* bustr, const double* bvstr, const double* stflx,
+                              const double* sustr, const double* svstr, const double* srflx, const double* Akt, const double* Akv, const double* ghats,
+                              const double* W, const double* ru, const double* rv, double* t, double* u, double* v);   /* pre_step3d.F:126-160 */
+int roms_b200_prsgrd32_tile(roms_b200_ctx* ctx, int ng, int tile, int LBi, int UBi, int LBj, int UBj, int IminS, int ImaxS, int JminS, int JmaxS,
+                            int nrhs, const double* om_v, const double* on_u, const double* Hz, const double* z_r, const double* z_w, const double* rho,
+                            double* ru, double* rv);                                                     /* prsgrd32.h:109-134 */
+int roms_b200_rhs3d_tile_tile(roms_b200_ctx* ctx, int ng, int tile, int LBi, int UBi, int LBj, int UBj, int IminS, int ImaxS, int JminS, int JmaxS,
+                              int nrhs, const double* Hz, const double* Huon, const double* Hvom, const double* dmde, const double* dndx, const double* fomn,
+                              const double* om_u, const double* om_v, const double* on_u, const double* on_v, const double* pm, const double* pn,
+                              const double* bustr, const double* bvstr, const double* sustr, const double* svstr, const double* u, const double* v,
+                              const double* W, double* rufrc, double* rvfrc, double* ru, double* rv);    /* rhs3d.F:196-221 */
+int roms_b200_step2d_tile(roms_b200_ctx* ctx, int ng, int tile, int LBi, int UBi, int LBj, int UBj, int UBk, int IminS, int ImaxS, int JminS, int JmaxS,
+                          int krhs, int kstp, int knew, int nstp, int nnew, const double* fomn, const double* h, const double* om_u, const double* om_v,
+                          const double* on_u, const double* on_v, const double* omn, const double* pm, const double* pn, const double* dndx, const double* dmde,
+                          const double* pmon_r, const double* pnom_r, const double* pmon_p, const double* pnom_p, const double* om_r, const double* on_r,
+                          const double* om_p, const double* on_p, const double* visc2_p, const double* visc2_r, const double* rhoA, const double* rhoS,
+                          double* DU_avg1, double* DU_avg2, double* DV_avg1, double* DV_avg2, double* Zt_avg1, double* rufrc, double* rvfrc, double* ru, double* rv,
+                          double* rubar, double* rvbar, double* rzeta, double* ubar, double* vbar, double* zeta);     /* step2d_LF_AM3.h:163-246 */
+int roms_b200_step3d_uv_tile(roms_b200_ctx* ctx, int ng, int tile, int LBi, int UBi, int LBj, int UBj, int IminS, int ImaxS, int JminS, int JmaxS,
+                             int nrhs, int nstp, int nnew, const double* om_v, const double* on_u, const double* pm, const double* pn, const double* Hz,
+                             const double* z_r, const double* z_w, const double* Akv, const double* DU_avg1, const double* DV_avg1, const double* DU_avg2,
+                             const double* DV_avg2, double* ru, double* rv, double* u, double* v, double* ubar, double* vbar, double* Huon, double* Hvom);
+                                                                                                         /* step3d_uv.F:134-172 */
+int roms_b200_step3d_t_tile(roms_b200_ctx* ctx, int ng, int tile, int LBi, int UBi, int LBj, int UBj, int IminS, int ImaxS, int JminS, int JmaxS,
+                            int nrhs, int nstp, int nnew, const double* omn, const double* om_u, const double* om_v, const double* on_u, const double* on_v,
+                            const double* pm, const double* pn, const double* Hz, const double* Huon, const double* Hvom, const double* z_r, const double* Akt,
+                            const double* W, double* t);                                                 /* step3d_t.F:120-151 */
+
 /* ---- output path without stalling the time loop (what `output` needs before wrt_his / wrt_rst / wrt_avg, output.F:217,703).
  * roms_b200_snapshot_begin copies the listed fields device-to-device into a staging area ON THE LAUNCH STREAM (it orders after
  * every kernel launched so far and costs microseconds), then device-to-host into the caller's PINNED buffers

@@ -244,20 +244,6 @@ int roms_b200_fill(roms_b200_ctx* c, int f, double value) {
   LEAVE();
 }
 
-// halo exchange of named fields / planes (no-op on a single tile)
-struct XF { int fid; int plane0; int nplanes; };      // plane0: first (i,j) plane of the field's storage
-static int xchg(roms_b200_ctx* c, const XF* x, int n) {
-  if (!c->comm) return 0;
-  double* bases[HALO_MAXF]; int np[HALO_MAXF];
-  for (int q = 0; q < n; ++q) { bases[q] = c->D.f[x[q].fid] + (size_t)x[q].plane0 * c->D.nij; np[q] = x[q].nplanes; }
-  return halo_exchange(c, bases, np, n);
-}
-static inline XF xf3(const roms_b200_ctx* c, int fid, int l = 1, int m = 1) {      // volume (l,m) of a 3-D field
-  const int nk = c->D.nk[fid];
-  return XF{fid, nk * ((l - 1) + c->D.nl[fid] * (m - 1)), nk};
-}
-static inline XF xf2(int fid, int l = 1) { return XF{fid, l - 1, 1}; }
-
 // main3d.F:810-918: LF-AM3 fast loop.  The launch sequence depends only on
 // (indx1 at entry, which of the three AB start-up forms the first predictor
 // uses), so it is captured once per key and replayed as a CUDA graph.

@@ -395,6 +395,226 @@
           type(c_ptr), value :: ctx
           real(c_double) :: out3(3)
         END FUNCTION
+!
+!  The boundary as an MPI host sees it (roms_b200/csrc/tile_api.cu): host arrays keep their own bounds (LBi:UBi,LBj:UBj) with
+!  NghostPoints = 2; register them once, then upload/download by field id.  The *_tile entry points take the argument lists of the
+!  reference's X_tile routines (UPWELLING / BENCHMARK cpp sets), check every array against its registration, run on the mirror and
+!  do the halo swaps the reference routine ends with.  Generated by tools/gen_fortran_iface.py from include/roms_b200.h.
+!
+        integer(c_int) FUNCTION roms_b200_register_field (ctx,        &
+     &    field, host, LBi, UBi, LBj, UBj)                            &
+     &                          BIND(C, name='roms_b200_register_field')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: field, LBi, UBi, LBj, UBj
+          real(c_double), intent(in) :: host(*)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_upload_bounds (ctx,         &
+     &    field, host, LBi, UBi, LBj, UBj)                            &
+     &                          BIND(C, name='roms_b200_upload_bounds')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: field, LBi, UBi, LBj, UBj
+          real(c_double), intent(in) :: host(*)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_download_bounds (ctx,       &
+     &    field, host, LBi, UBi, LBj, UBj)                            &
+     &                          BIND(C, name='roms_b200_download_bounds')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: field, LBi, UBi, LBj, UBj
+          real(c_double), intent(inout) :: host(*)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_upload_registered (ctx,     &
+     &    field)                                                      &
+     &                          BIND(C, name='roms_b200_upload_registered')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: field
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_download_registered (       &
+     &    ctx, field)                                                 &
+     &                          BIND(C, name='roms_b200_download_registered')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: field
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_exchange_field (ctx,        &
+     &    field)                                                      &
+     &                          BIND(C, name='roms_b200_exchange_field')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: field
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_mpi_array_bounds (Lm,       &
+     &    Mm, NtileI, NtileJ, tile, EWperiodic, NSperiodic,           &
+     &    Nghost, lbub4)                                              &
+     &                          BIND(C, name='roms_b200_mpi_array_bounds')
+          IMPORT
+          integer(c_int), value :: Lm, Mm, NtileI, NtileJ, tile,      &
+     &      EWperiodic, NSperiodic, Nghost
+          integer(c_int) :: lbub4(*)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_set_fast_step (ctx,         &
+     &    iif, predictor_2d_step)                                     &
+     &                          BIND(C, name='roms_b200_set_fast_step')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: iif, predictor_2d_step
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_fast_loop_begin (ctx)       &
+     &                          BIND(C, name='roms_b200_fast_loop_begin')
+          IMPORT
+          type(c_ptr), value :: ctx
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_set_massflux_tile (ctx,     &
+     &    ng, tile, model, LBi, UBi, LBj, UBj, IminS, ImaxS,          &
+     &    JminS, JmaxS, nrhs, u, v, Hz, om_v, on_u, Huon, Hvom)       &
+     &                          BIND(C, name='roms_b200_set_massflux_tile')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: ng, tile, model, LBi, UBi,         &
+     &      LBj, UBj, IminS, ImaxS, JminS, JmaxS, nrhs
+          real(c_double), intent(in) :: u(*), v(*), Hz(*),            &
+     &      om_v(*), on_u(*)
+          real(c_double), intent(inout) :: Huon(*), Hvom(*)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_omega_tile (ctx, ng,        &
+     &    tile, model, LBi, UBi, LBj, UBj, IminS, ImaxS, JminS,       &
+     &    JmaxS, Huon, Hvom, z_w, W)                                  &
+     &                          BIND(C, name='roms_b200_omega_tile')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: ng, tile, model, LBi, UBi,         &
+     &      LBj, UBj, IminS, ImaxS, JminS, JmaxS
+          real(c_double), intent(in) :: Huon(*), Hvom(*), z_w(*)
+          real(c_double), intent(inout) :: W(*)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_set_zeta_tile (ctx, ng,     &
+     &    tile, LBi, UBi, LBj, UBj, IminS, ImaxS, JminS, JmaxS,       &
+     &    Zt_avg1, zeta)                                              &
+     &                          BIND(C, name='roms_b200_set_zeta_tile')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: ng, tile, LBi, UBi, LBj, UBj,      &
+     &      IminS, ImaxS, JminS, JmaxS
+          real(c_double), intent(in) :: Zt_avg1(*)
+          real(c_double), intent(inout) :: zeta(*)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_set_depth_tile (ctx,        &
+     &    ng, tile, model, LBi, UBi, LBj, UBj, IminS, ImaxS,          &
+     &    JminS, JmaxS, nstp, nnew, h, Zt_avg1, Hz, z_r, z_w)         &
+     &                          BIND(C, name='roms_b200_set_depth_tile')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: ng, tile, model, LBi, UBi,         &
+     &      LBj, UBj, IminS, ImaxS, JminS, JmaxS, nstp, nnew
+          real(c_double), intent(in) :: h(*), Zt_avg1(*)
+          real(c_double), intent(inout) :: Hz(*), z_r(*), z_w(*)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_pre_step3d_tile (ctx,       &
+     &    ng, tile, LBi, UBi, LBj, UBj, IminS, ImaxS, JminS,          &
+     &    JmaxS, nrhs, nstp, nnew, pm, pn, Hz, Huon, Hvom, z_r,       &
+     &    z_w, btflx, bustr, bvstr, stflx, sustr, svstr, srflx,       &
+     &    Akt, Akv, ghats, W, ru, rv, t, u, v)                        &
+     &                          BIND(C, name='roms_b200_pre_step3d_tile')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: ng, tile, LBi, UBi, LBj, UBj,      &
+     &      IminS, ImaxS, JminS, JmaxS, nrhs, nstp, nnew
+          real(c_double), intent(in) :: pm(*), pn(*), Hz(*),          &
+     &      Huon(*), Hvom(*), z_r(*), z_w(*), btflx(*), bustr(*),     &
+     &      bvstr(*), stflx(*), sustr(*), svstr(*), Akt(*),           &
+     &      Akv(*), W(*), ru(*), rv(*)
+          real(c_double), intent(in), optional :: srflx(*),           &
+     &      ghats(*)
+          real(c_double), intent(inout) :: t(*), u(*), v(*)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_prsgrd32_tile (ctx, ng,     &
+     &    tile, LBi, UBi, LBj, UBj, IminS, ImaxS, JminS, JmaxS,       &
+     &    nrhs, om_v, on_u, Hz, z_r, z_w, rho, ru, rv)                &
+     &                          BIND(C, name='roms_b200_prsgrd32_tile')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: ng, tile, LBi, UBi, LBj, UBj,      &
+     &      IminS, ImaxS, JminS, JmaxS, nrhs
+          real(c_double), intent(in) :: om_v(*), on_u(*), Hz(*),      &
+     &      z_r(*), z_w(*), rho(*)
+          real(c_double), intent(inout) :: ru(*), rv(*)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_rhs3d_tile_tile (ctx,       &
+     &    ng, tile, LBi, UBi, LBj, UBj, IminS, ImaxS, JminS,          &
+     &    JmaxS, nrhs, Hz, Huon, Hvom, dmde, dndx, fomn, om_u,        &
+     &    om_v, on_u, on_v, pm, pn, bustr, bvstr, sustr, svstr,       &
+     &    u, v, W, rufrc, rvfrc, ru, rv)                              &
+     &                          BIND(C, name='roms_b200_rhs3d_tile_tile')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: ng, tile, LBi, UBi, LBj, UBj,      &
+     &      IminS, ImaxS, JminS, JmaxS, nrhs
+          real(c_double), intent(in) :: Hz(*), Huon(*), Hvom(*),      &
+     &      fomn(*), om_u(*), om_v(*), on_u(*), on_v(*), pm(*),       &
+     &      pn(*), bustr(*), bvstr(*), sustr(*), svstr(*), u(*),      &
+     &      v(*), W(*)
+          real(c_double), intent(in), optional :: dmde(*), dndx(*)
+          real(c_double), intent(inout) :: rufrc(*), rvfrc(*),        &
+     &      ru(*), rv(*)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_step2d_tile (ctx, ng,       &
+     &    tile, LBi, UBi, LBj, UBj, UBk, IminS, ImaxS, JminS,         &
+     &    JmaxS, krhs, kstp, knew, nstp, nnew, fomn, h, om_u,         &
+     &    om_v, on_u, on_v, omn, pm, pn, dndx, dmde, pmon_r,          &
+     &    pnom_r, pmon_p, pnom_p, om_r, on_r, om_p, on_p,             &
+     &    visc2_p, visc2_r, rhoA, rhoS, DU_avg1, DU_avg2,             &
+     &    DV_avg1, DV_avg2, Zt_avg1, rufrc, rvfrc, ru, rv, rubar,     &
+     &    rvbar, rzeta, ubar, vbar, zeta)                             &
+     &                          BIND(C, name='roms_b200_step2d_tile')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: ng, tile, LBi, UBi, LBj, UBj,      &
+     &      UBk, IminS, ImaxS, JminS, JmaxS, krhs, kstp, knew,        &
+     &      nstp, nnew
+          real(c_double), intent(in) :: fomn(*), h(*), om_u(*),       &
+     &      om_v(*), on_u(*), on_v(*), omn(*), pm(*), pn(*),          &
+     &      pmon_r(*), pnom_r(*), pmon_p(*), pnom_p(*), om_r(*),      &
+     &      on_r(*), om_p(*), on_p(*), visc2_p(*), visc2_r(*)
+          real(c_double), intent(in), optional :: dndx(*),            &
+     &      dmde(*), rhoA(*), rhoS(*)
+          real(c_double), intent(inout) :: DU_avg1(*),                &
+     &      DU_avg2(*), DV_avg1(*), DV_avg2(*), Zt_avg1(*),           &
+     &      rufrc(*), rvfrc(*), ru(*), rv(*), rubar(*), rvbar(*),     &
+     &      rzeta(*), ubar(*), vbar(*), zeta(*)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_step3d_uv_tile (ctx,        &
+     &    ng, tile, LBi, UBi, LBj, UBj, IminS, ImaxS, JminS,          &
+     &    JmaxS, nrhs, nstp, nnew, om_v, on_u, pm, pn, Hz, z_r,       &
+     &    z_w, Akv, DU_avg1, DV_avg1, DU_avg2, DV_avg2, ru, rv,       &
+     &    u, v, ubar, vbar, Huon, Hvom)                               &
+     &                          BIND(C, name='roms_b200_step3d_uv_tile')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: ng, tile, LBi, UBi, LBj, UBj,      &
+     &      IminS, ImaxS, JminS, JmaxS, nrhs, nstp, nnew
+          real(c_double), intent(in) :: om_v(*), on_u(*), pm(*),      &
+     &      pn(*), Hz(*), z_r(*), z_w(*), Akv(*), DU_avg1(*),         &
+     &      DV_avg1(*), DU_avg2(*), DV_avg2(*)
+          real(c_double), intent(inout) :: ru(*), rv(*), u(*),        &
+     &      v(*), ubar(*), vbar(*), Huon(*), Hvom(*)
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_step3d_t_tile (ctx, ng,     &
+     &    tile, LBi, UBi, LBj, UBj, IminS, ImaxS, JminS, JmaxS,       &
+     &    nrhs, nstp, nnew, omn, om_u, om_v, on_u, on_v, pm, pn,      &
+     &    Hz, Huon, Hvom, z_r, Akt, W, t)                             &
+     &                          BIND(C, name='roms_b200_step3d_t_tile')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int), value :: ng, tile, LBi, UBi, LBj, UBj,      &
+     &      IminS, ImaxS, JminS, JmaxS, nrhs, nstp, nnew
+          real(c_double), intent(in) :: omn(*), om_u(*), om_v(*),     &
+     &      on_u(*), on_v(*), pm(*), pn(*), Hz(*), Huon(*),           &
+     &      Hvom(*), z_r(*), Akt(*), W(*)
+          real(c_double), intent(inout) :: t(*)
+        END FUNCTION
       END INTERFACE
 
       CONTAINS
