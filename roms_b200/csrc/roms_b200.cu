@@ -34,8 +34,10 @@ int roms_b200_field_id(const char* name) {
   return -1;
 }
 
+static int create_impl(roms_b200_ctx* c, const roms_b200_bounds* b, const roms_b200_params* p, int device);
 int roms_b200_create(const roms_b200_bounds* b, const roms_b200_params* p, int device, roms_b200_ctx** out) {
   if (!b || !p || !out) return 1;
+  *out = nullptr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     fprintf(stderr, "roms_b200: no CUDA device available; this library has no CPU path\n");
@@ -43,10 +45,17 @@ int roms_b200_create(const roms_b200_bounds* b, const roms_b200_params* p, int d
   }
   if (b->N > RB_MAXN) { fprintf(stderr, "roms_b200: N=%d exceeds RB_MAXN=%d\n", b->N, RB_MAXN); return 3; }
   if (!b->EWperiodic || b->NSperiodic) { fprintf(stderr, "roms_b200: only E-W periodic / N-S closed channels are supported\n"); return 3; }
-  CUDA_OK(cudaSetDevice(device));
+  if (cudaSetDevice(device) != cudaSuccess) { fprintf(stderr, "roms_b200: cannot select CUDA device %d\n", device); return 2; }
   roms_b200_ctx* c = new roms_b200_ctx();
   memset(c, 0, sizeof(*c));
   c->device = device;
+  const int rc = create_impl(c, b, p, device);
+  if (rc) { roms_b200_destroy(c); return rc; }      // nothing of a half-built context survives a failed allocation
+  *out = c;
+  return 0;
+}
+static int create_impl(roms_b200_ctx* c, const roms_b200_bounds* b, const roms_b200_params* p, int device) {
+  (void)device;
   Dev& D = c->D;
   D.b = *b; D.p = *p;
   D.ni = b->UBi - b->LBi + 1; D.nj = b->UBj - b->LBj + 1; D.nij = (size_t)D.ni * D.nj;
@@ -102,23 +111,25 @@ int roms_b200_create(const roms_b200_bounds* b, const roms_b200_params* p, int d
   // initialise_mixing (mod_mixing.F:1430-1530) background values are the host's job (upload Akv,Akt,...)
   c->iic = 0; c->ntfirst = 1; c->nstp = 1; c->nnew = 1; c->nrhs = 1; c->indx1 = 1; c->time = 0.0;
   c->use_graph = (getenv("ROMS_B200_NO_GRAPH") == nullptr);
-  *out = c;
   return 0;
 }
 
 int roms_b200_destroy(roms_b200_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   for (int a = 0; a < 12; ++a) if (c->graph2d[a]) cudaGraphExecDestroy(c->graph2d[a]);
   for (int f = 0; f < ROMS_B200_NFIELDS; ++f) cudaFree(c->D.f[f]);
   cudaFree((void*)c->D.sc_r); cudaFree((void*)c->D.w1); cudaFree(c->D.P); cudaFree(c->D.scratch2); cudaFree(c->D.swdk); cudaFree(c->D.dtdz); cudaFree(c->D.kpp4); cudaFree(c->D.red); cudaFree(c->D.ksbl); cudaFree(c->D.err);
-  cudaFreeHost(c->h_red);
+  if (c->h_red) cudaFreeHost(c->h_red);
   if (c->snap_stream) { cudaStreamSynchronize(c->snap_stream); cudaStreamDestroy(c->snap_stream); cudaEventDestroy(c->snap_ready); cudaEventDestroy(c->snap_done); }
   cudaFree(c->snap_buf);
   roms_b200_comm_destroy(c);
-  cudaStreamDestroy(c->stream); cudaStreamDestroy(c->stream2); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
-  for (int q = 0; q < 6; ++q) cudaEventDestroy(c->ev[q]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  for (int q = 0; q < 6; ++q) if (c->ev[q]) cudaEventDestroy(c->ev[q]);
   delete c;
   return 0;
 }
