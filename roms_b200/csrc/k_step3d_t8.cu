@@ -51,13 +51,14 @@ struct alignas(64) A8 {
   const double *pm, *pn;
   int* err;
   double dt;
-  int N, ni, sk, LBi, LBj, Lm;
+  int N, ni, sk, LBi, LBj, Lm, backoff, pfd;
+  long long* prof;                              // -DS3T_PROF builds only: cycles per role and phase (tools/prof_step3d_t.py)
   int i0, i1, ib, j0, j1, Jstr, Jend, wallS, wallN, wrapEW;   // ib: first column of stripe 0 (<= i0, see k_step3d_t_v8)
   int nstripes, JCH, nitems, S, NC, NP;
 };
 
 // shared-memory layout of one slot (offsets in doubles; every TMA destination is a multiple of 16 doubles = 128 bytes)
-template <int NTR, bool TM> struct Lay {
+template <int NTR, int TM> struct Lay {
   int N;
   __host__ __device__ int q(int c) const { return c * N * LS; }                               // t(nnew) -> q           [N][16]
   __host__ __device__ int ak(int c) const { return NTR * N * LS + c * (N + 1) * LS; }         // Akt, levels 0..N       [N+1][16]
@@ -66,7 +67,7 @@ template <int NTR, bool TM> struct Lay {
   __host__ __device__ int hu() const { return hv() + N * LS; }                                // Huon -> CF of tracer 0 [N][18]
   __host__ __device__ int w() const { return hu() + pad16(N * HUW); }                         // W 0..N -> CF of tracer 1 [N+1][16]
   __host__ __device__ int dc(int c) const { return w() + (N + 1) * LS + c * N * LS; }         // DC                     [N][16]
-  __host__ __device__ int slot() const { return TM ? w() + (N + 1) * LS : dc(0) + NTR * N * LS; }
+  __host__ __device__ int slot() const { return TM ? w() + (N + 1) * LS : dc(0) + NTR * N * LS; }   // TM != 0: no DC arrays
   __host__ __device__ int cf(int c) const { return c == 0 ? hu() : w(); }
   __host__ __device__ int ring_tr() const { return pad16(N * TW); }                           // one tracer of a ring row [N][20]
   __host__ __device__ int ring_row() const { return NTR * ring_tr(); }
@@ -86,7 +87,7 @@ __device__ __forceinline__ void eb_check(EmuBar* e) { if (e->pending == 0 && e->
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) { std::lock_guard<std::mutex> lk(emu_bar_mu); EmuBar* e = eb(b); e->tx = 0; e->pending = (uint16_t)count; e->init_phase = (uint16_t)count; }
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) { std::lock_guard<std::mutex> lk(emu_bar_mu); EmuBar* e = eb(b); if (e->pending == 0) abort(); --e->pending; eb_check(e); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) { std::lock_guard<std::mutex> lk(emu_bar_mu); EmuBar* e = eb(b); e->tx += (int32_t)bytes; if (e->pending == 0) abort(); --e->pending; eb_check(e); }
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int*) {
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int*, unsigned = 0) {
   for (;;) {
     { std::lock_guard<std::mutex> lk(emu_bar_mu); if (((eb(b)->init_phase >> 15) & 1u) != parity) return; }
     emu::yield();
@@ -125,6 +126,19 @@ __device__ __forceinline__ void tmem_ld2d(uint32_t taddr, double& x, double& y) 
   if (ln < 0 || ln > 127 || col < 0 || col + 4 > 512 || ((taddr >> 16) != 32u * ((threadIdx.x >> 5) & 3u))) { fprintf(stderr, "emu: tensor-memory access outside the warp's quadrant or the columns\n"); abort(); }
   memcpy(&x, &emu_tmem[ln][col], 8); memcpy(&y, &emu_tmem[ln][col + 2], 8);
 }
+__device__ __forceinline__ void tmem_st4d(uint32_t taddr, double x, double y, double z, double w) { tmem_st2d(taddr, x, y); tmem_st2d(taddr + 4, z, w); }
+__device__ __forceinline__ void tmem_ld4d(uint32_t taddr, double& x, double& y, double& z, double& w) { tmem_ld2d(taddr, x, y); tmem_ld2d(taddr + 4, z, w); }
+__device__ __forceinline__ void tmem_st1d(uint32_t taddr, double x) {
+  const int ln = (int)(taddr >> 16) + (int)(threadIdx.x & 31), col = (int)(taddr & 0xffffu);
+  if (ln < 0 || ln > 127 || col < 0 || col + 2 > 512) { fprintf(stderr, "emu: tensor-memory access outside the columns\n"); abort(); }
+  memcpy(&emu_tmem[ln][col], &x, 8);
+}
+__device__ __forceinline__ void tmem_ld1d(uint32_t taddr, double& x) {
+  const int ln = (int)(taddr >> 16) + (int)(threadIdx.x & 31), col = (int)(taddr & 0xffffu);
+  if (ln < 0 || ln > 127 || col < 0 || col + 2 > 512) { fprintf(stderr, "emu: tensor-memory access outside the columns\n"); abort(); }
+  memcpy(&x, &emu_tmem[ln][col], 8);
+}
+__device__ __forceinline__ void tma3d_prefetch(const TMap*, int, int, int) {}
 __device__ __forceinline__ double* align128(double* p) { return (double*)(((uintptr_t)p + 127) & ~(uintptr_t)127); }
 #else
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -134,12 +148,13 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t byte
 // try_wait suspends the warp in hardware until the phase completes or the time hint (ns) passes, so a waiting warp takes no
 // issue slots from the working warps of its scheduler; a wait that lasts longer than ~4 s (a lost arrival: a bug) raises the
 // device error word and traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int* err) {
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int* err, unsigned backoff = 0) {
   uint32_t ok; unsigned spins = 0; unsigned long long t0 = 0;
   for (;;) {
     asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
                  : "=r"(ok) : "r"(s32(b)), "r"(parity), "r"(20000u) : "memory");
     if (ok) return;
+    if (backoff) __nanosleep(backoff);
     if ((++spins & 255u) == 0) {
       unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       if (!t0) t0 = t; else if (t - t0 > 4000000000ull) { atomicOr(err, 4); __threadfence(); asm volatile("trap;"); }
@@ -174,6 +189,29 @@ __device__ __forceinline__ void tmem_ld2d(uint32_t taddr, double& x, double& y) 
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr) : "memory");
   x = __hiloint2double(b, a); y = __hiloint2double(d, c);
 }
+__device__ __forceinline__ void tmem_st4d(uint32_t taddr, double x, double y, double z, double w) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(__double2loint(x)), "r"(__double2hiint(x)), "r"(__double2loint(y)), "r"(__double2hiint(y)),
+                 "r"(__double2loint(z)), "r"(__double2hiint(z)), "r"(__double2loint(w)), "r"(__double2hiint(w)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4d(uint32_t taddr, double& x, double& y, double& z, double& w) {
+  int a, b, c, d, e, f, g, h;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(f), "=r"(g), "=r"(h) : "r"(taddr) : "memory");
+  x = __hiloint2double(b, a); y = __hiloint2double(d, c); z = __hiloint2double(f, e); w = __hiloint2double(h, g);
+}
+__device__ __forceinline__ void tmem_st1d(uint32_t taddr, double x) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__double2loint(x)), "r"(__double2hiint(x)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld1d(uint32_t taddr, double& x) {
+  int a, b;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
+  x = __hiloint2double(b, a);
+}
+// L2 prefetch of a TMA box (the loader requests the operands of a later row so that the real copy finds them in L2)
+__device__ __forceinline__ void tma3d_prefetch(const TMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(m), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 // pointer arithmetic on the shared array (a round trip through uintptr_t would lose the address space: generic LD/ST instead of LDS/STS)
 __device__ __forceinline__ double* align128(double* p) { return p + (((128u - (s32(p) & 127u)) & 127u) >> 3); }
 #endif
@@ -198,6 +236,13 @@ __device__ __forceinline__ double vflux8(int k, int N, double tm1, double t0, do
 }  // namespace
 
 // ring of n entries walked in order: index and phase parity without integer division
+#ifdef S3T_PROF
+#define PROF_T(v) const long long v = clock64()
+#define PROF_ADD(acc, t0) acc += clock64() - (t0)
+#else
+#define PROF_T(v)
+#define PROF_ADD(acc, t0)
+#endif
 struct Ring8 {
   int i, n; unsigned ph;
   __device__ __forceinline__ Ring8(int n_) : i(0), n(n_), ph(0) {}
@@ -205,10 +250,13 @@ struct Ring8 {
 };
 
 // KP: level-pair batches per producer warp (NP * KP >= ceil(N/2))
-// TM: CF/DC of the tridiagonal solve in tensor memory instead of the slot (smaller slots -> more of them, more consumer warps)
-// MAXT: launch bound (384: up to 12 warps with up to 168 registers per thread; 512: up to 16 warps with 128)
-template <int NTR, int KP, bool TM, int MAXT>
+// TM: 0 = CF/DC of the tridiagonal solve in the slot; 1 = CF/DC in tensor memory (smaller slots -> more of them, more consumer
+// warps); 2 = everything the back substitution needs (CF, DC, q, Akt, dt/Hz per level) in tensor memory: the consumer hands the
+// slot back to the loader right after its forward sweep, the backward sweep and the stores run out of tensor memory
+// MAXT: launch bound (384: up to 12 warps with up to 168 registers per thread; 512: up to 16 warps with 128; 640: up to 20 with 96)
+template <int NTR, int KP, int TM, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_constant__ A8 a) {
+  constexpr int TMC = (TM == 2) ? 10 : 4;         // tensor-memory columns per level
   extern __shared__ __align__(128) double sm_raw[];
   double* sm = align128(sm_raw);
   const int N = a.N, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -228,8 +276,8 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
     for (int q = 0; q < MAXS; ++q) { mbar_init(&slot_full[q], 1); mbar_init(&slot_ready[q], NP); mbar_init(&slot_empty[q], 1); }
     fence_barrier_init();
   }
-  uint32_t tm_cols = 32;                        // 4 32-bit columns per level (CF, DC), a power of two
-  while (tm_cols < 4u * (unsigned)N) tm_cols *= 2;
+  uint32_t tm_cols = 32;                        // 4 (CF, DC) or 10 (CF, DC, q, Akt, dt/Hz) 32-bit columns per level, a power of two
+  while (tm_cols < (TM == 2 ? 10u : 4u) * (unsigned)N) tm_cols *= 2;
   if (TM && warp == 1) tmem_alloc(tmem_word, tm_cols);
   if (TM) tmem_fence_before();
   __syncthreads();
@@ -242,6 +290,9 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
     // ======================= loader: one thread issues every TMA copy of the CTA =======================
     if (lane == 0) {
       Ring8 g(RING), q(S);                      // ring rows / slots issued so far
+#ifdef S3T_PROF
+      long long p_ring = 0, p_slot = 0; const long long p_t0 = clock64();
+#endif
       for (int it = blockIdx.x; it < a.nitems; it += gridDim.x) {
         const int stripe = it % a.nstripes, chunk = it / a.nstripes;
         const int i0s = a.ib + stripe * BI, ja = a.j0 + chunk * a.JCH, jb = min(ja + a.JCH - 1, a.j1);
@@ -249,7 +300,7 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
         for (int r = 0; r < nrows + 4; ++r) {
           const int n = ja - 2 + r;             // t(3) row that arrives at this step
           {
-            mbar_wait(&ring_empty[g.i], g.ph ^ 1u, a.err);
+            { PROF_T(t_); mbar_wait(&ring_empty[g.i], g.ph ^ 1u, a.err); PROF_ADD(p_ring, t_); }
             mbar_arrive_expect_tx(&ring_full[g.i], 8u * (unsigned)(NTR * N * TW));
 #pragma unroll
             for (int c = 0; c < NTR; ++c) tma3d(ring + g.i * rowD + c * trD, &a.t3[c], ci - 2, n - a.LBj, 0, &ring_full[g.i]);
@@ -257,7 +308,7 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
           }
           if (r >= 3) {                         // operands of row j = n-2 (r == 3: the row below the chunk, only its Hvom(j+1) is needed)
             const int cj = n - 2 - a.LBj, sl = q.i;
-            mbar_wait(&slot_empty[sl], q.ph ^ 1u, a.err);
+            { PROF_T(t_); mbar_wait(&slot_empty[sl], q.ph ^ 1u, a.err); PROF_ADD(p_slot, t_); }
             double* sp = slots + sl * slotD;
             if (r == 3) {
               mbar_arrive_expect_tx(&slot_full[sl], 8u * (unsigned)(N * LS));
@@ -276,8 +327,25 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
             }
             q.next();
           }
+          if (a.pfd > 0) {                      // L2 prefetch of what the step `pfd` steps ahead will copy
+            const int rp = r + a.pfd;
+            if (rp < nrows + 4) {
+              const int np_ = ja - 2 + rp;
+#pragma unroll
+              for (int c = 0; c < NTR; ++c) tma3d_prefetch(&a.t3[c], ci - 2, np_ - a.LBj, 0);
+              if (rp >= 4) {
+                const int cjp = np_ - 2 - a.LBj;
+#pragma unroll
+                for (int c = 0; c < NTR; ++c) { tma3d_prefetch(&a.tw[c], ci, cjp, 0); tma3d_prefetch(&a.ak[c], ci, cjp, 0); }
+                tma3d_prefetch(&a.hz, ci, cjp, 0); tma3d_prefetch(&a.hv, ci, cjp + 1, 0); tma3d_prefetch(&a.hu, ci, cjp, 0); tma3d_prefetch(&a.w, ci, cjp, 0);
+              }
+            }
+          }
         }
       }
+#ifdef S3T_PROF
+      if (a.prof) { atomicAdd((unsigned long long*)&a.prof[0], (unsigned long long)(clock64() - p_t0)); atomicAdd((unsigned long long*)&a.prof[1], (unsigned long long)p_ring); atomicAdd((unsigned long long*)&a.prof[2], (unsigned long long)p_slot); }
+#endif
     }
   } else if (warp > NC) {
     // ======================= producers: advection, level-parallel =======================
@@ -299,6 +367,9 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
     const int oq = L.q(0), dq_ = L.q(1) - L.q(0), ohz_ = L.hz(), ohv = L.hv(), ohu = L.hu(), ow = L.w();
     int gi = 0;                                 // ring buffer of the row that arrives at this step
     unsigned gph = 0;
+#ifdef S3T_PROF
+    long long p_ring = 0, p_slot = 0, p_work = 0; const long long p_t0 = clock64();
+#endif
     Ring8 q(S);
     for (int it = blockIdx.x; it < a.nitems; it += gridDim.x) {
       const int stripe = it % a.nstripes, chunk = it / a.nstripes;
@@ -310,7 +381,7 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
       int o2 = (ic - a.LBi) + a.ni * (ja - a.LBj);
       double cffn = dt * __ldg(a.pm + o2) * __ldg(a.pn + o2);         // dt*pm*pn of the chunk's first row (later rows: one row ahead)
       for (int r = 0; r < nrows + 4; ++r) {
-        mbar_wait(&ring_full[gi], gph, a.err);
+        { PROF_T(t_); mbar_wait(&ring_full[gi], gph, a.err, a.backoff); PROF_ADD(p_ring, t_); }
         const int g0 = gi;                                            // row n
         const int g1 = (gi + RING - 1) & (RING - 1), g2 = (gi + RING - 2) & (RING - 1);   // rows n-1, n-2
         if (++gi == RING) { gi = 0; gph ^= 1u; }
@@ -322,7 +393,7 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
           // start of a chunk, part 1 (rows ja-2, ja-1, ja): cm1 = curv(ja-1), e0 = FE-gradient at ja  (step3d_t.F:697-724)
 #pragma unroll
           for (int m = 0; m < KP; ++m) {
-            if (kk[m] == 0) break;
+            if (kk[m] != 0) {
 #pragma unroll
             for (int c = 0; c < NTR; ++c) {
               const double tm2 = R0[c * trD + o0[m]], tm1 = R1[c * trD + o0[m]], tA = R2[c * trD + o0[m]];
@@ -330,15 +401,16 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
               const double em1 = southw ? e0 : (tm1 - tm2);           // FE(i,Jstr-1)=FE(i,Jstr) on the southern wall
               Cj[m][c] = e0 - em1; FEs[m][c] = e0;
             }
+            }
           }
         } else if (r == 3) {
           // part 2 (rows ja-1, ja, ja+1; Hvom(ja) in the slot of the row below the chunk): FE(ja), curv(ja)
           const int sl = q.i;
-          mbar_wait(&slot_full[sl], q.ph, a.err);
+          mbar_wait(&slot_full[sl], q.ph, a.err, a.backoff);
           const double* sp = slots + sl * slotD;
 #pragma unroll
           for (int m = 0; m < KP; ++m) {
-            if (kk[m] == 0) break;
+            if (kk[m] != 0) {
             const double hv = sp[ohv + so[m]];
             double hvx, hvn; posneg(hv, hvx, hvn);
             const double hvh = hv * 0.5;
@@ -348,6 +420,7 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
               const double e1 = tB - tA, c0 = e1 - FEs[m][c];
               FEs[m][c] = hvh * (tm1 + tA) - c16 * (Cj[m][c] * hvx + c0 * hvn);
               Cj[m][c] = c0;
+            }
             }
           }
           __syncwarp();
@@ -362,11 +435,12 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
           const bool more = (r < nrows + 3);
           double pmn = 0.0, pnn = 0.0;
           if (more) { pmn = __ldg(a.pm + o2); pnn = __ldg(a.pn + o2); }    // metrics of the next row: requested now, used after the batches
-          mbar_wait(&slot_full[sl], q.ph, a.err);
+          { PROF_T(t_); mbar_wait(&slot_full[sl], q.ph, a.err, a.backoff); PROF_ADD(p_slot, t_); }
+          PROF_T(tw_);
           double* sp = slots + sl * slotD;
 #pragma unroll
           for (int m = 0; m < KP; ++m) {
-            if (kk[m] == 0) break;
+            if (kk[m] != 0) {
             const int k = kk[m];
             const bool valid = (k <= N);
             // ---- load phase (shared memory only)
@@ -410,7 +484,9 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
               Cj[m][c] = c1; FEs[m][c] = FEn;
             }
             if (valid) sp[ohv + sm_] = ohz;
+            }
           }
+          PROF_ADD(p_work, tw_);
           __syncwarp();
           if (lane == 0) mbar_arrive(&slot_ready[sl]);
           q.next();
@@ -424,6 +500,9 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
         }
       }
     }
+#ifdef S3T_PROF
+    if (a.prof && lane == 0) { atomicAdd((unsigned long long*)&a.prof[4], (unsigned long long)(clock64() - p_t0)); atomicAdd((unsigned long long*)&a.prof[5], (unsigned long long)p_ring); atomicAdd((unsigned long long*)&a.prof[6], (unsigned long long)p_slot); atomicAdd((unsigned long long*)&a.prof[7], (unsigned long long)p_work); }
+#endif
   } else {
     // ======================= consumers: spline tridiagonal per (column, tracer) =======================
     const int cw = warp - 1, col = lane & 15, c = (NTR == 2) ? (lane >> 4) : 0;
@@ -434,6 +513,9 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
     const uint32_t tm0 = tm_base + ((32u * (unsigned)(warp & 3)) << 16);      // this warp's lanes, level 1
     Ring8 q(S);
     int turn = 0;                                                     // consumer warp that owns the next slot
+#ifdef S3T_PROF
+    long long p_wait = 0, p_fwd = 0, p_bwd = 0; const long long p_t0 = clock64();
+#endif
     for (int it = blockIdx.x; it < a.nitems; it += gridDim.x) {
       const int stripe = it % a.nstripes, chunk = it / a.nstripes;
       const int i0s = a.ib + stripe * BI, ja = a.j0 + chunk * a.JCH, jb = min(ja + a.JCH - 1, a.j1);
@@ -444,8 +526,9 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
       for (int rr = -1; rr < nrows; ++rr, q.next(), turn = (turn + 1 == NC) ? 0 : turn + 1) {
         if (turn != cw) continue;
         const int sl = q.i;
-        mbar_wait(&slot_ready[sl], q.ph, a.err);
+        { PROF_T(t_); mbar_wait(&slot_ready[sl], q.ph, a.err); PROF_ADD(p_wait, t_); }
         if (rr >= 0) {
+          PROF_T(tf_);
           const int j = ja + rr;
           double* sp = slots + sl * slotD;
           const double* pq = sp + oq;                    // q(k)    at pq[(k-1)*LS]
@@ -472,6 +555,7 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
           pq += 2 * LS; pa += 3 * LS; ph += 2 * LS; po += 2 * LS;        // -> level 3
           double cf_prev = 0.0, dc_prev = 0.0;
           double ak_top = akN, q_top = qN, ohz_top = ohzN;
+          double ak_lvl = pa[-2 * LS], q_lvl = pq[-2 * LS], ohz_lvl = po[-2 * LS];   // level k of the coming pass (TM == 2)
           int badl = 0;
           uint32_t tmc = tm0;                                            // tensor-memory address of (CF, DC)(k)
 #pragma unroll 4
@@ -482,7 +566,8 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
             const double cf = rcp_ieee(BC - FC * cf_prev, badl);
             cf_prev = cf * CF;
             dc_prev = cf * (dq - FC * dc_prev);
-            if (TM) { tmem_st2d(tmc, cf_prev, dc_prev); tmc += 4; }
+            if (TM == 2) { tmem_st4d(tmc, cf_prev, dc_prev, q_lvl, ak_lvl); tmem_st1d(tmc + 8, dt * ohz_lvl); tmc += TMC; ak_lvl = akN; q_lvl = qN; ohz_lvl = ohzN; }
+            else if (TM == 1) { tmem_st2d(tmc, cf_prev, dc_prev); tmc += TMC; }
             else { *pcf = cf_prev; *pdc = dc_prev; pcf += LS; pdc += LS; }
             const double c16L = c16 * hzL, dtakL = dt * akL;
             FC = c16N - dtakK * ohzN;
@@ -492,6 +577,8 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
             dtakK = dtakN; hzN = hzL; ohzN = ohzL; c16N = c16L; dtakN = dtakL; qN = qL; akN = akL;
           }
           if (act) bad |= badl;
+          PROF_ADD(p_fwd, tf_);
+          PROF_T(tb_);
           // back substitution + final update, level N first.  pcf/pdc point one past level N-1; pq/po/pa at level N+2.
           const bool south = a.wallS && j == a.Jstr, north = a.wallN && j == a.Jend;
           double* tw = a.out[c] + ((i - a.LBi) + (size_t)ni * (j - a.LBj)) + (size_t)sk * (N - 1);   // t(nnew)(i,j,N)
@@ -499,27 +586,42 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
           double a_next = dc_next * ak_top;                              // DC(N)*Akt(N)
           double q_next = q_top, dtohz_next = dt * ohz_top;
           pcf -= LS; pdc -= LS; pq -= 3 * LS; po -= 3 * LS; pa -= 3 * LS;    // level N-1
-          double Xk, Yk;
-          if (TM) { tmem_wait_st(); tmc -= 4; tmem_ld2d(tmc, Xk, Yk); tmem_wait_ld(); }
-          else { Xk = *pcf; Yk = *pdc; }
-          double akk = *pa, qk = *pq, ohzk = *po;
-          // operands of level k-1 are fetched one level ahead; for k = 1 that is "level 0" = the array space just below (not used)
+          double Xk, Yk, akk, qk, dtk;                                   // CF, DC, Akt, q, dt/Hz of level k
+          if (TM == 2) {
+            tmem_wait_st();
+            fence_proxy_async();                                         // the slot goes back to the loader before the backward sweep
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slot_empty[sl]);
+            tmc -= TMC; tmem_ld4d(tmc, Xk, Yk, qk, akk); tmem_ld1d(tmc + 8, dtk); tmem_wait_ld();
+          } else {
+            if (TM == 1) { tmem_wait_st(); tmc -= TMC; tmem_ld2d(tmc, Xk, Yk); tmem_wait_ld(); }
+            else { Xk = *pcf; Yk = *pdc; }
+            akk = *pa; qk = *pq; dtk = dt * *po;
+          }
+          // operands of level k-1 are fetched one level ahead; for k = 1 that is "level 0": tensor memory re-reads level 1, the
+          // shared-memory path reads the array space just below (neither is used)
+          auto level_below = [&](int k, double& Xm, double& Ym, double& akm, double& qm, double& dtm) {
+            if (TM == 2) { if (k > 1) tmc -= TMC; tmem_ld4d(tmc, Xm, Ym, qm, akm); tmem_ld1d(tmc + 8, dtm); }
+            else {
+              pq -= LS; po -= LS; pa -= LS;
+              if (TM == 1) { if (k > 1) tmc -= TMC; tmem_ld2d(tmc, Xm, Ym); }
+              else { pcf -= LS; pdc -= LS; Xm = *pcf; Ym = *pdc; }
+              akm = *pa; qm = *pq; dtm = dt * *po;
+            }
+          };
           if (!(edge_stripe || south || north)) {
             // interior stripe and row: one store per level
 #pragma unroll 4
             for (int k = N - 1; k >= 1; --k) {
-              pq -= LS; po -= LS; pa -= LS;
-              double Xm, Ym;
-              if (TM) { if (k > 1) tmc -= 4; tmem_ld2d(tmc, Xm, Ym); }   // k == 1: "level 0", re-reads level 1 (not used)
-              else { pcf -= LS; pdc -= LS; Xm = *pcf; Ym = *pdc; }
-              const double akm = *pa, qm = *pq, ohzm = *po;
+              double Xm, Ym, akm, qm, dtm;
+              level_below(k, Xm, Ym, akm, qm, dtm);
               const double dc_k = Yk - Xk * dc_next;
               const double a_k = dc_k * akk;
               if (act) *tw = q_next + dtohz_next * (a_next - a_k);       // level k+1
               tw -= sk;
-              dc_next = dc_k; a_next = a_k; q_next = qk; dtohz_next = dt * ohzk;
+              dc_next = dc_k; a_next = a_k; q_next = qk; dtohz_next = dtk;
               if (TM) tmem_wait_ld();
-              Xk = Xm; Yk = Ym; akk = akm; qk = qm; ohzk = ohzm;
+              Xk = Xm; Yk = Ym; akk = akm; qk = qm; dtk = dtm;
             }
             if (act) *tw = q_next + dtohz_next * (a_next - 0.0);         // level 1; DC(0)=0 is not scaled by Akt
           } else {
@@ -535,26 +637,28 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
             };
 #pragma unroll 1
             for (int k = N - 1; k >= 1; --k) {
-              pq -= LS; po -= LS; pa -= LS;
-              double Xm, Ym;
-              if (TM) { if (k > 1) tmc -= 4; tmem_ld2d(tmc, Xm, Ym); }
-              else { pcf -= LS; pdc -= LS; Xm = *pcf; Ym = *pdc; }
-              const double akm = *pa, qm = *pq, ohzm = *po;
+              double Xm, Ym, akm, qm, dtm;
+              level_below(k, Xm, Ym, akm, qm, dtm);
               const double dc_k = Yk - Xk * dc_next;
               const double a_k = dc_k * akk;
               put(q_next + dtohz_next * (a_next - a_k));
-              dc_next = dc_k; a_next = a_k; q_next = qk; dtohz_next = dt * ohzk;
+              dc_next = dc_k; a_next = a_k; q_next = qk; dtohz_next = dtk;
               if (TM) tmem_wait_ld();
-              Xk = Xm; Yk = Ym; akk = akm; qk = qm; ohzk = ohzm;
+              Xk = Xm; Yk = Ym; akk = akm; qk = qm; dtk = dtm;
             }
             put(q_next + dtohz_next * (a_next - 0.0));
           }
+          PROF_ADD(p_bwd, tb_);
+          if (TM == 2) continue;                                         // slot already released
         }
         fence_proxy_async();                     // generic-proxy accesses of the slot are ordered before the TMA refill
         __syncwarp();
         if (lane == 0) mbar_arrive(&slot_empty[sl]);
       }
     }
+#ifdef S3T_PROF
+    if (a.prof && lane == 0) { atomicAdd((unsigned long long*)&a.prof[8], (unsigned long long)(clock64() - p_t0)); atomicAdd((unsigned long long*)&a.prof[9], (unsigned long long)p_wait); atomicAdd((unsigned long long*)&a.prof[10], (unsigned long long)p_fwd); atomicAdd((unsigned long long*)&a.prof[11], (unsigned long long)p_bwd); }
+#endif
   }
   if (bad) atomicOr(a.err, 1);
   if (TM) {
@@ -597,26 +701,29 @@ int make_map(TMap* m, const double* base, int ni, int nj, int nk, int bw, int bk
 #endif
 }
 
-template <int NTR, int KP, bool TM, int MAXT>
+template <int NTR, int KP, int TM, int MAXT>
 int launch_v8_t(roms_b200_ctx* c, const A8& a, int grid, size_t smem) {
   static size_t set = 0;
   if (smem > set) { CUDA_OK(cudaFuncSetAttribute(step3d_t_v8_kernel<NTR, KP, TM, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = smem; }
   step3d_t_v8_kernel<NTR, KP, TM, MAXT><<<dim3(grid), dim3(32 * (1 + a.NC + a.NP)), smem, c->stream>>>(a);
   return 0;
 }
-template <int NTR, int KP, bool TM>
+template <int NTR, int KP, int TM>
 int launch_v8(roms_b200_ctx* c, const A8& a, int grid, size_t smem) {
-  return 32 * (1 + a.NC + a.NP) <= 384 ? launch_v8_t<NTR, KP, TM, 384>(c, a, grid, smem) : launch_v8_t<NTR, KP, TM, 512>(c, a, grid, smem);
+  const int nt = 32 * (1 + a.NC + a.NP);
+  if (nt <= 384) return launch_v8_t<NTR, KP, TM, 384>(c, a, grid, smem);
+  if (nt <= 512) return launch_v8_t<NTR, KP, TM, 512>(c, a, grid, smem);
+  return launch_v8_t<NTR, KP, TM, 640>(c, a, grid, smem);
 }
-template <int NTR, bool TM>
+template <int NTR, int TM>
 int launch_v8_kp(roms_b200_ctx* c, const A8& a, int grid, size_t smem, int KP) {
   if (KP == 1) return launch_v8<NTR, 1, TM>(c, a, grid, smem);
   if (KP == 2) return launch_v8<NTR, 2, TM>(c, a, grid, smem);
   return launch_v8<NTR, 4, TM>(c, a, grid, smem);
 }
-size_t smem_v8(int ntr, bool tm, int N, int S) {
-  if (ntr == 2) return tm ? Lay<2, true>{N}.bytes(S) : Lay<2, false>{N}.bytes(S);
-  return tm ? Lay<1, true>{N}.bytes(S) : Lay<1, false>{N}.bytes(S);
+size_t smem_v8(int ntr, int tm, int N, int S) {
+  if (ntr == 2) return tm ? Lay<2, 1>{N}.bytes(S) : Lay<2, 0>{N}.bytes(S);
+  return tm ? Lay<1, 1>{N}.bytes(S) : Lay<1, 0>{N}.bytes(S);
 }
 }  // namespace
 
@@ -640,8 +747,9 @@ int k_step3d_t_v8(roms_b200_ctx* c, int nnew) {
   for (int itr0 = 1; itr0 <= b.NT; itr0 += 2) {
     const int ntr = (itr0 + 1 <= b.NT) ? 2 : 1;
     // CF/DC of the tridiagonal solve in tensor memory (4 32-bit columns per level, <= 512 columns) unless switched off
-    static const bool no_tm = (getenv("ROMS_B200_S3T_TMEM") != nullptr && atoi(getenv("ROMS_B200_S3T_TMEM")) == 0);
-    const bool tm = !no_tm && 4 * N <= 512;
+    // (mode 2, 10 columns per level: also q, Akt, dt/Hz, so that the slot is released after the forward sweep)
+    static const int tm_env = getenv("ROMS_B200_S3T_TMEM") ? atoi(getenv("ROMS_B200_S3T_TMEM")) : 2;
+    const int tm = (tm_env >= 2 && 10 * N <= 512) ? 2 : ((tm_env >= 1 && 4 * N <= 512) ? 1 : 0);
     // slots: as many as fit (at most 6); consumers: every slot that is neither being loaded nor being produced, at most 4
     // (with tensor memory each consumer warp needs its own lane quadrant: warps 1..4)
     int S = 0;
@@ -655,7 +763,7 @@ int k_step3d_t_v8(roms_b200_ctx* c, int nnew) {
     int KP = 0, NP = 0;
     for (int kp = 1; kp <= 4 && !KP; kp *= 2) {
       const int np = force_np ? force_np : (nb + kp - 1) / kp;
-      if (np * kp >= nb && 1 + NC + np <= 16) { KP = kp; NP = np; }
+      if (np * kp >= nb && 1 + NC + np <= (force_np ? 20 : 16)) { KP = kp; NP = np; }
     }
     if (!KP) return 2;
     // TMA: the first element of a box must be 16-byte aligned in global memory (measured on B200, tools/ubench/tma3d_test.cu: an odd
@@ -679,6 +787,10 @@ int k_step3d_t_v8(roms_b200_ctx* c, int nnew) {
     a.wallS = b.Southern_Edge && !b.NSperiodic; a.wallN = b.Northern_Edge && !b.NSperiodic; a.wrapEW = D.wrapEW;
     a.nstripes = nstripes; a.JCH = best_jch; a.nitems = nstripes * ((rows + best_jch - 1) / best_jch);
     a.S = S; a.NC = NC; a.NP = NP; a.dt = D.p.dt; a.err = D.err;
+    static const int backoff = getenv("ROMS_B200_S3T_BACKOFF") ? atoi(getenv("ROMS_B200_S3T_BACKOFF")) : 0;
+    a.backoff = backoff;
+    static const int pfd = getenv("ROMS_B200_S3T_PFD") ? atoi(getenv("ROMS_B200_S3T_PFD")) : 0;
+    a.pfd = pfd;
     a.pm = D.f[FID(pm)]; a.pn = D.f[FID(pn)];
     const size_t vol = D.nij * (size_t)N;
     int rc = 0;
@@ -698,14 +810,29 @@ int k_step3d_t_v8(roms_b200_ctx* c, int nnew) {
     rc |= make_map(&a.w, D.f[FID(W)], D.ni, D.nj, N + 1, BI, N + 1);
     if (rc) return 2;
     const int grid = a.nitems < nsm ? a.nitems : nsm;
+#ifdef S3T_PROF
+    static long long* prof = nullptr;
+    if (!prof) cudaMalloc((void**)&prof, 16 * sizeof(long long));
+    cudaMemsetAsync(prof, 0, 16 * sizeof(long long), c->stream);
+    a.prof = prof;
+#endif
     static const bool verbose = (getenv("ROMS_B200_S3T_VERBOSE") != nullptr);
     if (verbose) fprintf(stderr, "step3d_t v8: N=%d ntr=%d stripes=%d JCH=%d items=%d grid=%d slots=%d consumers=%d producers=%dx%d smem=%zu tmem=%d\n", N, ntr, nstripes,
-                         a.JCH, a.nitems, grid, S, NC, NP, KP, smem_v8(ntr, tm, N, S), (int)tm);
+                         a.JCH, a.nitems, grid, S, NC, NP, KP, smem_v8(ntr, tm, N, S), tm);
     const size_t smem = smem_v8(ntr, tm, N, S);
-    if (ntr == 2) rc = tm ? launch_v8_kp<2, true>(c, a, grid, smem, KP) : launch_v8_kp<2, false>(c, a, grid, smem, KP);
-    else rc = tm ? launch_v8_kp<1, true>(c, a, grid, smem, KP) : launch_v8_kp<1, false>(c, a, grid, smem, KP);
+    if (ntr == 2) rc = tm == 2 ? launch_v8_kp<2, 2>(c, a, grid, smem, KP) : (tm == 1 ? launch_v8_kp<2, 1>(c, a, grid, smem, KP) : launch_v8_kp<2, 0>(c, a, grid, smem, KP));
+    else rc = tm == 2 ? launch_v8_kp<1, 2>(c, a, grid, smem, KP) : (tm == 1 ? launch_v8_kp<1, 1>(c, a, grid, smem, KP) : launch_v8_kp<1, 0>(c, a, grid, smem, KP));
     if (rc) return rc;
     c->launches++;
+#ifdef S3T_PROF
+    {
+      long long h[16]; cudaStreamSynchronize(c->stream); cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+      const double L = (double)grid, P = (double)grid * NP, C = (double)grid * NC;
+      fprintf(stderr, "S3T_PROF kcycles per CTA/warp: loader total %.0f wait_ring %.0f wait_slot %.0f | producer total %.0f wait_ring %.0f wait_slot %.0f work %.0f | "
+                      "consumer total %.0f wait %.0f fwd %.0f bwd %.0f\n", h[0] / L / 1e3, h[1] / L / 1e3, h[2] / L / 1e3, h[4] / P / 1e3, h[5] / P / 1e3, h[6] / P / 1e3,
+              h[7] / P / 1e3, h[8] / C / 1e3, h[9] / C / 1e3, h[10] / C / 1e3, h[11] / C / 1e3);
+    }
+#endif
   }
   return 0;
 }
