@@ -278,6 +278,13 @@ int roms_b200_step3d_t_tile(roms_b200_ctx* ctx, int ng, int tile, int LBi, int U
 int roms_b200_snapshot_begin(roms_b200_ctx* ctx, int nfields, const int* fields, double* const* pinned_host);
 int roms_b200_snapshot_end(roms_b200_ctx* ctx);
 
+/* PERFECT_RESTART (Utility/wrt_rst.F:178-211,345-900): ids of the fields a bit-identical continuation needs (returns the count, -1
+ * if `cap` is too small); write them with roms_b200_snapshot_begin/end or roms_b200_download together with the six stepping
+ * integers and the time (roms_b200_get_stepping).  To restart: initialise a context as usual, upload the set, roms_b200_set_stepping,
+ * roms_b200_restart_finish (what post_initial repeats on restart: depths from Zt_avg1). */
+int roms_b200_restart_fields(const roms_b200_ctx* ctx, int* ids, int cap);
+int roms_b200_restart_finish(roms_b200_ctx* ctx);
+
 /* CUDA-event stopwatch on the context's launch stream, and an L2 flush (writes `mbytes` MiB) */
 int roms_b200_timer_start(roms_b200_ctx* ctx);
 int roms_b200_timer_stop(roms_b200_ctx* ctx, float* ms);

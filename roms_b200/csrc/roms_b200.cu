@@ -457,6 +457,24 @@ int roms_b200_snapshot_end(roms_b200_ctx* c) {
   LEAVE();
 }
 
+// ---- PERFECT_RESTART (Utility/wrt_rst.F:178-211 time indices; :345-900 fields): the state a bit-identical continuation needs.
+// The list is the reference's for the UPWELLING / BENCHMARK option sets -- zeta(3), rzeta(2), ubar(3), rubar(2), vbar(3), rvbar(2),
+// u(2), ru(0:N,2), v(2), rv(0:N,2), t(3,NT), rho, Hsbl, ghats, Akv, Akt(NAT) -- plus Zt_avg1, which the reference rebuilds from
+// zeta in ini_zeta on restart and this library takes as stored.  Use with roms_b200_snapshot_begin/end (asynchronous) or
+// roms_b200_download; after uploading the set into a freshly initialised context call roms_b200_set_stepping with the stored
+// indices and roms_b200_restart_finish (the part of post_initial a restart repeats: set_depth from Zt_avg1).
+int roms_b200_restart_fields(const roms_b200_ctx* c, int* ids, int cap) {
+  if (!c || !ids) return -1;
+  const bool bench = (c->D.p.app == ROMS_B200_APP_BENCHMARK);
+  const int all[] = {FID(zeta), FID(rzeta), FID(ubar), FID(rubar), FID(vbar), FID(rvbar), FID(u), FID(ru), FID(v), FID(rv), FID(t), FID(rho),
+                     FID(Akv), FID(Akt), FID(Zt_avg1), FID(hsbl), FID(ghats)};
+  const int n = bench ? 17 : 15;                       // Hsbl (LMD_SKPP), ghats (LMD_NONLOCAL): BENCHMARK only
+  if (cap < n) return -1;
+  for (int q = 0; q < n; ++q) ids[q] = all[q];
+  return n;
+}
+int roms_b200_restart_finish(roms_b200_ctx* c) { ENTER(c); k_set_depth(c); LEAVE(); }
+
 // CUDA-event stopwatch on the context's launch stream (cudaEvent sees only that stream)
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 int roms_b200_timer_start(roms_b200_ctx* c) {

@@ -615,6 +615,22 @@
      &      Hvom(*), z_r(*), Akt(*), W(*)
           real(c_double), intent(inout) :: t(*)
         END FUNCTION
+!
+!  PERFECT_RESTART state list (wrt_rst.F) and the restart epilogue.
+!
+        integer(c_int) FUNCTION roms_b200_restart_fields (ctx,        &
+     &    ids, cap)                                                   &
+     &                          BIND(C, name='roms_b200_restart_fields')
+          IMPORT
+          type(c_ptr), value :: ctx
+          integer(c_int) :: ids(*)
+          integer(c_int), value :: cap
+        END FUNCTION
+        integer(c_int) FUNCTION roms_b200_restart_finish (ctx)        &
+     &                          BIND(C, name='roms_b200_restart_finish')
+          IMPORT
+          type(c_ptr), value :: ctx
+        END FUNCTION
       END INTERFACE
 
       CONTAINS

@@ -166,6 +166,47 @@ def tiles():
     print("EMU-TILES-OK app=%d %dx%dx%d steps=%d tiles=%dx%d" % (app, Lm, Mm, N, nsteps, nti, ntj))
 
 
+def restart():
+    """PERFECT_RESTART: the field list of roms_b200_restart_fields + the stepping integers written after 5 steps, uploaded into a
+    freshly initialised context, must continue bit-identically to the uninterrupted run."""
+    print("EMU-RESTART-OK", perfect_restart_check(int(sys.argv[2]), tuple(int(x) for x in sys.argv[3:6])))
+
+
+def perfect_restart_check(app, grid, use_snapshot=False):
+    import ctypes as C
+    L = rb.lib.Lib.get().L
+    L.roms_b200_restart_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.roms_b200_restart_finish.argtypes = [C.c_void_p]
+    d = rb.Driver(rb.default_config(app, *grid))
+    d.run(5)
+    ids = (C.c_int * 32)()
+    n = L.roms_b200_restart_fields(d.ctx.h, ids, 32)
+    assert n >= 15
+    names = [rb.FIELD_NAMES[ids[q]] for q in range(n)]
+    if use_snapshot:                           # the asynchronous output path: the loop keeps running while the record drains
+        views = d.ctx.snapshot_begin(names)
+        st, tm = d.ctx.get_stepping()
+        d.run(4)
+        d.ctx.snapshot_end()
+        snap = {nm: views[nm].copy() for nm in names}
+    else:
+        snap = {nm: d.ctx.download(nm) for nm in names}
+        st, tm = d.ctx.get_stepping()
+        d.run(4)
+    ref = {nm: d.ctx.download(nm) for nm in rb.FIELD_NAMES}
+    d2 = rb.Driver(rb.default_config(app, *grid))
+    for nm in names:
+        d2.ctx.upload(nm, snap[nm])
+    d2.ctx.set_stepping(st["iic"], st["ntfirst"], st["nstp"], st["nnew"], st["nrhs"], st["indx1"], tm)
+    assert L.roms_b200_restart_finish(d2.ctx.h) == 0
+    d2.run(4)
+    bad = [nm for nm in ("zeta", "ubar", "vbar", "u", "v", "t", "ru", "rv", "Akv", "Akt", "W", "rho", "Zt_avg1", "Hz")
+           if not np.array_equal(ref[nm], d2.ctx.download(nm))]
+    assert not bad, bad
+    d.finalize(); d2.finalize()
+    return names
+
+
 def eos():
     """rho_eos_kernel (emulated) against the reference's own check values, rho_eos.F:21-29."""
     from parity_common import eos_check_state, eos_check_compare, push
@@ -180,6 +221,8 @@ def eos():
 if __name__ == "__main__":
     if sys.argv[1] == "eos":
         eos()
+    elif sys.argv[1] == "restart":
+        restart()
     elif sys.argv[1] == "tiles":
         tiles()
     elif sys.argv[1] == "driver":

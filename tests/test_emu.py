@@ -80,6 +80,15 @@ def test_host_driver_on_emulated_kernels(emu_lib):
     assert r.returncode == 0 and "EMU-DRIVER-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("app,grid", [(1, (33, 9, 10)), (0, (24, 10, 8))])
+def test_perfect_restart_field_list(emu_lib, app, grid):
+    """roms_b200_restart_fields (the reference's PERFECT_RESTART record, Utility/wrt_rst.F:178-900, for both option sets) written
+    after 5 steps and read into a fresh context continues bit-identically to the uninterrupted run."""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "restart", str(app)] + [str(x) for x in grid], capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0 and "EMU-RESTART-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_kernel_sources_memory_safe_under_asan(emu_lib):
     """Same protocol with the emulation built under AddressSanitizer: every mirror field is its own heap block and every
     shared-memory tile its own static array, so a stencil index outside a field or a tile aborts the worker."""

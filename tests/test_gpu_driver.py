@@ -90,6 +90,39 @@ def test_output_snapshot_does_not_disturb_the_time_loop():
     d.finalize(); d2.finalize()
 
 
+@pytest.mark.parametrize("app,grid", [(ol.BENCHMARK, (96, 40, 30)), (ol.UPWELLING, (0, 0, 0))])
+def test_perfect_restart_through_the_snapshot_path(app, grid):
+    """The PERFECT_RESTART record (roms_b200_restart_fields: the reference's list, Utility/wrt_rst.F:178-900) taken with the
+    asynchronous snapshot API while the loop keeps stepping, read into a fresh context: the continuation is bit-identical to the
+    uninterrupted run (zeta, ubar, vbar, u, v, t, ru, rv, Akv, Akt, W, rho, Zt_avg1, Hz)."""
+    import ctypes as C
+    L = rb.lib.Lib.get().L
+    L.roms_b200_restart_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.roms_b200_restart_finish.argtypes = [C.c_void_p]
+    d = rb.Driver(rb.default_config(app, *grid))
+    d.run(5)
+    ids = (C.c_int * 32)()
+    n = L.roms_b200_restart_fields(d.ctx.h, ids, 32)
+    names = [rb.FIELD_NAMES[ids[q]] for q in range(n)]
+    assert {"zeta", "rzeta", "ubar", "rubar", "vbar", "rvbar", "u", "ru", "v", "rv", "t", "rho", "Akv", "Akt"} <= set(names)
+    views = d.ctx.snapshot_begin(names)
+    st, tm = d.ctx.get_stepping()
+    d.run(4)
+    d.ctx.snapshot_end()
+    snap = {nm: views[nm].copy() for nm in names}
+    check = ("zeta", "ubar", "vbar", "u", "v", "t", "ru", "rv", "Akv", "Akt", "W", "rho", "Zt_avg1", "Hz")
+    ref = {nm: d.ctx.download(nm) for nm in check}
+    d2 = rb.Driver(rb.default_config(app, *grid))
+    for nm in names:
+        d2.ctx.upload(nm, snap[nm])
+    d2.ctx.set_stepping(st["iic"], st["ntfirst"], st["nstp"], st["nnew"], st["nrhs"], st["indx1"], tm)
+    assert L.roms_b200_restart_finish(d2.ctx.h) == 0
+    d2.run(4)
+    bad = [nm for nm in check if not np.array_equal(ref[nm], d2.ctx.download(nm))]
+    assert not bad, bad
+    d.finalize(); d2.finalize()
+
+
 def test_two_stream_step_is_bit_identical_to_the_serial_order():
     """roms_b200_main3d runs independent branches of a step on a second stream (tracer branch beside the momentum branch and the
     fast loop; mass fluxes / omega beside density / surface fluxes / KPP).  A missing dependency would show up as a difference
