@@ -351,14 +351,17 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
     // ======================= producers: advection, level-parallel =======================
     const int p = warp - 1 - NC, h = lane >> 4, col = lane & 15;
     double Cj[KP][NTR], FEs[KP][NTR];           // eta-direction carry per (batch, tracer): curv(j), FE(j) (south face of the next row)
+    // A thread owns KP CONSECUTIVE levels of its column (half-warp h of producer warp p: levels KP*(2p+h)+1 ...), one per batch m,
+    // so the vertical stencil walks through registers: t(3) at k-1, k, k+1 and the flux through the lower face of level k are
+    // those of the batch before (one new t(3) level and one vertical flux per level instead of five and two).
     // per batch: level k; element offset of (level k, this column) inside one tracer of a ring row / inside a slot array / inside
     // the Huon array.  The vertical neighbours k-2..k+2 sit at fixed distances; at k <= 2 and k >= N-1 they fall outside the
     // tracer's levels (padding, the neighbouring tracer or row): those values are not used by the C4 flux at these levels.
     int kk[KP], o0[KP], so[KP], sh[KP];
 #pragma unroll
     for (int m = 0; m < KP; ++m) {
-      const int kb = 2 * (p + m * NP) + 1;
-      kk[m] = (kb <= N) ? kb + h : 0;           // 0: this warp has no such batch; N+1 (odd N): shadow of level N, not stored
+      const int kl = KP * 2 * p + m + 1;        // level of the lower half-warp in this batch (warp-uniform)
+      kk[m] = (kl <= N) ? min(KP * (2 * p + h) + m + 1, N + 1) : 0;   // 0: no such batch; N+1: shadow of level N, not stored
       const int kc = min(max(kk[m], 1), N);
       o0[m] = (kc - 1) * TW + col + 2;
       so[m] = (kc - 1) * LS + col;
@@ -438,6 +441,7 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
           { PROF_T(t_); mbar_wait(&slot_full[sl], q.ph, a.err, a.backoff); PROF_ADD(p_slot, t_); }
           PROF_T(tw_);
           double* sp = slots + sl * slotD;
+          double cA[NTR], cM1[NTR], cP1[NTR], cP2[NTR], cFC[NTR], cW = 0.0;    // t(3) at k, k-1, k+1, k+2, FC(k), W(k) of the batch before
 #pragma unroll
           for (int m = 0; m < KP; ++m) {
             if (kk[m] != 0) {
@@ -447,13 +451,16 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
             const int sm_ = so[m];
             const double hu = sp[ohu + sh[m]], hup = sp[ohu + sh[m] + 1];
             const double hvn_ = sp[ohv + sm_], hz = sp[ohz_ + sm_];
-            const double wk = sp[ow + sm_ + LS], wkm = sp[ow + sm_];    // W: level index 0..N
+            const double wk = sp[ow + sm_ + LS];                        // W: level index 0..N
+            const double wkm = (m == 0) ? sp[ow + sm_] : cW;
             double qm2[NTR], qm1[NTR], A[NTR], qp1[NTR], qp2[NTR], Bv[NTR], T2[NTR], tm2[NTR], tm1[NTR], tp1[NTR], tp2[NTR], twv[NTR];
 #pragma unroll
             for (int c = 0; c < NTR; ++c) {
               const double* pr = R0 + c * trD + o0[m];
-              qm2[c] = pr[-2]; qm1[c] = pr[-1]; A[c] = pr[0]; qp1[c] = pr[1]; qp2[c] = pr[2];
-              tm2[c] = pr[-2 * TW]; tm1[c] = pr[-TW]; tp1[c] = pr[TW]; tp2[c] = pr[2 * TW];
+              qm2[c] = pr[-2]; qm1[c] = pr[-1]; qp1[c] = pr[1]; qp2[c] = pr[2];
+              if (m == 0) { A[c] = pr[0]; tm2[c] = pr[-2 * TW]; tm1[c] = pr[-TW]; tp1[c] = pr[TW]; }
+              else { A[c] = cP1[c]; tm2[c] = cM1[c]; tm1[c] = cA[c]; tp1[c] = cP2[c]; }
+              tp2[c] = pr[2 * TW];
               Bv[c] = R1[c * trD + o0[m]]; T2[c] = R2[c * trD + o0[m]];
               twv[c] = sp[oq + c * dq_ + sm_];
             }
@@ -476,13 +483,15 @@ __global__ void __launch_bounds__(MAXT, 1) step3d_t_v8_kernel(const __grid_const
               const double FEn = hvh * (A[c] + Bv[c]) - c16 * (Cj[m][c] * hvx + c1 * hvm);
               const double x1 = cff * (FXp - FXi), x2 = cff * (FEn - FEs[m][c]), x3 = x1 + x2;
               double tv = twv[c] - x3;
-              const double FCm = vflux8(k - 1, N, tm2[c], tm1[c], A[c], tp1[c], wkm);
+              const double FCm = (m == 0) ? vflux8(k - 1, N, tm2[c], tm1[c], A[c], tp1[c], wkm) : cFC[c];
               const double FCk = vflux8(k, N, tm1[c], A[c], tp1[c], tp2[c], wk);
               const double cv = cff * (FCk - FCm);
               tv = tv - cv;
               if (valid) sp[oq + c * dq_ + sm_] = tv * ohz;
               Cj[m][c] = c1; FEs[m][c] = FEn;
+              cA[c] = A[c]; cM1[c] = tm1[c]; cP1[c] = tp1[c]; cP2[c] = tp2[c]; cFC[c] = FCk;
             }
+            cW = wk;
             if (valid) sp[ohv + sm_] = ohz;
             }
           }

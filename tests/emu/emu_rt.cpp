@@ -170,11 +170,68 @@ struct Fibers {
   }
 };
 Fibers& fibers() { static Fibers* p = new Fibers(); return *p; }
+
+// Cooperative grids (kernels with a grid-wide barrier: the persistent barotropic fast loop): EVERY thread of EVERY block is a
+// fiber of one scheduler, resumed round-robin; a block barrier waits for the threads of that block, the kernel's own grid barrier
+// (an atomic counter it spins on, yielding) for all blocks.  Each block has its own dynamic shared memory.
+struct Coop {
+  struct F { ucontext_t ctx; bool done = false; int blk = 0, tid = 0; };
+  std::vector<F> f; std::vector<char*> stacks; ucontext_t sched; int cur = -1, live = 0;
+  const std::function<void()>* body = nullptr; dim3 bdim, gdim;
+  std::vector<int> bar_count, bar_live; std::vector<long> bar_gen;
+  std::vector<std::vector<double>> smem;
+  bool active = false;
+  static constexpr size_t kStack = 96 * 1024;
+  static void entry(unsigned lo, unsigned hi) {
+    Coop* self = (Coop*)(((uintptr_t)hi << 32) | (uintptr_t)lo);
+    in_team = true;
+    (*self->body)();
+    F& me = self->f[self->cur];
+    me.done = true;
+    --self->live;
+    int& bl = self->bar_live[me.blk];
+    --bl;
+    if (bl > 0 && self->bar_count[me.blk] == bl) { self->bar_count[me.blk] = 0; ++self->bar_gen[me.blk]; }
+    swapcontext(&me.ctx, &self->sched);
+  }
+  void set_ids(const F& x) {
+    threadIdx.x = x.tid % bdim.x; threadIdx.y = (x.tid / bdim.x) % bdim.y; threadIdx.z = x.tid / (bdim.x * bdim.y);
+    blockIdx.x = x.blk % gdim.x; blockIdx.y = (x.blk / gdim.x) % gdim.y; blockIdx.z = x.blk / (gdim.x * gdim.y);
+  }
+  void run(dim3 g, dim3 b, size_t smem_bytes, const std::function<void()>& fn) {
+    const int nb = (int)(g.x * g.y * g.z), nt = (int)(b.x * b.y * b.z), n = nb * nt;
+    gdim = g; bdim = b; body = &fn; live = n; active = true;
+    bar_count.assign(nb, 0); bar_live.assign(nb, nt); bar_gen.assign(nb, 0);
+    smem.assign(nb, std::vector<double>((smem_bytes + 7) / 8 + 16, 0.0));
+    if ((int)f.size() < n) f.resize(n);
+    while ((int)stacks.size() < n) stacks.push_back((char*)malloc(kStack));
+    const uintptr_t me = (uintptr_t)this;
+    for (int w = 0; w < n; ++w) {
+      f[w].done = false; f[w].blk = w / nt; f[w].tid = w % nt;
+      getcontext(&f[w].ctx);
+      f[w].ctx.uc_stack.ss_sp = stacks[w]; f[w].ctx.uc_stack.ss_size = kStack; f[w].ctx.uc_link = &sched;
+      makecontext(&f[w].ctx, (void (*)())entry, 2, (unsigned)(me & 0xffffffffu), (unsigned)(me >> 32));
+    }
+    while (live > 0)
+      for (int w = 0; w < n; ++w) if (!f[w].done) { cur = w; set_ids(f[w]); swapcontext(&sched, &f[w].ctx); }
+    in_team = false; active = false;
+  }
+  void yield() { const int w = cur; swapcontext(&f[w].ctx, &sched); set_ids(f[w]); }
+  void barrier() {
+    const int blk = f[cur].blk; const long g = bar_gen[blk];
+    if (++bar_count[blk] == bar_live[blk]) { bar_count[blk] = 0; ++bar_gen[blk]; return; }
+    while (bar_gen[blk] == g) yield();
+  }
+  void* dyn() { return smem[f[cur].blk].data(); }
+};
+Coop& coop() { static Coop* p = new Coop(); return *p; }
 bool use_fibers() { static const bool v = !(getenv("EMU_TEAM") && !strcmp(getenv("EMU_TEAM"), "threads")); return v; }
 }  // namespace
 
-void* dyn_smem() { return g_smem.data(); }
+void* dyn_smem() { return coop().active ? coop().dyn() : (void*)g_smem.data(); }
+bool coop_supported() { return use_fibers(); }
 void barrier() {
+  if (coop().active) { coop().barrier(); return; }
   if (!in_team) { fprintf(stderr, "emu: __syncthreads() in a kernel that is not listed in kTeamKernels (tests/emu/emu_rt.cpp)\n"); abort(); }
   if (use_fibers()) fibers().barrier(); else team().barrier();
 }
@@ -194,7 +251,7 @@ double warp_shfl(double v, int src) {
   const unsigned lin = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
   return use_fibers() ? fibers().warp_shfl((int)(lin / 32), (int)(lin & 31), v, src) : team().warp_shfl((int)(lin / 32), (int)(lin & 31), v, src);
 }
-void yield() { if (in_team && use_fibers()) fibers().yield(); else std::this_thread::yield(); }
+void yield() { if (coop().active) coop().yield(); else if (in_team && use_fibers()) fibers().yield(); else std::this_thread::yield(); }
 std::mutex g_kernel_lock;          // several ranks (one host thread each, see the multi-tile emulation below): one kernel at a time
 void run_grid(dim3 g, dim3 b, size_t smem, const char* kernel, const std::function<void()>& body) {
   std::lock_guard<std::mutex> kl(g_kernel_lock);
@@ -209,6 +266,12 @@ void run_grid(dim3 g, dim3 b, size_t smem, const char* kernel, const std::functi
       body();
     }
   }
+}
+void run_grid_coop(dim3 g, dim3 b, size_t smem, const char* kernel, const std::function<void()>& body) {
+  std::lock_guard<std::mutex> kl(g_kernel_lock);
+  if (!use_fibers()) { fprintf(stderr, "emu: cooperative grid %s needs the fiber scheduler\n", kernel); abort(); }
+  gridDim = g; blockDim = b;
+  coop().run(g, b, smem, body);
 }
 }  // namespace emu
 

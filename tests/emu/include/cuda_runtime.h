@@ -35,6 +35,8 @@ extern dim3 blockDim, gridDim;
 
 namespace emu {
 void run_grid(dim3 g, dim3 b, size_t smem, const char* kernel, const std::function<void()>& body);
+void run_grid_coop(dim3 g, dim3 b, size_t smem, const char* kernel, const std::function<void()>& body);   // all blocks at once
+bool coop_supported();
 void barrier();
 void* dyn_smem();
 void named_barrier(int id, int nthreads, bool wait);     // PTX bar.sync / bar.arrive id, nthreads
@@ -51,6 +53,8 @@ inline void __syncwarp() { emu::sync_warp(); }              // rendezvous of the
 inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline bool __any_sync(unsigned, bool pred) { return emu::warp_any(pred); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline int min(int a, int b) { return a < b ? a : b; }

@@ -18,8 +18,18 @@ phases = [("set_massflux", (nrhs,)), ("rho_eos", (nrhs,)), ("bulk_flux", (nrhs,)
           ("omega", ()), ("wvelocity", (nstp,)), ("set_zeta", ()), ("pre_step3d", (nrhs, nstp, nnew, iic, ntf)), ("prsgrd", (nrhs,)),
           ("t3dmix2", (nrhs, nstp, nnew)), ("rhs3d_tile", (nrhs,)), ("uv3dmix2", (nrhs, nnew)),
           ("set_depth", ()), ("step3d_uv", (nrhs, nstp, nnew, iic, ntf)), ("step3d_t", (nrhs, nstp, nnew))]
+# algorithmic doubles per interior cell per call: every 3-D array read once and written once (column "min")
+ALG = {"set_massflux": 5, "rho_eos": 8, "lmd_vmix": 14, "omega": 4, "wvelocity": 6, "pre_step3d": 27, "prsgrd": 6, "t3dmix2": 8,
+       "rhs3d_tile": 10, "uv3dmix2": 8, "set_depth": 3, "step3d_uv": 12, "step3d_t": 12}
+try:
+    import json
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    PEAK = 6650.0
+cells = Lm * Mm * N
 tot = 0.0
-print("%dx%dx%d, %d reps each, warm L2" % (Lm, Mm, N, reps))
+print("%dx%dx%d, %d reps each (%s); algorithmic GB/s = doubles/cell x 8 B x cells / time, fraction of %.0f GB/s"
+      % (Lm, Mm, N, reps, "warm L2" if cells < 4e6 else "3-D state >> L2", PEAK))
 for name, args in phases:
     ctx.call(name, *args); ctx.sync()
     d.timer_start()
@@ -27,7 +37,11 @@ for name, args in phases:
         ctx.call(name, *args)
     ms = d.timer_stop() / reps
     tot += ms * (2 if name == "omega" else 1)
-    print("  %-14s %8.1f us" % (name, 1e3 * ms))
+    if name in ALG:
+        gbs = ALG[name] * 8.0 * cells / (ms * 1e-3) / 1e9
+        print("  %-14s %9.1f us   %2d doubles/cell  %7.0f GB/s  %.2f" % (name, 1e3 * ms, ALG[name], gbs, gbs / PEAK))
+    else:
+        print("  %-14s %9.1f us" % (name, 1e3 * ms))
 ctx.diag(nstp)
 d.timer_start()
 for _ in range(reps):
