@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(128) kpp_spline_kernel(const Dev D, Box bx, in
 }
 
 __global__ void __launch_bounds__(256) kpp_levels_kernel(const Dev D, Box bx, int nstp, KppC kc) {
-  IJ_FROM_BOX(bx);
-  const int N = D.b.N, k = blockIdx.z; const size_t vol = D.nij * (size_t)(N + 1);
+  IJZ_FROM_BOX(bx, D.b.N + 1);
+  const int N = D.b.N, k = zlev; const size_t vol = D.nij * (size_t)(N + 1);
   const double gorho0 = D.p.g / D.p.rho0;
   V3 Hz = v3(D, FID(Hz)), z_w = v3(D, FID(z_w)), pden = v3(D, FID(pden)), bvf = v3(D, FID(bvf));
   V3 u = v3l(D, FID(u), nstp), v = v3l(D, FID(v), nstp);

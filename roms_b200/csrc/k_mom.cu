@@ -254,8 +254,8 @@ __device__ __forceinline__ double m_VFx(const MQ& Q, int i, int j, int k) { retu
 // to rufrc/rvfrc (uv3dmix2_s.h:296-297,326-327) are parked in scratch volumes and summed in the reference's order
 // (acc = acc + c1 + c2, k = 1..N) by uv3dmix2_sum_kernel, one thread per column and component.
 __global__ void __launch_bounds__(256) uv3dmix2_kernel(const Dev D, Box bx, int nrhs, int nnew, double* scratch) {
-  IJ_FROM_BOX(bx);
-  const roms_b200_bounds& b = D.b; const int N = b.N, k = 1 + blockIdx.z % N, comp = blockIdx.z / N; const double dt = D.p.dt;
+  IJZ_FROM_BOX(bx, D.b.N);
+  const roms_b200_bounds& b = D.b; const int N = b.N, k = 1 + zlev, comp = zcomp; const double dt = D.p.dt;
   MQ Q{v3l(D, FID(u), nrhs), v3l(D, FID(v), nrhs), v3(D, FID(Hz)), v2(D, FID(pm)), v2(D, FID(pn)), v2(D, FID(pmon_r)), v2(D, FID(pnom_r)),
        v2(D, FID(pmon_p)), v2(D, FID(pnom_p)), v2(D, FID(om_r)), v2(D, FID(on_r)), v2(D, FID(om_p)), v2(D, FID(on_p)), v2(D, FID(visc2_r)), v2(D, FID(visc2_p))};
   const size_t vol = D.nij * (size_t)(N + 1);

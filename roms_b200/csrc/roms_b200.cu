@@ -123,7 +123,7 @@ int roms_b200_destroy(roms_b200_ctx* c) {
   cudaFree((void*)c->D.sc_r); cudaFree((void*)c->D.w1); cudaFree(c->D.P); cudaFree(c->D.scratch2); cudaFree(c->D.swdk); cudaFree(c->D.dtdz); cudaFree(c->D.kpp4); cudaFree(c->D.red); cudaFree(c->D.ksbl); cudaFree(c->D.err);
   if (c->h_red) cudaFreeHost(c->h_red);
   if (c->snap_stream) { cudaStreamSynchronize(c->snap_stream); cudaStreamDestroy(c->snap_stream); cudaEventDestroy(c->snap_ready); cudaEventDestroy(c->snap_done); }
-  cudaFree(c->snap_buf);
+  cudaFree(c->snap_buf); cudaFree(c->s2p_done);
   roms_b200_comm_destroy(c);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -258,8 +258,8 @@ int roms_b200_fill(roms_b200_ctx* c, int f, double value) {
 // main3d.F:810-918: LF-AM3 fast loop.  The launch sequence depends only on
 // (indx1 at entry, which of the three AB start-up forms the first predictor
 // uses), so it is captured once per key and replayed as a CUDA graph.
-static int fast_loop_launch(roms_b200_ctx* c, int nstp, int nnew, int iic, int ntfirst, int* indx1_io) {
-  const int nfast = c->D.p.nfast;
+struct FastPhase { int krhs, kstp, knew, iif, pred; };
+static void fast_loop_sequence(int nfast, int* indx1_io, std::vector<FastPhase>& seq) {
   int indx1 = *indx1_io, kstp = 1, knew = 1, krhs = 1, iif = 1; bool PRED = false;
   for (int my_iif = 1; my_iif <= nfast + 1; ++my_iif) {
     const int next_indx1 = 3 - indx1;
@@ -268,30 +268,46 @@ static int fast_loop_launch(roms_b200_ctx* c, int nstp, int nnew, int iic, int n
       kstp = (iif == 1) ? indx1 : 3 - indx1;
       knew = 3; krhs = indx1;
     }
-    if (my_iif <= nfast + 1) {
-      k_step2d(c, krhs, kstp, knew, nstp, nnew, iif, 1, iic, ntfirst);
-      if (c->comm) {      // mp_exchange2d calls of step2d_LF_AM3.h:842,1013,1068,3043 aggregated into one message
-        if (iif == nfast + 1) { const XF x[3] = {xf2(FID(Zt_avg1)), xf2(FID(DU_avg1)), xf2(FID(DV_avg1))}; if (xchg(c, x, 3)) return 1; }
-        else if (c->deep) { }            // deep-halo predictor (k_step2d): its results exist on the 3 halo points the corrector reads
-        else { const XF x[4] = {xf2(FID(zeta), knew), xf2(FID(ubar), knew), xf2(FID(vbar), knew), xf2(FID(rzeta), krhs)}; if (xchg(c, x, 4)) return 1; }
-        if (k_step2d_join(c)) return 1;
-      }
-    }
+    if (my_iif <= nfast + 1) seq.push_back(FastPhase{krhs, kstp, knew, iif, 1});
     if (PRED) {
       PRED = false; knew = next_indx1; kstp = 3 - knew; krhs = 3;
       if (iif < nfast + 1) indx1 = next_indx1;
     }
-    if (iif < nfast + 1) {
-      k_step2d(c, krhs, kstp, knew, nstp, nnew, iif, 0, iic, ntfirst);
-      if (c->comm) { const XF x[3] = {xf2(FID(zeta), knew), xf2(FID(ubar), knew), xf2(FID(vbar), knew)}; if (xchg(c, x, 3)) return 1; if (k_step2d_join(c)) return 1; }
-    }
+    if (iif < nfast + 1) seq.push_back(FastPhase{krhs, kstp, knew, iif, 0});
   }
   *indx1_io = indx1;
+}
+static int fast_loop_launch(roms_b200_ctx* c, int nstp, int nnew, int iic, int ntfirst, int* indx1_io) {
+  const int nfast = c->D.p.nfast;
+  std::vector<FastPhase> seq;
+  fast_loop_sequence(nfast, indx1_io, seq);
+  for (const FastPhase& f : seq) {
+    k_step2d(c, f.krhs, f.kstp, f.knew, nstp, nnew, f.iif, f.pred, iic, ntfirst);
+    if (!c->comm) continue;
+    if (f.pred) {      // mp_exchange2d calls of step2d_LF_AM3.h:842,1013,1068,3043 aggregated into one message
+      if (f.iif == nfast + 1) { const XF x[3] = {xf2(FID(Zt_avg1)), xf2(FID(DU_avg1)), xf2(FID(DV_avg1))}; if (xchg(c, x, 3)) return 1; }
+      else if (c->deep) { }            // deep-halo predictor (k_step2d): its results exist on the 3 halo points the corrector reads
+      else { const XF x[4] = {xf2(FID(zeta), f.knew), xf2(FID(ubar), f.knew), xf2(FID(vbar), f.knew), xf2(FID(rzeta), f.krhs)}; if (xchg(c, x, 4)) return 1; }
+    } else { const XF x[3] = {xf2(FID(zeta), f.knew), xf2(FID(ubar), f.knew), xf2(FID(vbar), f.knew)}; if (xchg(c, x, 3)) return 1; }
+    if (k_step2d_join(c)) return 1;
+  }
   return 0;
+}
+// single tile: the whole loop as one persistent kernel (k_step2d.cu) when every block tile can be resident at once
+static int fast_loop_persistent(roms_b200_ctx* c, int nstp, int nnew, int iic, int ntfirst, int* indx1_io) {
+  if (c->comm) return 2;
+  std::vector<FastPhase> seq; int ix = *indx1_io;
+  fast_loop_sequence(c->D.p.nfast, &ix, seq);
+  std::vector<int> ph(seq.size());
+  for (size_t q = 0; q < seq.size(); ++q) ph[q] = seq[q].krhs | seq[q].kstp << 2 | seq[q].knew << 4 | seq[q].pred << 6 | seq[q].iif << 8;
+  const int rc = k_step2d_persist(c, ph.data(), (int)ph.size(), nstp, nnew, iic, ntfirst);
+  if (rc == 0) *indx1_io = ix;
+  return rc;
 }
 int roms_b200_step2d_loop(roms_b200_ctx* c, int nstp, int nnew, int iic, int ntfirst, int* indx1) {
   ENTER(c);
   const int mode = (iic == ntfirst) ? 0 : (iic == ntfirst + 1 ? 1 : 2);
+  { const int rc = fast_loop_persistent(c, nstp, nnew, iic, ntfirst, indx1); if (rc == 0) { LEAVE(); } if (rc != 2) return 1; }
   if (!c->use_graph) { if (fast_loop_launch(c, nstp, nnew, iic, ntfirst, indx1)) return 1; LEAVE(); }
   // the launch sequence is a pure function of (indx1 at entry, nstp, AB start-up mode)
   const int key = ((*indx1 - 1) & 1) * 6 + ((nstp - 1) & 1) * 3 + mode;

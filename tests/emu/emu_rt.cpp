@@ -17,7 +17,7 @@ double emu_now_ms() { return std::chrono::duration<double, std::milli>(std::chro
 namespace emu {
 namespace {
 // kernels that call __syncthreads(): their blocks run as teams of real threads; every other kernel runs its threads in a loop
-const char* kTeamKernels[] = {"step2d_kernel", "diag_cols_kernel", "diag_sum_kernel", "step3d_t_v6_kernel", "step3d_t_v8_kernel", "step3d_t_v4_kernel"};
+const char* kTeamKernels[] = {"step2d_kernel", "diag_cols_kernel", "diag_sum_kernel", "step3d_t_v6_kernel", "step3d_t_v8_kernel", "step3d_t_v4_kernel", "t3dmix2_geo_roll_kernel", "pre_step3d_t_roll_kernel"};
 bool needs_team(const char* k) { for (const char* t : kTeamKernels) if (strstr(k, t)) return true; return false; }
 std::vector<double> g_smem(64 * 1024, 0.0);          // dynamic shared memory of the running block
 thread_local bool in_team = false;
@@ -212,8 +212,15 @@ struct Coop {
       f[w].ctx.uc_stack.ss_sp = stacks[w]; f[w].ctx.uc_stack.ss_size = kStack; f[w].ctx.uc_link = &sched;
       makecontext(&f[w].ctx, (void (*)())entry, 2, (unsigned)(me & 0xffffffffu), (unsigned)(me >> 32));
     }
-    while (live > 0)
-      for (int w = 0; w < n; ++w) if (!f[w].done) { cur = w; set_ids(f[w]); swapcontext(&sched, &f[w].ctx); }
+    // EMU_SCHED_SEED=s: in every pass a pseudo-random half of the BLOCKS is left out, so blocks drift apart by whole sub-steps
+    // unless the kernel's own inter-block synchronisation holds them together (round-robin would keep them in lockstep)
+    static const char* seed_env = getenv("EMU_SCHED_SEED");
+    static unsigned long long rng = seed_env ? (unsigned long long)atoll(seed_env) * 2654435761ull + 88172645463325252ull : 0;
+    std::vector<char> on(nb, 1);
+    while (live > 0) {
+      if (seed_env) for (int q = 0; q < nb; ++q) { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; on[q] = (char)((rng >> 20) & 1); }
+      for (int w = 0; w < n; ++w) if (!f[w].done && on[f[w].blk]) { cur = w; set_ids(f[w]); swapcontext(&sched, &f[w].ctx); }
+    }
     in_team = false; active = false;
   }
   void yield() { const int w = cur; swapcontext(&f[w].ctx, &sched); set_ids(f[w]); }

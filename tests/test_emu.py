@@ -66,6 +66,31 @@ def test_step3d_t_synchronisation_under_random_schedules(emu_lib, seed, s3t, ext
     assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("case,seed", [((1, 70, 9, 30, 2), 5), ((1, 33, 5, 9, 2), 11), ((0, 24, 10, 8, 3), 12), ((1, 130, 9, 8, 2), 7)])
+def test_persistent_fast_loop_neighbour_flags_under_random_block_schedules(emu_lib, case, seed):
+    """ROMS_B200_S2_PERSIST=1: the 2*nfast+1 sub-steps of a baroclinic step in ONE kernel, every block waiting for the sub-step
+    counters of the blocks of the adjacent tiles (k_step2d.cu).  All blocks run as fibers of one scheduler that leaves a random
+    half of the blocks out in every pass, so blocks drift apart by whole sub-steps unless the flags hold them together; 33 wide:
+    the last tile of a periodic row is narrower than the stencil reach (neighbourhood of two tiles).  Bit-identical to the oracle.
+    Negative control: with the waits skipped (EMU_S2P_NOWAIT) the same schedule must fail."""
+    args = [sys.executable, os.path.join(HERE, "emu_worker.py")] + [str(x) for x in case] + ["v8"]
+    env = dict(os.environ, EMU_SM_COUNT="148", EMU_SCHED_SEED=str(seed), ROMS_B200_S2_PERSIST="1")
+    r = subprocess.run(args, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    if seed == 5:
+        r = subprocess.run(args, capture_output=True, text=True, timeout=900, env=dict(env, EMU_S2P_NOWAIT="1"))
+        assert r.returncode != 0 and "step2d_loop" in r.stderr, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("case", [(1, 70, 19, 30, 2), (0, 24, 10, 8, 2)])
+def test_level_major_block_order_is_a_pure_renumbering(emu_lib, case):
+    """common.cuh level_major(): the level-parallel kernels renumber their blocks (bands of tiles, level by level) on grids of more
+    than LM_G block tiles; EMU_LM_G=3 makes the small test grids take that path (bands of 3 tiles, a ragged last band)."""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py")] + [str(x) for x in case] + ["v8"],
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, EMU_SM_COUNT="148", EMU_LM_G="3"))
+    assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_emulated_rho_eos_matches_the_reference_check_values(emu_lib):
     r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "eos"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "EMU-EOS-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
