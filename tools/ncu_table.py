@@ -1,5 +1,5 @@
 """tools/ncu_table.py REP.ncu-rep [...] -- one line per report: duration, DRAM bytes, throughputs, registers, occupancy, cache hit
-rates, top stall reason.  Reads the reports with `ncu -i ... --page raw --csv` (run where ncu is installed; no GPU needed)."""
+rates, top stall reasons (warps stalled per issued instruction).  Reads the reports with `ncu -i ... --page raw --csv` (run where ncu is installed; no GPU needed)."""
 import csv, io, subprocess, sys
 
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
@@ -19,12 +19,13 @@ def row(path):
         if n not in d or d[n][0] in ("", "n/a"):
             return float("nan")
         return float(d[n][0].replace(",", "")) * SCALE.get(d[n][1], 1.0)
-    stalls = sorted(((float(d[k][0].replace(",", "")), k.split("issue_stalled_")[1].split("_per_warp")[0]) for k in d
-                     if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_warp_active.pct") and d[k][0] not in ("", "n/a")), reverse=True)[:2]
+    stalls = sorted(((float(d[k][0].replace(",", "")), k.split("issue_stalled_")[1].split("_per_issue")[0]) for k in d
+                     if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio") and "not_issued" not in k
+                     and d[k][0] not in ("", "n/a")), reverse=True)[:3]
     name = d.get("Kernel Name", ("?", ""))[0].split("(")[0]
     print("%-24s %8.1f us  dram rd %7.1f wr %7.1f MB  dram %5.1f%%  sm %5.1f%%  fp64 %5.1f%%  issue %5.1f%%  regs %3d  occ %5.1f%%  L1 %5.1f  L2 %5.1f  stalls: %s"
           % (name, g(WANT[0]), g(WANT[1]), g(WANT[2]), g(WANT[8]), g(WANT[7]), g(WANT[9]), g(WANT[10]), int(g(WANT[3])), g(WANT[4]), g(WANT[5]), g(WANT[6]),
-             ", ".join("%s %.0f%%" % (n, x) for x, n in stalls)))
+             ", ".join("%s %.1f" % (n, x) for x, n in stalls)))
 
 
 for p in sys.argv[1:]:
