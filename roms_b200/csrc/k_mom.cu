@@ -2,6 +2,7 @@
 // right-hand side (rhs3d_tile), harmonic viscosity (uv3dmix2_s) and the momentum
 // corrector (step3d_uv).  Column-marching threads, i fastest (coalesced rows).
 #include "common.cuh"
+#include <algorithm>
 
 // ---- prsgrd32_tile, prsgrd32.h:238-433 -----------------------------------------
 // pass 1: column pressure P(i,j,k) with harmonic-mean spline slopes dR,dZ.  Only the running sum over k is a recurrence:
@@ -298,11 +299,164 @@ __global__ void __launch_bounds__(128) uv3dmix2_sum_kernel(const Dev D, Box bx, 
   }
   frc(i, j) = acc;
 }
+// ---- uv3dmix2, production form: a block marches a 32 x 8 tile up a chunk of levels (the recipe of k_tracer.cu) ----------------
+// Per level the rho-point strain term (m_cffr) and the psi-point one (m_cffp) are evaluated ONCE per point from the u, v, Hz
+// planes of the level (tile + one ring of halo, staged through shared memory, loaded into registers one level ahead), scaled
+// into UFx, VFe (rho points) and UFe, VFx (psi points) in shared memory; the u and v updates of a point read them there.  The
+// 2-D coefficients of a point (metric sums and products) sit in shared memory for the whole march instead of being re-read per
+// level.  With one chunk (the whole column) the two terms every level adds to rufrc/rvfrc are accumulated in registers in the
+// reference's order and the scratch volumes and the sum kernel disappear; with several chunks they are parked as before.
+constexpr int M2_TX = 32, M2_TY = 8, M2_NT = M2_TX * M2_TY;
+constexpr int M2_RW = M2_TX + 2, M2_NR = M2_RW * (M2_TY + 2);        // raw planes u, v, Hz: i in [I0-1, I0+32], j in [J0-1, J0+8]
+constexpr int M2_CW = M2_TX + 1, M2_NC = M2_CW * (M2_TY + 1);        // rho cells: i in [I0-1, I0+31], j in [J0-1, J0+7]; psi cells: i in [I0, I0+32], j in [J0, J0+8]
+constexpr int M2_NQ = (M2_NR + M2_NT - 1) / M2_NT, M2_CQ = (M2_NC + M2_NT - 1) / M2_NT;
+constexpr int M2_DSLOT = 4 * M2_NC;                                   // UFx, VFe, UFe, VFx
+constexpr int M2_NCOEF = 8;                                           // per cell: pmon, pnom, 4 metric sums, 2 scale factors
+constexpr size_t M2_SMEM = (3 * M2_DSLOT + 2 * 3 * M2_NR + 2 * M2_NCOEF * M2_NC) * sizeof(double);
+template <bool FULL>
+__global__ void __launch_bounds__(M2_NT, 2) uv3dmix2_roll_kernel(const Dev D, Box bx, int nrhs, int nnew, int nch, double* scratch) {
+  extern __shared__ double m2sm[];
+  double* const smD = m2sm; double* const smR = smD + 3 * M2_DSLOT; double* const cR = smR + 2 * 3 * M2_NR; double* const cP = cR + M2_NCOEF * M2_NC;
+  const roms_b200_bounds& b = D.b; const int N = b.N; const double dt = D.p.dt;
+  const int ch = (int)blockIdx.z, per = (N + nch - 1) / nch, k0 = 1 + per * ch, k1 = min(k0 + per - 1, N);
+  if (k0 > N) return;
+  const int I0 = bx.i0 + blockIdx.x * M2_TX, J0 = bx.j0 + blockIdx.y * M2_TY;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * M2_TX + tx, i = I0 + tx, j = J0 + ty;
+  V3 u = v3l(D, FID(u), nrhs), v = v3l(D, FID(v), nrhs), Hz = v3(D, FID(Hz)), un = v3l(D, FID(u), nnew), vn = v3l(D, FID(v), nnew);
+  V2 pm = v2(D, FID(pm)), pn = v2(D, FID(pn));
+  auto DS = [&](int L) { return smD + (L % 3) * M2_DSLOT; };
+  auto RAW = [&](int L) { return smR + (L & 1) * 3 * M2_NR; };           // u; v at + M2_NR; Hz at + 2*M2_NR
+  // ---- cells of this thread; coefficients of the rho and psi cells into shared memory (once)
+  int ri[M2_NQ], rj[M2_NQ]; bool ro[M2_NQ];
+#pragma unroll
+  for (int n = 0; n < M2_NQ; ++n) {
+    const int q = tid + n * M2_NT;
+    ri[n] = I0 - 1 + q % M2_RW; rj[n] = J0 - 1 + q / M2_RW;
+    ro[n] = q < M2_NR && ri[n] <= bx.i1 + 1 && rj[n] <= bx.j1 + 1 && ri[n] >= b.LBi && ri[n] <= b.UBi && rj[n] >= b.LBj && rj[n] <= b.UBj;
+  }
+  bool co_r[M2_CQ], co_p[M2_CQ]; int cq_r[M2_CQ], cq_p[M2_CQ];             // raw-plane offset of the cell's (i,j)
+  {
+    V2 pmon_r = v2(D, FID(pmon_r)), pnom_r = v2(D, FID(pnom_r)), pmon_p = v2(D, FID(pmon_p)), pnom_p = v2(D, FID(pnom_p));
+    V2 om_r = v2(D, FID(om_r)), on_r = v2(D, FID(on_r)), om_p = v2(D, FID(om_p)), on_p = v2(D, FID(on_p)), visc2_r = v2(D, FID(visc2_r)), visc2_p = v2(D, FID(visc2_p));
+#pragma unroll
+    for (int n = 0; n < M2_CQ; ++n) {
+      const int q = tid + n * M2_NT, ci = q % M2_CW, cj = q / M2_CW;
+      // rho cell (I0-1+ci, J0-1+cj): needed for i in [Istr-1, Iend], j in [Jstr-1, Jend]
+      { const int ii = I0 - 1 + ci, jj = J0 - 1 + cj;
+        co_r[n] = q < M2_NC && ii <= bx.i1 && jj <= bx.j1 && ii - 1 >= b.LBi && jj - 1 >= b.LBj; cq_r[n] = ci + M2_RW * cj;   // (a row beyond a closed wall is never used)
+        if (co_r[n]) {
+          double* c = cR + q;
+          c[0 * M2_NC] = pmon_r(ii, jj); c[1 * M2_NC] = pnom_r(ii, jj);
+          c[2 * M2_NC] = pn(ii, jj) + pn(ii + 1, jj); c[3 * M2_NC] = pn(ii - 1, jj) + pn(ii, jj);
+          c[4 * M2_NC] = pm(ii, jj) + pm(ii, jj + 1); c[5 * M2_NC] = pm(ii, jj - 1) + pm(ii, jj);
+          c[6 * M2_NC] = on_r(ii, jj) * on_r(ii, jj) * visc2_r(ii, jj); c[7 * M2_NC] = om_r(ii, jj) * om_r(ii, jj) * visc2_r(ii, jj);
+        } }
+      // psi cell (I0+ci, J0+cj): needed for i in [Istr, Iend+1], j in [Jstr, Jend+1]
+      { const int ii = I0 + ci, jj = J0 + cj;
+        co_p[n] = q < M2_NC && ii <= bx.i1 + 1 && jj <= bx.j1 + 1; cq_p[n] = (ci + 1) + M2_RW * (cj + 1);
+        if (co_p[n]) {
+          double* c = cP + q;
+          c[0 * M2_NC] = pmon_p(ii, jj); c[1 * M2_NC] = pnom_p(ii, jj);
+          c[2 * M2_NC] = pn(ii, jj - 1) + pn(ii, jj); c[3 * M2_NC] = pn(ii - 1, jj - 1) + pn(ii - 1, jj);
+          c[4 * M2_NC] = pm(ii - 1, jj) + pm(ii, jj); c[5 * M2_NC] = pm(ii - 1, jj - 1) + pm(ii, jj - 1);
+          c[6 * M2_NC] = om_p(ii, jj) * om_p(ii, jj) * visc2_p(ii, jj); c[7 * M2_NC] = on_p(ii, jj) * on_p(ii, jj) * visc2_p(ii, jj);
+        } }
+    }
+  }
+  double ru_[M2_NQ], rv_[M2_NQ], rh_[M2_NQ];
+  auto loadR = [&](int L) {
+#pragma unroll
+    for (int n = 0; n < M2_NQ; ++n) {
+      ru_[n] = 0.0; rv_[n] = 0.0; rh_[n] = 0.0;
+      if (ro[n] && L >= 1 && L <= N) { ru_[n] = u(ri[n], rj[n], L); rv_[n] = v(ri[n], rj[n], L); rh_[n] = Hz(ri[n], rj[n], L); }
+    }
+  };
+  auto commitR = [&](int L) {
+    double* R = RAW(L);
+#pragma unroll
+    for (int n = 0; n < M2_NQ; ++n) { const int q = tid + n * M2_NT; if (q < M2_NR) { R[q] = ru_[n]; R[M2_NR + q] = rv_[n]; R[2 * M2_NR + q] = rh_[n]; } }
+  };
+  auto derive = [&](int L) {                        // m_cffr / m_cffp of level L and the four scaled fluxes
+    const double* U = RAW(L); const double* V = U + M2_NR; const double* H = V + M2_NR; double* F = DS(L);
+#pragma unroll
+    for (int n = 0; n < M2_CQ; ++n) {
+      const int q = tid + n * M2_NT;
+      if (co_r[n]) {
+        const double* c = cR + q; const int r = cq_r[n];
+        const double cffr = H[r] * 0.5 * (c[0] * (c[2 * M2_NC] * U[r + 1] - c[3 * M2_NC] * U[r]) - c[M2_NC] * (c[4 * M2_NC] * V[r + M2_RW] - c[5 * M2_NC] * V[r]));
+        F[q] = c[6 * M2_NC] * cffr; F[M2_NC + q] = c[7 * M2_NC] * cffr;
+      }
+      if (co_p[n]) {
+        const double* c = cP + q; const int r = cq_p[n];
+        const double cffp = 0.125 * (H[r - 1] + H[r] + H[r - 1 - M2_RW] + H[r - M2_RW]) *
+                            (c[0] * (c[2 * M2_NC] * V[r] - c[3 * M2_NC] * V[r - 1]) + c[M2_NC] * (c[4 * M2_NC] * U[r] - c[5 * M2_NC] * U[r - M2_RW]));
+        F[2 * M2_NC + q] = c[6 * M2_NC] * cffp; F[3 * M2_NC + q] = c[7 * M2_NC] * cffp;
+      }
+    }
+  };
+  // ---- this thread's u point and v point
+  const bool doU = (i <= bx.i1 && j <= bx.j1) && (i >= b.IstrU && i <= b.Iend && j >= b.Jstr && j <= b.Jend);
+  const bool doV = (i <= bx.i1 && j <= bx.j1) && (i >= b.Istr && i <= b.Iend && j >= b.JstrV && j <= b.Jend);
+  double cffu = 0.0, pnu = 0.0, pmu = 0.0, cffv = 0.0, pnv = 0.0, pmv = 0.0, accu = 0.0, accv = 0.0;
+  if (doU) { pnu = pn(i - 1, j) + pn(i, j); pmu = pm(i - 1, j) + pm(i, j); cffu = dt * 0.25 * pmu * pnu; if (FULL) accu = v2(D, FID(rufrc))(i, j); }
+  if (doV) { pnv = pn(i, j - 1) + pn(i, j); pmv = pm(i, j - 1) + pm(i, j); cffv = dt * 0.25 * (pm(i, j) + pm(i, j - 1)) * (pn(i, j) + pn(i, j - 1)); if (FULL) accv = v2(D, FID(rvfrc))(i, j); }
+  const size_t vol = D.nij * (size_t)(N + 1);
+  V3 S1u{scratch, b.LBi, D.ni, b.LBj, D.nj, 0}, S2u{scratch + vol, b.LBi, D.ni, b.LBj, D.nj, 0}, S1v{scratch + 2 * vol, b.LBi, D.ni, b.LBj, D.nj, 0}, S2v{scratch + 3 * vol, b.LBi, D.ni, b.LBj, D.nj, 0};
+  const int lr = (tx + 1) + M2_CW * (ty + 1), lp = tx + M2_CW * ty;     // rho cell (i,j) and psi cell (i,j) of this thread
+  // ---- prologue
+  loadR(k0); commitR(k0);
+  loadR(k0 + 1);
+  double unn = doU ? un(i, j, k0) : 0.0, vnn = doV ? vn(i, j, k0) : 0.0;
+  __syncthreads();                                  // coefficients and raw[k0] visible
+  derive(k0);
+  for (int k = k0; k <= k1; ++k) {
+    commitR(k + 1);
+    loadR(k + 2);
+    const double unk = unn, vnk = vnn;
+    if (k + 1 <= k1) { if (doU) unn = un(i, j, k + 1); if (doV) vnn = vn(i, j, k + 1); }
+    __syncthreads();                                // derived[k] and raw[k+1] visible; everybody is done with derived[k-1] ... raw[k]
+    if (k + 1 <= k1) derive(k + 1);
+    const double* F = DS(k);
+    if (doU) {
+      const double c1 = 0.5 * pnu * (F[lr] - F[lr - 1]);                                        // UFx(i,j) - UFx(i-1,j)
+      const double c2 = 0.5 * pmu * (F[2 * M2_NC + lp + M2_CW] - F[2 * M2_NC + lp]);           // UFe(i,j+1) - UFe(i,j)
+      const double c3 = cffu * (c1 + c2);
+      if (FULL) accu = accu + c1 + c2; else { S1u(i, j, k) = c1; S2u(i, j, k) = c2; }
+      un(i, j, k) = unk + c3;
+    }
+    if (doV) {
+      const double c1 = 0.5 * pnv * (F[3 * M2_NC + lp + 1] - F[3 * M2_NC + lp]);               // VFx(i+1,j) - VFx(i,j)
+      const double c2 = 0.5 * pmv * (F[M2_NC + lr] - F[M2_NC + lr - M2_CW]);                   // VFe(i,j) - VFe(i,j-1)
+      const double c3 = cffv * (c1 - c2);
+      if (FULL) accv = accv + c1 - c2; else { S1v(i, j, k) = c1; S2v(i, j, k) = c2; }
+      vn(i, j, k) = vnk + c3;
+    }
+  }
+  if (FULL) { if (doU) v2(D, FID(rufrc))(i, j) = accu; if (doV) v2(D, FID(rvfrc))(i, j) = accv; }
+}
 int k_uv3dmix2(roms_b200_ctx* c, int nrhs, int nnew) {
   const roms_b200_bounds& b = c->D.b;
   if (!c->D.kpp4) return 1;
-  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = 2 * b.N;
-  uv3dmix2_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs, nnew, c->D.kpp4); c->launches++;
+  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend};
+  static const bool per_level = (getenv("ROMS_B200_UVMIX_PERLEVEL") != nullptr);        // the first form
+  if (!per_level) {
+    static bool attr = false;
+    if (!attr) {
+      CUDA_OK(cudaFuncSetAttribute(uv3dmix2_roll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M2_SMEM));
+      CUDA_OK(cudaFuncSetAttribute(uv3dmix2_roll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M2_SMEM));
+      attr = true;
+    }
+    dim3 blk(M2_TX, M2_TY); dim3 g = grid2(bx, blk);
+    const long cols = (long)g.x * g.y;
+    static const int waves = getenv("ROMS_B200_UVMIX_FILL") ? atoi(getenv("ROMS_B200_UVMIX_FILL")) : 1;
+    int nch = (int)std::min<long>(((long)waves * 148 + cols - 1) / cols, (b.N + 4) / 5); if (nch < 1) nch = 1;
+    g.z = nch;
+    if (nch == 1) { uv3dmix2_roll_kernel<true><<<g, blk, M2_SMEM, c->stream>>>(c->D, bx, nrhs, nnew, nch, c->D.kpp4); c->launches++; return 0; }
+    uv3dmix2_roll_kernel<false><<<g, blk, M2_SMEM, c->stream>>>(c->D, bx, nrhs, nnew, nch, c->D.kpp4); c->launches++;
+  } else {
+    dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = 2 * b.N;
+    uv3dmix2_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs, nnew, c->D.kpp4); c->launches++;
+  }
   dim3 blk2(32, 4); dim3 g2 = grid2(bx, blk2); g2.z = 2;
   uv3dmix2_sum_kernel<<<g2, blk2, 0, c->stream>>>(c->D, bx, c->D.kpp4); c->launches++;
   return 0;
