@@ -108,44 +108,44 @@ int k_prsgrd(roms_b200_ctx* c, int nrhs) {
 // ---- rhs3d_tile, rhs3d.F:498-1919 ----------------------------------------------
 struct RQ { V3 u, v, Hz, Huon, Hvom, W; V2 fomn, dndx, dmde; int curv; int S, N, Jstr, Jend; };
 // second differences with the closed-wall replacements of rhs3d.F:793-806,909-922
-__device__ __forceinline__ double q_uee(const RQ& Q, int i, int j, int k) {
+template <class RQT> __device__ __forceinline__ double q_uee(const RQT& Q, int i, int j, int k) {
   int jj = j; if (Q.S && j == Q.Jstr - 1) jj = Q.Jstr; if (Q.N && j == Q.Jend + 1) jj = Q.Jend;
   return Q.u(i, jj - 1, k) - 2.0 * Q.u(i, jj, k) + Q.u(i, jj + 1, k);
 }
-__device__ __forceinline__ double q_vee(const RQ& Q, int i, int j, int k) {
+template <class RQT> __device__ __forceinline__ double q_vee(const RQT& Q, int i, int j, int k) {
   int jj = j; if (Q.S && j == Q.Jstr) jj = Q.Jstr + 1; if (Q.N && j == Q.Jend + 1) jj = Q.Jend;
   return Q.v(i, jj - 1, k) - 2.0 * Q.v(i, jj, k) + Q.v(i, jj + 1, k);
 }
-__device__ __forceinline__ double q_Hvee(const RQ& Q, int i, int j, int k) {
+template <class RQT> __device__ __forceinline__ double q_Hvee(const RQT& Q, int i, int j, int k) {
   int jj = j; if (Q.S && j == Q.Jstr) jj = Q.Jstr + 1; if (Q.N && j == Q.Jend + 1) jj = Q.Jend;
   return Q.Hvom(i, jj - 1, k) - 2.0 * Q.Hvom(i, jj, k) + Q.Hvom(i, jj + 1, k);
 }
-__device__ __forceinline__ double q_uxx(const RQ& Q, int i, int j, int k) { return Q.u(i - 1, j, k) - 2.0 * Q.u(i, j, k) + Q.u(i + 1, j, k); }
-__device__ __forceinline__ double q_Huxx(const RQ& Q, int i, int j, int k) { return Q.Huon(i - 1, j, k) - 2.0 * Q.Huon(i, j, k) + Q.Huon(i + 1, j, k); }
-__device__ __forceinline__ double q_vxx(const RQ& Q, int i, int j, int k) { return Q.v(i - 1, j, k) - 2.0 * Q.v(i, j, k) + Q.v(i + 1, j, k); }
-__device__ __forceinline__ double q_Hvxx(const RQ& Q, int i, int j, int k) { return Q.Hvom(i - 1, j, k) - 2.0 * Q.Hvom(i, j, k) + Q.Hvom(i + 1, j, k); }
-__device__ __forceinline__ double q_Huee(const RQ& Q, int i, int j, int k) { return Q.Huon(i, j - 1, k) - 2.0 * Q.Huon(i, j, k) + Q.Huon(i, j + 1, k); }
+template <class RQT> __device__ __forceinline__ double q_uxx(const RQT& Q, int i, int j, int k) { return Q.u(i - 1, j, k) - 2.0 * Q.u(i, j, k) + Q.u(i + 1, j, k); }
+template <class RQT> __device__ __forceinline__ double q_Huxx(const RQT& Q, int i, int j, int k) { return Q.Huon(i - 1, j, k) - 2.0 * Q.Huon(i, j, k) + Q.Huon(i + 1, j, k); }
+template <class RQT> __device__ __forceinline__ double q_vxx(const RQT& Q, int i, int j, int k) { return Q.v(i - 1, j, k) - 2.0 * Q.v(i, j, k) + Q.v(i + 1, j, k); }
+template <class RQT> __device__ __forceinline__ double q_Hvxx(const RQT& Q, int i, int j, int k) { return Q.Hvom(i - 1, j, k) - 2.0 * Q.Hvom(i, j, k) + Q.Hvom(i + 1, j, k); }
+template <class RQT> __device__ __forceinline__ double q_Huee(const RQT& Q, int i, int j, int k) { return Q.Huon(i, j - 1, k) - 2.0 * Q.Huon(i, j, k) + Q.Huon(i, j + 1, k); }
 #define GADV (-0.25)
 // UFx at rho-point (i,j): rhs3d.F:767-784
-__device__ __forceinline__ double q_UFx(const RQ& Q, int i, int j, int k) {
+template <class RQT> __device__ __forceinline__ double q_UFx(const RQT& Q, int i, int j, int k) {
   const double c1 = Q.u(i, j, k) + Q.u(i + 1, j, k);
   const double c = (c1 > 0.0) ? q_uxx(Q, i, j, k) : q_uxx(Q, i + 1, j, k);
   return 0.25 * (c1 + GADV * c) * (Q.Huon(i, j, k) + Q.Huon(i + 1, j, k) + GADV * 0.5 * (q_Huxx(Q, i, j, k) + q_Huxx(Q, i + 1, j, k)));
 }
 // UFe at psi-point (i,j): rhs3d.F:822-840
-__device__ __forceinline__ double q_UFe(const RQ& Q, int i, int j, int k) {
+template <class RQT> __device__ __forceinline__ double q_UFe(const RQT& Q, int i, int j, int k) {
   const double c1 = Q.u(i, j, k) + Q.u(i, j - 1, k), c2 = Q.Hvom(i, j, k) + Q.Hvom(i - 1, j, k);
   const double c = (c2 > 0.0) ? q_uee(Q, i, j - 1, k) : q_uee(Q, i, j, k);
   return 0.25 * (c1 + GADV * c) * (c2 + GADV * 0.5 * (q_Hvxx(Q, i, j, k) + q_Hvxx(Q, i - 1, j, k)));
 }
 // VFx at psi-point (i,j): rhs3d.F:871-889
-__device__ __forceinline__ double q_VFx(const RQ& Q, int i, int j, int k) {
+template <class RQT> __device__ __forceinline__ double q_VFx(const RQT& Q, int i, int j, int k) {
   const double c1 = Q.v(i, j, k) + Q.v(i - 1, j, k), c2 = Q.Huon(i, j, k) + Q.Huon(i, j - 1, k);
   const double c = (c2 > 0.0) ? q_vxx(Q, i - 1, j, k) : q_vxx(Q, i, j, k);
   return 0.25 * (c1 + GADV * c) * (c2 + GADV * 0.5 * (q_Huee(Q, i, j, k) + q_Huee(Q, i, j - 1, k)));
 }
 // VFe at rho-point (i,j): rhs3d.F:924-942
-__device__ __forceinline__ double q_VFe(const RQ& Q, int i, int j, int k) {
+template <class RQT> __device__ __forceinline__ double q_VFe(const RQT& Q, int i, int j, int k) {
   const double c1 = Q.v(i, j, k) + Q.v(i, j + 1, k);
   const double c = (c1 > 0.0) ? q_vee(Q, i, j, k) : q_vee(Q, i, j + 1, k);
   return 0.25 * (c1 + GADV * c) * (Q.Hvom(i, j, k) + Q.Hvom(i, j + 1, k) + GADV * 0.5 * (q_Hvee(Q, i, j, k) + q_Hvee(Q, i, j + 1, k)));
@@ -226,10 +226,212 @@ __global__ void __launch_bounds__(128) rhs3d_sum_kernel(const Dev D, Box bx, int
     v2(D, FID(rvfrc))(i, j) = sum + s1 + s2;
   }
 }
+// ---- rhs3d, production form: a block marches a 32 x 8 tile up a chunk of levels (the recipe of k_tracer.cu) ---------------------
+// Per level the planes u, v, Huon, Hvom, Hz, W of the tile + two rings of halo go through shared memory (loaded into registers
+// one level ahead); from them every rho point evaluates UFx, VFe, the Coriolis and the curvilinear terms ONCE, every psi point
+// UFe and VFx, every u / v point the horizontal weight of its vertical flux; the u and v updates of a point read those planes.
+// The vertical C4 fluxes of w-level k-1 are carried, the column values u, v (k-1..k+2) roll through registers.  With one chunk
+// (whole column) rufrc/rvfrc are summed in registers in the reference's order (rhs3d.F:1707-1916) and the sum kernel disappears.
+// RS: view of a raw plane in shared memory with the (i,j,k) call syntax of V3, so the flux functions above are reused as they are.
+constexpr int R2_TX = 32, R2_TY = 8, R2_NT = R2_TX * R2_TY;
+constexpr int R2_RW = R2_TX + 4, R2_NR = R2_RW * (R2_TY + 4);        // raw planes: i in [I0-2, I0+33], j in [J0-2, J0+9]
+constexpr int R2_CW = R2_TX + 1, R2_NC = R2_CW * (R2_TY + 1);        // rho cells from (I0-1, J0-1), psi / u / v cells from (I0, J0): 33 x 9
+constexpr int R2_NQ = (R2_NR + R2_NT - 1) / R2_NT, R2_CQ = (R2_NC + R2_NT - 1) / R2_NT;
+constexpr int R2_NPL = 10;                                           // UFx, VFe, cor_u, cor_v, curv_u, curv_v | UFe, VFx, wt_u, wt_v
+constexpr size_t R2_SMEM = (2 * R2_NPL * R2_NC + 2 * 6 * R2_NR) * sizeof(double);
+struct RS {
+  const double* p; int i0, j0;             // element (i,j) at (i - i0) + R2_RW * (j - j0)
+  __device__ __forceinline__ double operator()(int i, int j, int) const { return p[(i - i0) + R2_RW * (j - j0)]; }
+};
+struct RQS { RS u, v, Hz, Huon, Hvom, W; V2 fomn, dndx, dmde; int curv; int S, N, Jstr, Jend; };
+// the flux functions of the per-level kernel, on shared-memory planes (same expressions: q_* above are templates over the view)
+template <bool FULL>
+__global__ void __launch_bounds__(R2_NT, 2) rhs3d_roll_kernel(const Dev D, Box bx, int nrhs, int nch) {
+  extern __shared__ double r2sm[];
+  double* const smD = r2sm; double* const smR = smD + 2 * R2_NPL * R2_NC;
+  const roms_b200_bounds& b = D.b; const int N = b.N;
+  const int ch = (int)blockIdx.z, per = (N + nch - 1) / nch, k0 = 1 + per * ch, k1 = min(k0 + per - 1, N);
+  if (k0 > N) return;
+  const int I0 = bx.i0 + blockIdx.x * R2_TX, J0 = bx.j0 + blockIdx.y * R2_TY;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * R2_TX + tx, i = I0 + tx, j = J0 + ty;
+  V3 u = v3l(D, FID(u), nrhs), v = v3l(D, FID(v), nrhs), Hz = v3(D, FID(Hz)), Huon = v3(D, FID(Huon)), Hvom = v3(D, FID(Hvom)), W = v3(D, FID(W));
+  V3 ru = v3l(D, FID(ru), nrhs), rv = v3l(D, FID(rv), nrhs);
+  auto DS = [&](int L) { return smD + (L & 1) * R2_NPL * R2_NC; };
+  auto RAW = [&](int L) { return smR + (L & 1) * 6 * R2_NR; };           // u, v, Huon, Hvom, Hz, W
+  auto view = [&](int L) {
+    const double* R = RAW(L);
+    return RQS{RS{R, I0 - 2, J0 - 2}, RS{R + R2_NR, I0 - 2, J0 - 2}, RS{R + 4 * R2_NR, I0 - 2, J0 - 2}, RS{R + 2 * R2_NR, I0 - 2, J0 - 2},
+               RS{R + 3 * R2_NR, I0 - 2, J0 - 2}, RS{R + 5 * R2_NR, I0 - 2, J0 - 2}, v2(D, FID(fomn)), v2(D, FID(dndx)), v2(D, FID(dmde)),
+               D.p.app == ROMS_B200_APP_BENCHMARK, b.Southern_Edge && !b.NSperiodic, b.Northern_Edge && !b.NSperiodic, b.Jstr, b.Jend};
+  };
+  int ri[R2_NQ], rj[R2_NQ]; bool ro[R2_NQ];
+#pragma unroll
+  for (int n = 0; n < R2_NQ; ++n) {
+    const int q = tid + n * R2_NT;
+    ri[n] = I0 - 2 + q % R2_RW; rj[n] = J0 - 2 + q / R2_RW;
+    ro[n] = q < R2_NR && ri[n] <= bx.i1 + 2 && rj[n] <= bx.j1 + 2 && ri[n] >= b.LBi && ri[n] <= b.UBi && rj[n] >= b.LBj && rj[n] <= b.UBj;
+  }
+  // which derived cells this thread evaluates, and which of their quantities somebody reads (the reference's loop ranges)
+  int ci_[R2_CQ], cj_[R2_CQ]; bool inq[R2_CQ];
+  bool nUFx[R2_CQ], nVFe[R2_CQ], nCor[R2_CQ], nUFe[R2_CQ], nVFx[R2_CQ], nWu[R2_CQ], nWv[R2_CQ];
+  double cf[R2_CQ], cdn[R2_CQ], cdm[R2_CQ];
+#pragma unroll
+  for (int n = 0; n < R2_CQ; ++n) {
+    const int q = tid + n * R2_NT; inq[n] = q < R2_NC;
+    ci_[n] = q % R2_CW; cj_[n] = q / R2_CW;
+    const int ir = I0 - 1 + ci_[n], jr = J0 - 1 + cj_[n], ip = I0 + ci_[n], jp = J0 + cj_[n];
+    const bool tr = inq[n] && ir <= bx.i1 && jr <= bx.j1, tp = inq[n] && ip <= bx.i1 + 1 && jp <= bx.j1 + 1;
+    nUFx[n] = tr && ir >= b.IstrU - 1 && ir <= b.Iend && jr >= b.Jstr && jr <= b.Jend;
+    nVFe[n] = tr && ir >= b.Istr && ir <= b.Iend && jr >= b.JstrV - 1 && jr <= b.Jend;
+    nCor[n] = nUFx[n] || nVFe[n];
+    nUFe[n] = tp && ip >= b.IstrU && ip <= b.Iend && jp >= b.Jstr && jp <= b.Jend + 1;
+    nVFx[n] = tp && ip >= b.Istr && ip <= b.Iend + 1 && jp >= b.JstrV && jp <= b.Jend;
+    nWu[n] = tp && ip >= b.IstrU && ip <= b.Iend && jp >= b.Jstr && jp <= b.Jend && ip <= bx.i1 && jp <= bx.j1;
+    nWv[n] = tp && ip >= b.Istr && ip <= b.Iend && jp >= b.JstrV && jp <= b.Jend && ip <= bx.i1 && jp <= bx.j1;
+    cf[n] = 0.0; cdn[n] = 0.0; cdm[n] = 0.0;
+    if (nCor[n]) { cf[n] = v2(D, FID(fomn))(ir, jr); cdn[n] = v2(D, FID(dndx))(ir, jr); cdm[n] = v2(D, FID(dmde))(ir, jr); }
+  }
+  double r_[6][R2_NQ];
+  auto loadR = [&](int L) {
+#pragma unroll
+    for (int n = 0; n < R2_NQ; ++n) {
+#pragma unroll
+      for (int f = 0; f < 6; ++f) r_[f][n] = 0.0;
+      if (ro[n] && L >= 0 && L <= N) {
+        r_[5][n] = W(ri[n], rj[n], L);
+        if (L >= 1) { r_[0][n] = u(ri[n], rj[n], L); r_[1][n] = v(ri[n], rj[n], L); r_[2][n] = Huon(ri[n], rj[n], L); r_[3][n] = Hvom(ri[n], rj[n], L); r_[4][n] = Hz(ri[n], rj[n], L); }
+      }
+    }
+  };
+  auto commitR = [&](int L) {
+    double* R = RAW(L);
+#pragma unroll
+    for (int n = 0; n < R2_NQ; ++n) { const int q = tid + n * R2_NT; if (q < R2_NR) {
+#pragma unroll
+      for (int f = 0; f < 6; ++f) R[f * R2_NR + q] = r_[f][n]; } }
+  };
+  auto derive = [&](int L) {
+    const RQS Q = view(L); double* F = DS(L);
+    const double c1 = 9.0 / 16.0, c2 = 1.0 / 16.0;
+#pragma unroll
+    for (int n = 0; n < R2_CQ; ++n) {
+      if (!inq[n]) continue;
+      const int q = tid + n * R2_NT;
+      const int ir = I0 - 1 + ci_[n], jr = J0 - 1 + cj_[n], ip = I0 + ci_[n], jp = J0 + cj_[n];
+      if (nUFx[n]) F[q] = q_UFx(Q, ir, jr, L);
+      if (nVFe[n]) F[R2_NC + q] = q_VFe(Q, ir, jr, L);
+      if (nCor[n]) {
+        const double cff = 0.5 * Q.Hz(ir, jr, L) * cf[n];
+        F[2 * R2_NC + q] = cff * (Q.v(ir, jr, L) + Q.v(ir, jr + 1, L)); F[3 * R2_NC + q] = cff * (Q.u(ir, jr, L) + Q.u(ir + 1, jr, L));
+        if (Q.curv) {
+          const double a1 = 0.5 * (Q.v(ir, jr, L) + Q.v(ir, jr + 1, L)), a2 = 0.5 * (Q.u(ir, jr, L) + Q.u(ir + 1, jr, L));
+          const double a3 = a1 * cdn[n], a4 = a2 * cdm[n];
+          const double cc = Q.Hz(ir, jr, L) * (a3 - a4);
+          F[4 * R2_NC + q] = cc * a1; F[5 * R2_NC + q] = cc * a2;
+        }
+      }
+      if (nUFe[n]) F[6 * R2_NC + q] = q_UFe(Q, ip, jp, L);
+      if (nVFx[n]) F[7 * R2_NC + q] = q_VFx(Q, ip, jp, L);
+      if (nWu[n]) F[8 * R2_NC + q] = c1 * (Q.W(ip, jp, L) + Q.W(ip - 1, jp, L)) - c2 * (Q.W(ip + 1, jp, L) + Q.W(ip - 2, jp, L));
+      if (nWv[n]) F[9 * R2_NC + q] = c1 * (Q.W(ip, jp, L) + Q.W(ip, jp - 1, L)) - c2 * (Q.W(ip, jp + 1, L) + Q.W(ip, jp - 2, L));
+    }
+  };
+  // C4 vertical flux at w-level k from the horizontal weight and the column values (q_FCw)
+  auto fcw = [&](int k, double wt, double qm1, double q0, double qp1, double qp2) -> double {
+    const double c1 = 9.0 / 16.0, c2 = 1.0 / 16.0;
+    if (k == 0 || k == N) return 0.0;
+    if (k == 1) return (c1 * (q0 + qp1) - c2 * (q0 + qp2)) * wt;
+    if (k == N - 1) return (c1 * (q0 + qp1) - c2 * (qm1 + qp1)) * wt;
+    return (c1 * (q0 + qp1) - c2 * (qm1 + qp2)) * wt;
+  };
+  const bool inb = (i <= bx.i1 && j <= bx.j1);
+  const bool doU = inb && (i >= b.IstrU && i <= b.Iend && j >= b.Jstr && j <= b.Jend);
+  const bool doV = inb && (i >= b.Istr && i <= b.Iend && j >= b.JstrV && j <= b.Jend);
+  const bool curv = (D.p.app == ROMS_B200_APP_BENCHMARK);
+  const int lr = (tx + 1) + R2_CW * (ty + 1), lp = tx + R2_CW * ty;
+  auto ucol = [&](int L) -> double { return (doU && L >= 1 && L <= N) ? u(i, j, L) : 0.0; };
+  auto vcol = [&](int L) -> double { return (doV && L >= 1 && L <= N) ? v(i, j, L) : 0.0; };
+  // ---- prologue: raw[k0-1] (only W is used: the weights of w-level k0-1), raw[k0]; column state
+  loadR(k0 - 1); commitR(k0 - 1);
+  __syncthreads();
+  double FCmu = 0.0, FCmv = 0.0;
+  {
+    // weights of w-level k0-1 straight from the raw plane (chunk start only)
+    const RQS Q = view(k0 - 1); const int km = k0 - 1;
+    const double c1 = 9.0 / 16.0, c2 = 1.0 / 16.0;
+    if (doU) { const double wt = c1 * (Q.W(i, j, km) + Q.W(i - 1, j, km)) - c2 * (Q.W(i + 1, j, km) + Q.W(i - 2, j, km)); FCmu = fcw(km, wt, ucol(km - 1), ucol(km), ucol(km + 1), ucol(km + 2)); }
+    if (doV) { const double wt = c1 * (Q.W(i, j, km) + Q.W(i, j - 1, km)) - c2 * (Q.W(i, j + 1, km) + Q.W(i, j - 2, km)); FCmv = fcw(km, wt, vcol(km - 1), vcol(km), vcol(km + 1), vcol(km + 2)); }
+  }
+  __syncthreads();                                  // everybody is done with raw[k0-1] before raw[k0+1] replaces it
+  loadR(k0); commitR(k0);
+  loadR(k0 + 1);
+  double um1 = ucol(k0 - 1), u0 = ucol(k0), up1 = ucol(k0 + 1), up2 = 0.0, unx = ucol(k0 + 2);     // unx, vnx: the next level of the column, in flight for a whole level
+  double vm1 = vcol(k0 - 1), v0 = vcol(k0), vp1 = vcol(k0 + 1), vp2 = 0.0, vnx = vcol(k0 + 2);
+  double run = doU ? ru(i, j, k0) : 0.0, rvn = doV ? rv(i, j, k0) : 0.0;
+  double sumu = 0.0, sumv = 0.0;
+  __syncthreads();
+  derive(k0);
+  for (int k = k0; k <= k1; ++k) {
+    commitR(k + 1);
+    loadR(k + 2);
+    const double ruk = run, rvk = rvn;
+    if (k + 1 <= k1) { if (doU) run = ru(i, j, k + 1); if (doV) rvn = rv(i, j, k + 1); }
+    up2 = unx; vp2 = vnx;
+    unx = ucol(k + 3); vnx = vcol(k + 3);
+    __syncthreads();
+    if (k + 1 <= k1) derive(k + 1);
+    const double* F = DS(k);
+    if (doU) {
+      double r = ruk;
+      r = r + 0.5 * (F[2 * R2_NC + lr] + F[2 * R2_NC + lr - 1]);
+      if (curv) r = r + 0.5 * (F[4 * R2_NC + lr] + F[4 * R2_NC + lr - 1]);
+      const double c1 = F[lr] - F[lr - 1], c2 = F[6 * R2_NC + lp + R2_CW] - F[6 * R2_NC + lp];
+      r = r - (c1 + c2);
+      const double FCk = fcw(k, F[8 * R2_NC + lp], um1, u0, up1, up2);
+      r = r - (FCk - FCmu);
+      ru(i, j, k) = r; FCmu = FCk;
+      if (FULL) sumu = (k == 1) ? r : sumu + r;
+    }
+    if (doV) {
+      double r = rvk;
+      r = r - 0.5 * (F[3 * R2_NC + lr] + F[3 * R2_NC + lr - R2_CW]);
+      if (curv) r = r - 0.5 * (F[5 * R2_NC + lr] + F[5 * R2_NC + lr - R2_CW]);
+      const double c1 = F[7 * R2_NC + lp + 1] - F[7 * R2_NC + lp], c2 = F[R2_NC + lr] - F[R2_NC + lr - R2_CW];
+      r = r - (c1 + c2);
+      const double FCk = fcw(k, F[9 * R2_NC + lp], vm1, v0, vp1, vp2);
+      r = r - (FCk - FCmv);
+      rv(i, j, k) = r; FCmv = FCk;
+      if (FULL) sumv = (k == 1) ? r : sumv + r;
+    }
+    um1 = u0; u0 = up1; up1 = up2; vm1 = v0; v0 = vp1; vp1 = vp2;
+  }
+  if (FULL) {                                       // rhs3d.F:1707-1916
+    if (doU) { const double cff = v2(D, FID(om_u))(i, j) * v2(D, FID(on_u))(i, j); const double s1 = v2(D, FID(sustr))(i, j) * cff, s2 = -v2(D, FID(bustr))(i, j) * cff; v2(D, FID(rufrc))(i, j) = sumu + s1 + s2; }
+    if (doV) { const double cff = v2(D, FID(om_v))(i, j) * v2(D, FID(on_v))(i, j); const double s1 = v2(D, FID(svstr))(i, j) * cff, s2 = -v2(D, FID(bvstr))(i, j) * cff; v2(D, FID(rvfrc))(i, j) = sumv + s1 + s2; }
+  }
+}
 int k_rhs3d_tile(roms_b200_ctx* c, int nrhs) {
   const roms_b200_bounds& b = c->D.b;
-  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = 2 * b.N;
-  rhs3d_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs); c->launches++;
+  Box bx{b.Istr, b.Iend, b.Jstr, b.Jend};
+  static const bool per_level = (getenv("ROMS_B200_RHS3D_PERLEVEL") != nullptr);        // the first form
+  if (!per_level) {
+    static bool attr = false;
+    if (!attr) {
+      CUDA_OK(cudaFuncSetAttribute(rhs3d_roll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM));
+      CUDA_OK(cudaFuncSetAttribute(rhs3d_roll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM));
+      attr = true;
+    }
+    dim3 blk(R2_TX, R2_TY); dim3 g = grid2(bx, blk);
+    const long cols = (long)g.x * g.y;
+    static const int waves = getenv("ROMS_B200_RHS3D_FILL") ? atoi(getenv("ROMS_B200_RHS3D_FILL")) : 1;
+    int nch = (int)std::min<long>(((long)waves * 148 + cols - 1) / cols, (b.N + 4) / 5); if (nch < 1) nch = 1;
+    g.z = nch;
+    if (nch == 1) { rhs3d_roll_kernel<true><<<g, blk, R2_SMEM, c->stream>>>(c->D, bx, nrhs, nch); c->launches++; return 0; }
+    rhs3d_roll_kernel<false><<<g, blk, R2_SMEM, c->stream>>>(c->D, bx, nrhs, nch); c->launches++;
+  } else {
+    dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = 2 * b.N;
+    rhs3d_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs); c->launches++;
+  }
   dim3 blk2(32, 4); dim3 g2 = grid2(bx, blk2); g2.z = 2;
   rhs3d_sum_kernel<<<g2, blk2, 0, c->stream>>>(c->D, bx, nrhs); c->launches++;
   return 0;

@@ -17,7 +17,7 @@ double emu_now_ms() { return std::chrono::duration<double, std::milli>(std::chro
 namespace emu {
 namespace {
 // kernels that call __syncthreads(): their blocks run as teams of real threads; every other kernel runs its threads in a loop
-const char* kTeamKernels[] = {"step2d_kernel", "diag_cols_kernel", "diag_sum_kernel", "step3d_t_v6_kernel", "step3d_t_v8_kernel", "step3d_t_v4_kernel", "t3dmix2_geo_roll_kernel", "pre_step3d_t_roll_kernel", "uv3dmix2_roll_kernel"};
+const char* kTeamKernels[] = {"step2d_kernel", "diag_cols_kernel", "diag_sum_kernel", "step3d_t_v6_kernel", "step3d_t_v8_kernel", "step3d_t_v4_kernel", "t3dmix2_geo_roll_kernel", "pre_step3d_t_roll_kernel", "uv3dmix2_roll_kernel", "rhs3d_roll_kernel"};
 bool needs_team(const char* k) { for (const char* t : kTeamKernels) if (strstr(k, t)) return true; return false; }
 std::vector<double> g_smem(64 * 1024, 0.0);          // dynamic shared memory of the running block
 thread_local bool in_team = false;
