@@ -316,6 +316,61 @@ __global__ void __launch_bounds__(P2_NT, 2) pre_step3d_t_roll_kernel(const Dev D
   }
 }
 
+// ---- pre_step3d momentum, production form: one thread per (u or v) column and chunk of levels, marching upward --------------
+// The vertical viscous flux of w-level k-1 and the z_r pair of level k are carried, everything a level needs is loaded one
+// level ahead; the per-level kernel evaluates every flux (a division) twice and reads 19 values per cell instead of 9.
+__global__ void __launch_bounds__(256) pre_step3d_uv_march_kernel(const Dev D, Box bx, int nrhs, int nstp, int nnew, int mode, int nch) {
+  IJ_FROM_BOX(bx);
+  const roms_b200_bounds& b = D.b; const int N = b.N, comp = (int)blockIdx.z / nch, ch = (int)blockIdx.z % nch; const double dt = D.p.dt;
+  const int per = (N + nch - 1) / nch, k0 = 1 + per * ch, k1 = min(k0 + per - 1, N);
+  if (k0 > N) return;
+  if (comp == 0 && !(i >= b.IstrU && i <= b.Iend && j >= b.Jstr && j <= b.Jend)) return;
+  if (comp == 1 && !(i >= b.Istr && i <= b.Iend && j >= b.JstrV && j <= b.Jend)) return;
+  V3 Hz = v3(D, FID(Hz)), z_r = v3(D, FID(z_r)), Akv = v3(D, FID(Akv));
+  V2 pm = v2(D, FID(pm)), pn = v2(D, FID(pn));
+  const int indx = 3 - nrhs, di = comp == 0 ? 1 : 0, dj = 1 - di, in = i - di, jn = j - dj;
+  const double cff3 = dt * (1.0 - 1.0 /*lambda*/);
+  V3 q = v3l(D, comp == 0 ? FID(u) : FID(v), nstp), qn = v3l(D, comp == 0 ? FID(u) : FID(v), nnew);
+  V3 r1 = v3l(D, comp == 0 ? FID(ru) : FID(rv), nrhs), r2 = v3l(D, comp == 0 ? FID(ru) : FID(rv), indx);
+  const double DC0 = (dt * 0.25) * (pm(i, j) + pm(in, jn)) * (pn(i, j) + pn(in, jn));
+  const double Fbot = dt * v2(D, comp == 0 ? FID(bustr) : FID(bvstr))(i, j), Ftop = dt * v2(D, comp == 0 ? FID(sustr) : FID(svstr))(i, j);
+  // flux at w-level kk from the z_r pairs of levels kk, kk+1, q(kk), q(kk+1) and the Akv pair of level kk
+  auto vflx = [&](int kk, double zo1, double zn1, double zo0, double zn0, double q1, double q0, double ako, double akn) -> double {
+    if (kk == 0) return Fbot;
+    if (kk == N) return Ftop;
+    const double c = 1.0 / (zo1 + zn1 - zo0 - zn0);
+    return cff3 * c * (q1 - q0) * (ako + akn);
+  };
+  // column state at the chunk start: level k0 pair of z_r, q(k0), the flux of w-level k0-1
+  double zo0 = z_r(i, j, k0), zn0 = z_r(in, jn, k0), q0 = q(i, j, k0), Fm;
+  { const int km = k0 - 1;
+    if (km >= 1) Fm = vflx(km, zo0, zn0, z_r(i, j, km), z_r(in, jn, km), q0, q(i, j, km), Akv(i, j, km), Akv(in, jn, km));
+    else Fm = Fbot; }
+  // level k operands, loaded one level ahead
+  double nzo, nzn, nq, nako, nakn, nhz, nhzn, nr1, nr2;
+  auto loadL = [&](int k) {
+    nzo = 0.0; nzn = 0.0; nq = 0.0; nako = 0.0; nakn = 0.0; nr1 = 0.0; nr2 = 0.0;
+    if (k < N) { nzo = z_r(i, j, k + 1); nzn = z_r(in, jn, k + 1); nq = q(i, j, k + 1); nako = Akv(i, j, k); nakn = Akv(in, jn, k); }
+    nhz = Hz(i, j, k); nhzn = Hz(in, jn, k);
+    if (mode >= 1) nr2 = r2(i, j, k);
+    if (mode == 2) nr1 = r1(i, j, k);
+  };
+  loadL(k0);
+  for (int k = k0; k <= k1; ++k) {
+    const double zo1 = nzo, zn1 = nzn, q1 = nq, ako = nako, akn = nakn, hz = nhz, hzn = nhzn, r1k = nr1, r2k = nr2;
+    if (k + 1 <= k1) loadL(k + 1);
+    const double Fk = vflx(k, zo1, zn1, zo0, zn0, q1, q0, ako, akn);
+    const double a = q0 * 0.5 * (hz + hzn);
+    const double d = Fk - Fm;
+    double val;
+    if (mode == 0) val = a + d;
+    else if (mode == 1) { const double c3 = 0.5 * DC0; val = a - c3 * r2k + d; }
+    else val = a + DC0 * ((5.0 / 12.0) * r1k - (16.0 / 12.0) * r2k) + d;
+    qn(i, j, k) = val;
+    Fm = Fk; zo0 = zo1; zn0 = zn1; q0 = q1;
+  }
+}
+
 // pre_step3d_tile in its two independent halves: tracers (pre_step3d.F:329-957) and momentum (:960-1168)
 int k_pre_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntfirst) {
   (void)nrhs;
@@ -340,6 +395,16 @@ int k_pre_step3d_uv(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int
   const roms_b200_bounds& b = c->D.b;
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = 2 * b.N;
   const int mode = (iic == ntfirst) ? 0 : (iic == ntfirst + 1 ? 1 : 2);
+  static const bool per_level = (getenv("ROMS_B200_PRE3D_PERLEVEL") != nullptr);      // the first form
+  if (!per_level) {
+    dim3 g2 = grid2(bx, blk);
+    const long cols = (long)g2.x * g2.y * 2;
+    static const int waves = getenv("ROMS_B200_PRE3DUV_FILL") ? atoi(getenv("ROMS_B200_PRE3DUV_FILL")) : 0;
+    int nch = (int)std::min<long>(((long)waves * 148 + cols - 1) / cols, (b.N + 4) / 5); if (nch < 1) nch = 1;
+    g2.z = 2 * nch;
+    pre_step3d_uv_march_kernel<<<g2, blk, 0, c->stream>>>(c->D, bx, nrhs, nstp, nnew, mode, nch); c->launches++;
+    return 0;
+  }
   pre_step3d_uv_kernel<<<g, blk, 0, c->stream>>>(c->D, bx, nrhs, nstp, nnew, mode); c->launches++;
   return 0;
 }
