@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(DG_NT) diag_sum_kernel(const Dev D, V2 ke2d, V
 int k_diag_begin(roms_b200_ctx* c, int nstp) {
   const Dev& D = c->D; const roms_b200_bounds& b = D.b; const int wi = b.Iend - b.Istr + 1, wj = b.Jend - b.Jstr + 1;
   const int nbx = (wi + DG_NT - 1) / DG_NT, nparts = nbx * wj;
-  V2 ke2d{D.scratch2 + 2 * D.nij, b.LBi, D.ni, b.LBj}, pe2d{D.scratch2 + 3 * D.nij, b.LBi, D.ni, b.LBj}, vo2d{D.scratch2 + 4 * D.nij, b.LBi, D.ni, b.LBj};
+  V2 ke2d{D.scratch2 + 8 * D.nij, b.LBi, D.ni, b.LBj}, pe2d{D.scratch2 + 9 * D.nij, b.LBi, D.ni, b.LBj}, vo2d{D.scratch2 + 10 * D.nij, b.LBi, D.ni, b.LBj};
   diag_cols_kernel<<<dim3(nbx, wj), DG_NT, 0, c->stream>>>(D, nstp, ke2d, pe2d, vo2d, D.red + 3 * wi + DG_NP); c->launches++;
   diag_sum_kernel<<<nbx + 1, DG_NT, 0, c->stream>>>(D, ke2d, pe2d, vo2d, D.red, nparts); c->launches++;
   CUDA_OK(cudaMemcpyAsync(c->h_red, D.red, sizeof(double) * (3 * wi + DG_NP), cudaMemcpyDeviceToHost, c->stream));

@@ -95,7 +95,7 @@ static int create_impl(roms_b200_ctx* c, const roms_b200_bounds* b, const roms_b
   if (dev_alloc(&v, (size_t)2 * (2 * p->ndtfast + 4))) return 4;
   D.w1 = v; D.w2 = v + (2 * p->ndtfast + 4);
   if (dev_alloc(&D.P, D.nij * b->N)) return 4;
-  if (dev_alloc(&D.scratch2, D.nij * 8)) return 4;
+  if (dev_alloc(&D.scratch2, D.nij * 12)) return 4;
   // four 3-D scratch volumes (ni,nj,0:N): KPP {dR, dU, dV, FC}, t3dmix2_geo dTdz per tracer, uv3dmix2's rufrc/rvfrc terms
   if (dev_alloc(&D.kpp4, D.nij * (size_t)(b->N + 1) * 4)) return 4;
   if (p->app == ROMS_B200_APP_BENCHMARK) {          // KPP surface buoyancy flux profile Bflux ; dTdz of t3dmix2_geo per tracer
@@ -376,20 +376,26 @@ int roms_b200_main3d(roms_b200_ctx* c, int nsteps, int analytic_forcing, int wit
     c->nstp = 1 + ((c->iic - c->ntfirst) % 2); c->nnew = 3 - c->nstp; c->nrhs = c->nstp;
     const int nstp = c->nstp, nnew = c->nnew, nrhs = c->nrhs, iic = c->iic, ntf = c->ntfirst;
     if (analytic_forcing) k_set_data(c, c->time / 86400.0);
-    // ---- branch A (stream2): mass fluxes, omega ; branch B (launch stream): density, diag, surface fluxes, vertical mixing
+    // ---- branch A (stream2): mass fluxes, omega, diag, wvelocity ; branch B (launch stream): density, surface fluxes, vertical
+    // mixing.  diag (main3d.F:300) reads the density of this step -> waits for rho_eos; wvelocity (main3d.F:535) overwrites the
+    // wvel diag reads -> behind it on the same stream.  diag has its own scratch planes (8..10 of scratch2; KPP uses 0..5).
     if (two) {
       CUDA_OK(cudaEventRecord(c->ev[0], c->stream)); CUDA_OK(cudaStreamWaitEvent(c->stream2, c->ev[0], 0));
       OnStream2 on(c);
       k_set_massflux(c, nrhs); k_omega(c);
     } else k_set_massflux(c, nrhs);
     k_rho_eos(c, nrhs);
-    if (with_diag == 1) { double d[3]; if (k_diag(c, nstp, d)) return 1; }      // main3d.F:300 (diag with NINFO=1), host waits
-    else if (with_diag) { if (k_diag_begin(c, nstp)) return 1; }                 // same place, reductions + D2H stay asynchronous:
-                                                                                 // the caller collects them with roms_b200_diag_end
-    if (two) {                                                                   // wvelocity (main3d.F:535) overwrites what diag read
+    if (two) {
       CUDA_OK(cudaEventRecord(c->ev[1], c->stream)); CUDA_OK(cudaStreamWaitEvent(c->stream2, c->ev[1], 0));
-      { OnStream2 on(c); if (k_wvelocity(c, nstp)) return 1; }
+      { OnStream2 on(c);
+        if (with_diag == 1) { double d[3]; if (k_diag(c, nstp, d)) return 1; }      // main3d.F:300 (diag with NINFO=1), host waits
+        else if (with_diag) { if (k_diag_begin(c, nstp)) return 1; }                 // reductions + D2H stay asynchronous: the caller
+                                                                                     // collects them with roms_b200_diag_end
+        if (k_wvelocity(c, nstp)) return 1; }
       CUDA_OK(cudaEventRecord(c->ev[2], c->stream2));
+    } else {
+      if (with_diag == 1) { double d[3]; if (k_diag(c, nstp, d)) return 1; }
+      else if (with_diag) { if (k_diag_begin(c, nstp)) return 1; }
     }
     if (bench) k_bulk_flux(c, nrhs);
     k_set_vbc(c, nrhs);
