@@ -91,6 +91,18 @@ def test_level_major_block_order_is_a_pure_renumbering(emu_lib, case):
     assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("case", [(1, 70, 19, 30, 3), (0, 24, 10, 8, 3), (1, 45, 7, 50, 2)])
+def test_marching_kernels_whole_column_mode(emu_lib, case):
+    """The level-marching kernels (t3dmix2_geo, pre_step3d tracers and momentum, uv3dmix2, rhs3d) split the column into chunks on
+    small grids -- what the other emulation cases run -- and take the WHOLE column per block on grids with enough tiles: then
+    rufrc/rvfrc are summed in registers and the sum kernels are not launched.  *_FILL=0 forces that mode on the small test grids."""
+    env = dict(os.environ, EMU_SM_COUNT="148", ROMS_B200_T3DMIX_FILL="0", ROMS_B200_PRE3D_FILL="0", ROMS_B200_PRE3DUV_FILL="0",
+               ROMS_B200_UVMIX_FILL="0", ROMS_B200_RHS3D_FILL="0")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py")] + [str(x) for x in case] + ["v8"],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_emulated_rho_eos_matches_the_reference_check_values(emu_lib):
     r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "eos"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "EMU-EOS-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
@@ -127,7 +139,7 @@ def test_kernel_sources_memory_safe_under_asan(emu_lib):
                        timeout=900, env=env)
     assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout and "AddressSanitizer" not in r.stderr, r.stdout[-2000:] + r.stderr[-4000:]
     r = subprocess.run([sys.executable, os.path.join(HERE, "emu_worker.py"), "1", "33", "9", "10", "1", "v6"], capture_output=True, text=True,
-                       timeout=900, env=env)
+                       timeout=900, env=dict(env, ROMS_B200_T3DMIX_FILL="0", ROMS_B200_PRE3D_FILL="0", ROMS_B200_UVMIX_FILL="0", ROMS_B200_RHS3D_FILL="0"))
     assert r.returncode == 0 and "EMU-PARITY-OK" in r.stdout and "AddressSanitizer" not in r.stderr, r.stdout[-2000:] + r.stderr[-4000:]
 
 
