@@ -139,6 +139,9 @@ __device__ __forceinline__ bool ll_load(const ulonglong2* p, unsigned s, double&
 // neighbours' mailboxes, (2) then polls and unpacks the strips that arrive for its items, (3) the last block to finish
 // commits the sequence number (device-side, so the kernel is replayable inside the fast-loop CUDA graph).
 __global__ void __launch_bounds__(256) halo_xchg_p2p_kernel(const Dev D, HaloList L, const __grid_constant__ P2PArgs a) {
+  // programmatic dependent launch (see the launch site): no-ops for an ordinary launch
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int ni = D.ni;
   const unsigned long long s64 = a.seq[0] + 1;        // this exchange's sequence number
   const unsigned s = (unsigned)s64;
@@ -305,7 +308,19 @@ int halo_exchange(roms_b200_ctx* c, double* const* bases, const int* nplanes, in
     // one block per (plane, direction) item, at most 8 per SM (a single block for the small 2-D swaps was measured much
     // slower: the strip copies are latency-bound and want to run side by side)
     int nblk = L.total_planes * P2P_NDIR; if (nblk > 8 * nsm) nblk = 8 * nsm;
-    halo_xchg_p2p_kernel<<<nblk, 256, 0, c->stream>>>(c->D, L, a); c->launches++;
+    // Launched as a programmatic dependent of the kernel before it (its launch latency and block scheduling overlap that
+    // kernel's tail; it waits in griddepcontrol.wait before touching any field) and releasing the kernel behind it at once
+    // (a step2d sub-step, which waits the same way until this exchange has completed).  ROMS_B200_HALO_PDL=0: ordinary launch.
+    static const bool pdl = !(getenv("ROMS_B200_HALO_PDL") && atoi(getenv("ROMS_B200_HALO_PDL")) == 0) && !getenv("ROMS_B200_NO_PDL");
+    if (pdl) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(nblk); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      CUDA_OK(cudaLaunchKernelEx(&cfg, halo_xchg_p2p_kernel, c->D, L, a));
+    } else halo_xchg_p2p_kernel<<<nblk, 256, 0, c->stream>>>(c->D, L, a);
+    c->launches++;
     return 0;
   }
   ncclComm_p comm = (ncclComm_p)c->comm;

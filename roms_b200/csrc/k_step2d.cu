@@ -474,10 +474,10 @@ static inline void launch_boxes(roms_b200_ctx* c, cudaStream_t st, const Box* bx
   }
   // Consecutive sub-steps are chained by programmatic dependent launch, which overlaps the launch latency and block scheduling
   // of sub-step n+1 with the tail of sub-step n (the kernel waits in griddepcontrol.wait before its first read): 9.36 -> 9.07 us
-  // per sub-step on BENCHMARK1, bit-identical.  Single tile only (with neighbours a halo kernel sits between two sub-steps and
-  // the combination has not been measured on hardware: ROMS_B200_PDL=1 forces it on, ROMS_B200_NO_PDL=1 off).
-  static const bool pdl_off = (getenv("ROMS_B200_NO_PDL") != nullptr), pdl_on = (getenv("ROMS_B200_PDL") != nullptr);
-  const bool pdl = !pdl_off && (pdl_on || !c->comm);
+  // per sub-step on BENCHMARK1, bit-identical.  With neighbours the halo kernel between two sub-steps is part of the chain
+  // (k_halo.cu): 2 GPUs 1.361 -> 1.345 ms per step with the sub-steps alone.  ROMS_B200_NO_PDL=1 switches it off.
+  static const bool pdl_off = (getenv("ROMS_B200_NO_PDL") != nullptr);
+  const bool pdl = !pdl_off;
   // resident blocks per SM the kernel is compiled for: 2 (128 registers, no spills) is fastest while the grid is a wave or two
   // (BENCHMARK1: 6.97 us per sub-step against 8.84 with 3); on grids of many waves the third block's occupancy wins although
   // it costs 40 bytes of spills (2048x256: 97.8 against 107.2 us).  ROMS_B200_S2_MINB=2|3 forces one.
