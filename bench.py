@@ -194,12 +194,18 @@ def _time_step3d_t(rb, Lm, Mm, N, reps):
 
 def roofline_step3d_t(rb, peak, peak_kind):
     """step3d_t (the graded kernel) on grids whose working set is >> L2 (126 MB), so every launch streams from HBM:
-    96 B algorithmic per cell per call (NT=2).  Primary: the BENCHMARK3 grid (N=30); also the
-    N=50 basin-like tile.  The timing loop re-applies the kernel to its own output (same traffic, arithmetic not meaningful)."""
+    96 B algorithmic per cell per call (NT=2).  Primary: the BENCHMARK3 grid (N=30); also a quarter
+    of and a whole 1024x2048x50 tile of the 4096^2 x 50 basin (also, also2).  The timing loop re-applies the kernel to its own output (same traffic, arithmetic not meaningful)."""
     out = None
     traffic = ncu_traffic()
-    for (Lm, Mm, N) in ((2048, 256, 30), (1024, 512, 50)):
-        ms = _time_step3d_t(rb, Lm, Mm, N, 20)
+    for (Lm, Mm, N) in ((2048, 256, 30), (1024, 512, 50), (1024, 2048, 50)):     # the last: one tile of the 4096^2 x 50 basin on 4x2 GPUs
+        try:
+            ms = _time_step3d_t(rb, Lm, Mm, N, 20 if Mm < 2048 else 8)
+        except Exception as e:                 # (the basin tile needs ~30 GB of HBM)
+            if out is not None:
+                out["also2"] = {"grid": "%dx%dx%d" % (Lm, Mm, N), "error": str(e)[:200]}
+                continue
+            raise
         cells = Lm * Mm * N
         achieved = 96.0 * cells / (ms * 1e-3) / 1e9
         tr = traffic.get("%dx%dx%d" % (Lm, Mm, N), {})
@@ -212,7 +218,7 @@ def roofline_step3d_t(rb, peak, peak_kind):
         if out is None:
             out = r
         else:
-            out["also"] = r
+            out["also" if "also" not in out else "also2"] = r
     return out
 
 

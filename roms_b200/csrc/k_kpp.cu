@@ -313,7 +313,9 @@ __global__ void __launch_bounds__(256) kpp_finish_kernel(const Dev D, Box bx, Kp
   if (south) { st(D, Akv, i, j - 1, k, akv); st(D, Akt1, i, j - 1, k, akt1); st(D, Akt2, i, j - 1, k, akt2); }
   if (north) { st(D, Akv, i, j + 1, k, akv); st(D, Akt1, i, j + 1, k, akt1); st(D, Akt2, i, j + 1, k, akt2); }
 }
-int k_lmd_vmix(roms_b200_ctx* c, int nstp) {
+// part: 1 = the spline derivatives of pden, u, v only (they need rho_eos, not the surface fluxes: main3d runs them beside
+// bulk_flux / set_vbc on the second stream), 2 = everything else, 3 = both
+int k_lmd_vmix_part(roms_b200_ctx* c, int nstp, int part) {
   const roms_b200_bounds& b = c->D.b;
   if (!c->D.kpp4 || !c->D.swdk) { fprintf(stderr, "roms_b200: lmd_vmix needs the BENCHMARK option set (KPP scratch not allocated)\n"); return 1; }
   if (b.N < 3) return 1;
@@ -326,12 +328,15 @@ int k_lmd_vmix(roms_b200_ctx* c, int nstp) {
   Box bx{e.Istr, e.Iend, e.Jstr, e.Jend};
   dim3 blkc(32, 4), blkl(64, 4);
   dim3 gc = grid2(bx, blkc), gl = grid2(bx, blkl); gl.z = b.N + 1;
-  kpp_spline_kernel<<<gc, blkc, 0, c->stream>>>(De, bx, nstp); c->launches++;
-  kpp_levels_kernel<<<gl, blkl, 0, c->stream>>>(De, bx, nstp, kc); c->launches++;
-  kpp_sbl_kernel<<<gc, blkc, 0, c->stream>>>(De, bx); c->launches++;
-  kpp_finish_kernel<<<gl, blkl, 0, c->stream>>>(De, bx, kc); c->launches++;
+  if (part & 1) { kpp_spline_kernel<<<gc, blkc, 0, c->stream>>>(De, bx, nstp); c->launches++; }
+  if (part & 2) {
+    kpp_levels_kernel<<<gl, blkl, 0, c->stream>>>(De, bx, nstp, kc); c->launches++;
+    kpp_sbl_kernel<<<gc, blkc, 0, c->stream>>>(De, bx); c->launches++;
+    kpp_finish_kernel<<<gl, blkl, 0, c->stream>>>(De, bx, kc); c->launches++;
+  }
   return 0;
 }
+int k_lmd_vmix(roms_b200_ctx* c, int nstp) { return k_lmd_vmix_part(c, nstp, 3); }
 
 // ---- bulk_flux_tile (COARE 3.0), bulk_flux.F -----------------------------------------------------------
 #define BLK_CPA 1004.67

@@ -650,7 +650,7 @@ int k_uv3dmix2(roms_b200_ctx* c, int nrhs, int nnew) {
     }
     dim3 blk(M2_TX, M2_TY); dim3 g = grid2(bx, blk);
     const long cols = (long)g.x * g.y;
-    static const int waves = getenv("ROMS_B200_UVMIX_FILL") ? atoi(getenv("ROMS_B200_UVMIX_FILL")) : 1;
+    static const int waves = getenv("ROMS_B200_UVMIX_FILL") ? atoi(getenv("ROMS_B200_UVMIX_FILL")) : 0;
     int nch = (int)std::min<long>(((long)waves * 148 + cols - 1) / cols, (b.N + 4) / 5); if (nch < 1) nch = 1;
     g.z = nch;
     if (nch == 1) { uv3dmix2_roll_kernel<true><<<g, blk, M2_SMEM, c->stream>>>(c->D, bx, nrhs, nnew, nch, c->D.kpp4); c->launches++; return 0; }

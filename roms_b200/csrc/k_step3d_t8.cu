@@ -763,9 +763,12 @@ int k_step3d_t_v8(roms_b200_ctx* c, int nnew) {
     // (with tensor memory each consumer warp needs its own lane quadrant: warps 1..4)
     int S = 0;
     for (int s = (force_s ? force_s : 6); s >= 2 && !S; --s) if (smem_v8(ntr, tm, N, s) <= (size_t)max_smem) S = s;
-    if (!S || (S < 4 && !force_s)) return 2;       // fewer than 4 slots (N > ~40) cannot overlap load, advection and solve: k_step3d_t6.cu is faster there
+    if (!S || (S < 3 && !force_s)) return 2;       // fewer than 3 slots (N > ~51) cannot overlap load, advection and solve: k_step3d_t6.cu is faster there
+    if (S == 3 && tm != 2 && !force_s) return 2;   // 3 slots need the early slot release of tensor-memory mode 2
     static const int force_nc = getenv("ROMS_B200_S3T_NC") ? atoi(getenv("ROMS_B200_S3T_NC")) : 0;
-    const int NC = force_nc ? force_nc : (S >= 5 ? 3 : (S == 4 ? 2 : 1));      // measured: 3 consumer warps are enough for 8 producer warps
+    // measured: 3 consumer warps are enough for 8 producer warps; with 3 slots (N = 50: 1024x512x50 in 0.88 ms against 1.26 ms
+    // for k_step3d_t6.cu) two consumers work because a slot goes back to the loader after the forward sweep (one consumer: 1.50 ms)
+    const int NC = force_nc ? force_nc : (S >= 5 ? 3 : (S >= 3 ? 2 : 1));
     if (NC > 4 || NC >= S) return 2;
     // producer warps x level-pair batches per warp: NP*KP >= ceil(N/2), at most 16 warps per CTA
     const int nb = (N + 1) / 2;

@@ -388,6 +388,7 @@ int roms_b200_main3d(roms_b200_ctx* c, int nsteps, int analytic_forcing, int wit
     if (two) {
       CUDA_OK(cudaEventRecord(c->ev[1], c->stream)); CUDA_OK(cudaStreamWaitEvent(c->stream2, c->ev[1], 0));
       { OnStream2 on(c);
+        if (bench) { if (k_lmd_vmix_part(c, nstp, 1)) return 1; CUDA_OK(cudaEventRecord(c->ev[5], c->stream)); }   // KPP's spline derivatives: need the density only
         if (with_diag == 1) { double d[3]; if (k_diag(c, nstp, d)) return 1; }      // main3d.F:300 (diag with NINFO=1), host waits
         else if (with_diag) { if (k_diag_begin(c, nstp)) return 1; }                 // reductions + D2H stay asynchronous: the caller
                                                                                      // collects them with roms_b200_diag_end
@@ -402,7 +403,10 @@ int roms_b200_main3d(roms_b200_ctx* c, int nsteps, int analytic_forcing, int wit
     // no halo swap of the stresses (bulk_flux, set_vbc evaluated two points into the halo) nor of Akv (KPP evaluated on the
     // first halo ring; ana_vmix on the whole mirror): ROMS_B200_SWAP_VBC=1 restores the two messages of the reference
     if (swap_vbc) { const XF x[4] = {xf2(FID(sustr)), xf2(FID(svstr)), xf2(FID(bustr)), xf2(FID(bvstr))}; if (xchg(c, x, 4)) return 1; }
-    if (bench) { if (k_lmd_vmix(c, nstp)) return 1; if (swap_vbc) { const XF x[1] = {xf3(c, FID(Akv))}; if (xchg(c, x, 1)) return 1; } } else k_ana_vmix(c);
+    if (bench) {
+      if (two) { CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev[5], 0)); if (k_lmd_vmix_part(c, nstp, 2)) return 1; }
+      else if (k_lmd_vmix(c, nstp)) return 1;
+      if (swap_vbc) { const XF x[1] = {xf3(c, FID(Akv))}; if (xchg(c, x, 1)) return 1; } } else k_ana_vmix(c);
     if (two) CUDA_OK(cudaStreamWaitEvent(c->stream, c->ev[2], 0));              // join A
     else { k_omega(c); if (k_wvelocity(c, nstp)) return 1; }
     k_set_zeta(c);
