@@ -17,6 +17,7 @@
 // neighbours straight into the receivers' mailboxes over NVLink as flag-in-data messages (see below) and unpacks what
 // arrives: no staging, no NCCL proxy, no fences.  The NCCL path above remains as ROMS_B200_HALO_NCCL=1 and for diag's all-reduce.
 #include "common.cuh"
+#include <algorithm>
 #include <dlfcn.h>
 #include <cstring>
 #include <cstdlib>
@@ -115,6 +116,7 @@ __global__ void halo_unpack_kernel(const Dev D, HaloList L, int phase, int w, co
 // instead of hanging the node (the reference sets exit_flag=2, mp_exchange.F:544-553): roms_b200_sync reports it.
 constexpr size_t P2P_HDR = 256;
 constexpr int P2P_NDIR = 8;
+constexpr int P2P_CH = 256;               // elements of a strip per work item (one per thread)
 __host__ __device__ inline int p2p_opp(int d) { return d < 4 ? (d ^ 1) : (11 - d); }     // W<->E, S<->N, SW<->NE, SE<->NW
 struct P2PView { ulonglong2* data; size_t cap; };
 __host__ __device__ inline P2PView p2p_view(void* mem, size_t cap) { return P2PView{(ulonglong2*)((char*)mem + P2P_HDR), cap}; }
@@ -123,6 +125,7 @@ struct P2PArgs {
   void* mine; void* peer[P2P_NDIR];        // my mailbox ; the mailboxes of the 8 neighbours (null: none)
   Rect snd[P2P_NDIR], rcv[P2P_NDIR];       // what I send towards direction d / where the strip arriving from direction d goes
   size_t cap; unsigned long long* seq; unsigned int* ticket;
+  int nsub, ch;                            // chunks per (plane, direction) strip, elements per chunk
 };
 __device__ __forceinline__ void ll_store(ulonglong2* p, double v, unsigned s) {
   const unsigned long long f = (unsigned long long)s << 32;
@@ -147,30 +150,34 @@ __global__ void __launch_bounds__(256) halo_xchg_p2p_kernel(const Dev D, HaloLis
   const unsigned s = (unsigned)s64;
   const int slot = (int)(s & 1u);
   const P2PView me = p2p_view(a.mine, a.cap);
-  const int nitems = L.total_planes * P2P_NDIR;
+  // work items: (plane, direction, chunk of P2P_CH elements of the strip): a 512 x 6 strip handled by one block is a dozen
+  // sequential remote stores and local polls per thread; chunks give every thread one or two
+  const int nsub = a.nsub, nitems = L.total_planes * P2P_NDIR * nsub;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const int d = item % P2P_NDIR, plane = item / P2P_NDIR;
+    const int sub = item % nsub, d = (item / nsub) % P2P_NDIR, plane = item / (nsub * P2P_NDIR);
     void* peer = a.peer[d];
     if (!peer) continue;
+    const Rect r = a.snd[d];
+    const int n = r.w * r.h, x0 = sub * a.ch, x1 = min(x0 + a.ch, n);
+    if (x0 >= n) continue;
     int f = 0, p = plane;
     while (p >= L.nplanes[f]) { p -= L.nplanes[f]; ++f; }
     const double* fld = L.base[f] + (size_t)p * D.nij;
-    const Rect r = a.snd[d];
-    const int n = r.w * r.h;
     ulonglong2* out = p2p_view(peer, a.cap).data + (size_t)(p2p_opp(d) * 2 + slot) * a.cap + (size_t)plane * n;
-    for (int x = threadIdx.x; x < n; x += blockDim.x) ll_store(out + x, fld[r.o + (x % r.w) + (size_t)ni * (x / r.w)], s);
+    for (int x = x0 + threadIdx.x; x < x1; x += blockDim.x) ll_store(out + x, fld[r.o + (x % r.w) + (size_t)ni * (x / r.w)], s);
   }
   bool dead = false;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const int d = item % P2P_NDIR, plane = item / P2P_NDIR;
+    const int sub = item % nsub, d = (item / nsub) % P2P_NDIR, plane = item / (nsub * P2P_NDIR);
     if (!a.peer[d]) continue;
+    const Rect r = a.rcv[d];
+    const int n = r.w * r.h, x0 = sub * a.ch, x1 = min(x0 + a.ch, n);
+    if (x0 >= n) continue;
     int f = 0, p = plane;
     while (p >= L.nplanes[f]) { p -= L.nplanes[f]; ++f; }
     double* fld = L.base[f] + (size_t)p * D.nij;
-    const Rect r = a.rcv[d];
-    const int n = r.w * r.h;
     const ulonglong2* in = me.data + (size_t)(d * 2 + slot) * a.cap + (size_t)plane * n;
-    for (int x = threadIdx.x; x < n; x += blockDim.x) {
+    for (int x = x0 + threadIdx.x; x < x1; x += blockDim.x) {
       double v; unsigned spins = 0; long long t0 = 0;
       while (!ll_load(in + x, s, v)) {
         if (dead) break;
@@ -307,7 +314,12 @@ int halo_exchange(roms_b200_ctx* c, double* const* bases, const int* nplanes, in
     if (!nsm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
     // one block per (plane, direction) item, at most 8 per SM (a single block for the small 2-D swaps was measured much
     // slower: the strip copies are latency-bound and want to run side by side)
-    int nblk = L.total_planes * P2P_NDIR; if (nblk > 8 * nsm) nblk = 8 * nsm;
+    int maxn = 1;
+    for (int q = 0; q < P2P_NDIR; ++q) if (a.peer[q]) { maxn = std::max(maxn, a.snd[q].w * a.snd[q].h); maxn = std::max(maxn, a.rcv[q].w * a.rcv[q].h); }
+    static const int ch_off = getenv("ROMS_B200_HALO_NOCHUNK") != nullptr;
+    static const int ch_env = getenv("ROMS_B200_HALO_CHUNK") ? atoi(getenv("ROMS_B200_HALO_CHUNK")) : P2P_CH;
+    a.ch = ch_off ? maxn : (ch_env > 0 ? ch_env : P2P_CH); a.nsub = (maxn + a.ch - 1) / a.ch;
+    int nblk = L.total_planes * P2P_NDIR * a.nsub; if (nblk > 8 * nsm) nblk = 8 * nsm;
     // Launched as a programmatic dependent of the kernel before it (its launch latency and block scheduling overlap that
     // kernel's tail; it waits in griddepcontrol.wait before touching any field) and releasing the kernel behind it at once
     // (a step2d sub-step, which waits the same way until this exchange has completed).  ROMS_B200_HALO_PDL=0: ordinary launch.
