@@ -34,7 +34,7 @@ python tools/ncu_traffic.py ${G}_v8_b3.ncu-rep 2048x256x30 > /dev/null
   echo; echo "the same loop as a CUDA graph of per-sub-step launches chained by programmatic dependent launch (production):"; grep -h step2d_loop ${G}_phases_b1.log
   echo; echo "first cut of the persistent kernel (body of the per-sub-step kernel unchanged, no early loads, metrics from global memory):"
   grep -h step2d gpurun_out/r2p_phases_b1.log gpurun_out/r2p_phases_b1_graph.log; echo "(first line persistent, second line graph, same build)"; } > profiles/r02_step2d_persistent.txt
-{ echo "bench.py lines of round 2 (commit $H for N=1; multi-GPU lines: tools/r2m.sh, commit 44bd1d0 or later)"; echo "--- N=1"; tail -1 ${G}_bench.log; echo "--- N=1 --impl reference"; tail -1 ${G}_bench_ref.log
-  for f in gpurun_out/r2ae_ROMS_B200_HALO_PDL=1.log gpurun_out/r2af_bench.log; do [ -f $f ] && { echo "--- $f"; grep '"metric"' $f | tail -1; }; done; } > profiles/r02_bench_lines.txt
+{ echo "bench.py lines of round 2 (commit $H for N=1; multi-GPU lines N=2, 4, 8: tools/r2m.sh / tools/r2ai.sh, final build)"; echo "--- N=1"; tail -1 ${G}_bench.log; echo "--- N=1 --impl reference"; tail -1 ${G}_bench_ref.log
+  for f in gpurun_out/fin2b_bench.log gpurun_out/r2ai_X=1.log gpurun_out/fin8b_bench.log; do [ -f $f ] && { echo "--- $f"; grep '"metric"' $f | tail -1; }; done; } > profiles/r02_bench_lines.txt
 git rm -q --cached profiles/r02_multi_gpu_bench_lines.txt 2>/dev/null; rm -f profiles/r02_multi_gpu_bench_lines.txt
 ls -la profiles | grep r02
