@@ -390,8 +390,9 @@ def run_ours_multi(args, rank, world):
         notes = {"tiles": "%dx%d tiles of %dx%d, one per GPU (the N=1 line of this series is BENCHMARK1 512x64x30)" % (nti, ntj, gLm // nti, gMm // ntj),
                 "halo": ("NVLink peer mailboxes (CUDA IPC): one kernel per exchange writes the strips and corner blocks of all 8 neighbours "
                          "into their mailboxes as flag-in-data messages (8-byte words carrying the sequence number, no fences or flags) and polls/unpacks "
-                         "what arrives; mirror halo 6, deep-halo fast loop (one 3-field swap per barotropic sub-step pair), 33 swaps per step; NCCL only "
-                         "for diag's all-reduce; fast loop replayed as a CUDA graph") if os.environ.get("ROMS_B200_HALO_NCCL") is None
+                         "what arrives, strips split into 256-element work items over the blocks, the kernel chained to the sub-steps around it by "
+                         "programmatic dependent launch; mirror halo 6, deep-halo fast loop (one 3-field swap per barotropic sub-step pair), 33 swaps "
+                         "per step; NCCL only for diag's all-reduce; fast loop replayed as a CUDA graph") if os.environ.get("ROMS_B200_HALO_NCCL") is None
                         else "NCCL send/recv (pack kernel, grouped send/recv, unpack kernel), W/E then S/N",
                 "l2": "state 0.3 GB per GPU per step > 126 MB L2, no explicit flush", "fmad": "false (parity build)"}
         line = {"metric": METRIC, "value": cells * args.steps / r["dev_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps,

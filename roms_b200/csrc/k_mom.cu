@@ -415,11 +415,10 @@ int k_rhs3d_tile(roms_b200_ctx* c, int nrhs) {
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend};
   static const bool per_level = (getenv("ROMS_B200_RHS3D_PERLEVEL") != nullptr);        // the first form
   if (!per_level) {
-    static bool attr = false;
-    if (!attr) {
+    static AttrOnce attr;
+    if (attr.need(R2_SMEM)) {
       CUDA_OK(cudaFuncSetAttribute(rhs3d_roll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM));
       CUDA_OK(cudaFuncSetAttribute(rhs3d_roll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R2_SMEM));
-      attr = true;
     }
     dim3 blk(R2_TX, R2_TY); dim3 g = grid2(bx, blk);
     const long cols = (long)g.x * g.y;
@@ -642,11 +641,10 @@ int k_uv3dmix2(roms_b200_ctx* c, int nrhs, int nnew) {
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend};
   static const bool per_level = (getenv("ROMS_B200_UVMIX_PERLEVEL") != nullptr);        // the first form
   if (!per_level) {
-    static bool attr = false;
-    if (!attr) {
+    static AttrOnce attr;
+    if (attr.need(M2_SMEM)) {
       CUDA_OK(cudaFuncSetAttribute(uv3dmix2_roll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M2_SMEM));
       CUDA_OK(cudaFuncSetAttribute(uv3dmix2_roll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M2_SMEM));
-      attr = true;
     }
     dim3 blk(M2_TX, M2_TY); dim3 g = grid2(bx, blk);
     const long cols = (long)g.x * g.y;
@@ -826,9 +824,9 @@ int k_step3d_uv(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int ntf
   double cffab;
   if (iic == ntfirst) cffab = 0.25 * dt; else if (iic == ntfirst + 1) cffab = 0.25 * dt * 3.0 / 2.0; else cffab = 0.25 * dt * 23.0 / 12.0;
   const size_t sm1 = (size_t)6 * (b.N + 2) * UV_T * sizeof(double), sm2 = (size_t)3 * (b.N + 2) * UV_T * sizeof(double);
-  static size_t set1 = 0, set2 = 0;
-  if (sm1 > set1) { CUDA_OK(cudaFuncSetAttribute(step3d_uv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1)); set1 = sm1; }
-  if (sm2 > set2) { CUDA_OK(cudaFuncSetAttribute(step3d_uv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2)); set2 = sm2; }
+  static AttrOnce set1, set2;
+  if (set1.need(sm1)) CUDA_OK(cudaFuncSetAttribute(step3d_uv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+  if (set2.need(sm2)) CUDA_OK(cudaFuncSetAttribute(step3d_uv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, UV_T / 32);
   dim3 g1 = grid2(bx, blk); g1.z = 2;
   step3d_uv1_kernel<<<g1, blk, sm1, c->stream>>>(c->D, bx, nrhs, nnew, cffab); c->launches++;

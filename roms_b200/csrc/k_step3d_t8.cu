@@ -712,8 +712,8 @@ int make_map(TMap* m, const double* base, int ni, int nj, int nk, int bw, int bk
 
 template <int NTR, int KP, int TM, int MAXT>
 int launch_v8_t(roms_b200_ctx* c, const A8& a, int grid, size_t smem) {
-  static size_t set = 0;
-  if (smem > set) { CUDA_OK(cudaFuncSetAttribute(step3d_t_v8_kernel<NTR, KP, TM, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = smem; }
+  static AttrOnce set;
+  if (set.need(smem)) CUDA_OK(cudaFuncSetAttribute(step3d_t_v8_kernel<NTR, KP, TM, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   step3d_t_v8_kernel<NTR, KP, TM, MAXT><<<dim3(grid), dim3(32 * (1 + a.NC + a.NP)), smem, c->stream>>>(a);
   return 0;
 }

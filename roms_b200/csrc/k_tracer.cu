@@ -378,8 +378,8 @@ int k_pre_step3d_t(roms_b200_ctx* c, int nrhs, int nstp, int nnew, int iic, int 
   Box bx{b.Istr, b.Iend, b.Jstr, b.Jend}; dim3 blk(32, 8); dim3 g = grid2(bx, blk); g.z = b.NT * b.N;
   static const bool per_level = (getenv("ROMS_B200_PRE3D_PERLEVEL") != nullptr);      // the first form
   if (!per_level) {
-    static bool attr = false;
-    if (!attr) { CUDA_OK(cudaFuncSetAttribute(pre_step3d_t_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM)); attr = true; }
+    static AttrOnce attr;
+    if (attr.need(P2_SMEM)) CUDA_OK(cudaFuncSetAttribute(pre_step3d_t_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM));
     dim3 blk2(P2_TX, P2_TY); dim3 g2 = grid2(bx, blk2);
     const long cols = (long)g2.x * g2.y * b.NT;
     static const int waves = getenv("ROMS_B200_PRE3D_FILL") ? atoi(getenv("ROMS_B200_PRE3D_FILL")) : 1;
@@ -689,12 +689,11 @@ int k_t3dmix2(roms_b200_ctx* c, int nrhs, int nstp, int nnew) {
       int nch = (int)std::min<long>(((long)waves * 148 + cols - 1) / cols, (b.N + 4) / 5); if (nch < 1) nch = 1;
       g2.z = b.NT * nch;
       static const int minb = getenv("ROMS_B200_T3DMIX_MINB") ? atoi(getenv("ROMS_B200_T3DMIX_MINB")) : 2;
-      static bool attr = false;
-      if (!attr) {
+      static AttrOnce attr;
+      if (attr.need(G2_SMEM)) {
         CUDA_OK(cudaFuncSetAttribute(t3dmix2_geo_roll_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
         CUDA_OK(cudaFuncSetAttribute(t3dmix2_geo_roll_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
         CUDA_OK(cudaFuncSetAttribute(t3dmix2_geo_roll_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
-        attr = true;
       }
       if (minb == 4) t3dmix2_geo_roll_kernel<4><<<g2, blk2, G2_SMEM, c->stream>>>(c->D, bx, nrhs, nnew, nch);
       else if (minb == 3) t3dmix2_geo_roll_kernel<3><<<g2, blk2, G2_SMEM, c->stream>>>(c->D, bx, nrhs, nnew, nch);
