@@ -23,7 +23,7 @@ PY
   echo "(stalls = warps stalled for that reason per issued instruction).  Round-2 kernels (tools/r2_evidence.sh, commit $H):"
   python tools/ncu_table.py ${G}_t3dmix2_geo_roll_kernel.ncu-rep ${G}_pre_step3d_t_roll_kernel.ncu-rep ${G}_uv3dmix2_roll_kernel.ncu-rep ${G}_rhs3d_roll_kernel.ncu-rep ${G}_pre_step3d_uv_march_kernel.ncu-rep ${G}_step2d_kernel.ncu-rep ${G}_v8_b3.ncu-rep
   echo "step2d on BENCHMARK1 (512x64):"; python tools/ncu_table.py ${G}_step2d_b1.ncu-rep
-  echo; echo "Per-level (round-1 form) kernels and the kernels not yet restructured (tools/r2s.sh, commit 9e8b9c4; this capture is what motivated the marching kernels):"
+  echo; echo "Per-level (round-1 form) kernels and the kernels not yet restructured (tools/ncu_kernels.sh, commit 9e8b9c4; this capture is what motivated the marching kernels):"
   python tools/ncu_table.py gpurun_out/r2s_*.ncu-rep
   echo; echo "pre_step3d_t_kernel (per-level form): L1 -> L2 read sectors 210 M (6.7 GB), DRAM read 148 M sectors (4.75 GB) for 1.5 GB of operands; long-scoreboard 10.5 stalled warps per issue, 7.3 warps per scheduler."
 } > profiles/r02_ncu_kernels_2048x256x30.txt 2>&1
@@ -34,7 +34,7 @@ python tools/ncu_traffic.py ${G}_v8_b3.ncu-rep 2048x256x30 > /dev/null
   echo; echo "the same loop as a CUDA graph of per-sub-step launches chained by programmatic dependent launch (production):"; grep -h step2d_loop ${G}_phases_b1.log
   echo; echo "first cut of the persistent kernel (body of the per-sub-step kernel unchanged, no early loads, metrics from global memory):"
   grep -h step2d gpurun_out/r2p_phases_b1.log gpurun_out/r2p_phases_b1_graph.log; echo "(first line persistent, second line graph, same build)"; } > profiles/r02_step2d_persistent.txt
-{ echo "bench.py lines of round 2 (commit $H for N=1; multi-GPU lines N=2, 4, 8: tools/r2m.sh / tools/r2ai.sh, final build)"; echo "--- N=1"; tail -1 ${G}_bench.log; echo "--- N=1 --impl reference"; tail -1 ${G}_bench_ref.log
+{ echo "bench.py lines of round 2 (commit $H for N=1; multi-GPU lines N=2, 4, 8: tools/mgpu_bench.sh / tools/mgpu_ab.sh, final build)"; echo "--- N=1"; tail -1 ${G}_bench.log; echo "--- N=1 --impl reference"; tail -1 ${G}_bench_ref.log
   for f in gpurun_out/fin2b_bench.log gpurun_out/r2ai_X=1.log gpurun_out/fin8b_bench.log; do [ -f $f ] && { echo "--- $f"; grep '"metric"' $f | tail -1; }; done; } > profiles/r02_bench_lines.txt
 git rm -q --cached profiles/r02_multi_gpu_bench_lines.txt 2>/dev/null; rm -f profiles/r02_multi_gpu_bench_lines.txt
 ls -la profiles | grep r02

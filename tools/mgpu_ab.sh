@@ -1,5 +1,5 @@
 #!/bin/bash
-# tools/r2ai.sh TAG N -- N GPUs: halo strips chunked over blocks against one block per strip
+# tools/mgpu_ab.sh TAG N -- N GPUs: halo strips chunked over blocks against one block per strip
 mkdir -p gpurun_out; O=gpurun_out/$1; N=$2
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 for e in $EVS; do

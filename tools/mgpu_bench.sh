@@ -1,5 +1,5 @@
 #!/bin/bash
-# tools/r2m.sh TAG NGPU [extra bench args] -- multi-GPU: tiling check tool + bench line on NGPU GPUs of one box
+# tools/mgpu_bench.sh TAG NGPU [extra bench args] -- multi-GPU: tiling check tool + bench line on NGPU GPUs of one box
 mkdir -p gpurun_out; O=gpurun_out/$1; N=$2; shift; shift
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 case $N in 2) TI="2 1";; 4) TI="2 2";; 8) TI="4 2";; esac

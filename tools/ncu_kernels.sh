@@ -1,5 +1,5 @@
 #!/bin/bash
-# tools/r2s.sh TAG -- ncu --set full of one warm launch of every mid-fraction kernel on the BENCHMARK3 grid (2048x256x30), step2d included
+# tools/ncu_kernels.sh TAG -- ncu --set full of one warm launch of every mid-fraction kernel on the BENCHMARK3 grid (2048x256x30), step2d included
 mkdir -p gpurun_out; O=gpurun_out/$1
 for k in step2d_kernel rhs3d_kernel rhs3d_sum_kernel uv3dmix2_kernel uv3dmix2_sum_kernel geo_dTdz_kernel t3dmix2_geo_kernel prsgrd_T_kernel prsgrd_P_kernel prsgrd_ruv_kernel pre_step3d_t_kernel pre_step3d_uv_kernel step3d_uv1_kernel step3d_uv2_kernel kpp_levels_kernel kpp_spline_kernel; do
   s=4; [ $k = step2d_kernel ] && s=300
