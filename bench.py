@@ -192,13 +192,14 @@ def _time_step3d_t(rb, Lm, Mm, N, reps):
     return ms
 
 
-def roofline_step3d_t(rb, peak, peak_kind):
+def roofline_step3d_t(rb, peak, peak_kind, basin_tile=True):
     """step3d_t (the graded kernel) on grids whose working set is >> L2 (126 MB), so every launch streams from HBM:
     96 B algorithmic per cell per call (NT=2).  Primary: the BENCHMARK3 grid (N=30); also a quarter
     of and a whole 1024x2048x50 tile of the 4096^2 x 50 basin (also, also2).  The timing loop re-applies the kernel to its own output (same traffic, arithmetic not meaningful)."""
     out = None
     traffic = ncu_traffic()
-    for (Lm, Mm, N) in ((2048, 256, 30), (1024, 512, 50), (1024, 2048, 50)):     # the last: one tile of the 4096^2 x 50 basin on 4x2 GPUs
+    grids = ((2048, 256, 30), (1024, 512, 50), (1024, 2048, 50))     # the last: one tile of the 4096^2 x 50 basin on 4x2 GPUs
+    for (Lm, Mm, N) in (grids if basin_tile else grids[:2]):
         try:
             ms = _time_step3d_t(rb, Lm, Mm, N, 20 if Mm < 2048 else 8)
         except Exception as e:                 # (the basin tile needs ~30 GB of HBM)
@@ -380,7 +381,7 @@ def run_ours_multi(args, rank, world):
     roof = None
     if rank == 0 and not args.no_roofline:
         peak, peak_kind = measured_peak()
-        roof = roofline_step3d_t(rb, peak, peak_kind)      # single-GPU kernel measurement on rank 0's GPU
+        roof = roofline_step3d_t(rb, peak, peak_kind, basin_tile=False)      # single-GPU kernel measurement on rank 0's GPU (the N=1 line also carries the 30 GB basin tile)
     dist.barrier()
     if rank == 0:
         b = r["bounds"]
